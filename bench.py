@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Headline benchmark: masked-voxel T2 fits per second (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] -- adult-brain 256x256x256 x 5 TE, ellipsoid
+brain mask (~1.6 M masked voxels), 2-parameter mono-exponential fit, LF preset, --no_prior.
+One *step* = the whole hot block of process_t2maps for one such volume (run_t2mapping.py:411-461):
+zero the four dense maps, fit every masked voxel, residual epilogue, scatter into the dense maps,
+plus convergence flags / iteration counts / final errors per voxel.
+
+  value     whole-job fits/s with the volume already resident in HBM (AoS [N,E] float32 + mask_indices)
+  e2e       same metric through fit_voxels_batch() with HOST numpy buffers: pack, H2D, fit, D2H inside
+  roofline  the fit kernel alone, CUDA events around each launch inside the timed region
+  cpu_baseline  the oracle port (scipy L-BFGS-B exactly as the reference drives it) on a bounded sample
+N > 1: weak scaling, one volume-sized slab of masked voxels per rank, no data-path collective; the
+final NCCL gather of the parameter maps is timed separately ("final_gather").
+
+--impl reference: the reference's own CPU implementation of the path (oracle port: scipy.optimize
+L-BFGS-B + multiprocessing over all host cores), each step a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "c2: 256x256x256 x 5 TE adult-brain, ellipsoid mask, gaussian 2-param fit, LF preset, --no_prior"
+METRIC = "masked_voxel_T2_fits_per_sec"
+UNIT = "fits/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "sm_max_mhz": float(d.get("sm_max_mhz", 1965.0)), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def make_workload(rank):
+    from fetal_t2mapping_b200 import synth
+    y, mask, te, _ = synth.make_volume("c2", scale=float(os.environ.get("T2FIT_BENCH_SCALE", "1.0")), volume_index=rank)
+    flat = np.ascontiguousarray(y.reshape(-1, te.size))
+    idx = np.flatnonzero(mask.reshape(-1)).astype(np.int64)
+    return flat, idx, te
+
+
+def cpu_sample(flat, idx, te, fp, n, seed=11):
+    rng = np.random.default_rng(seed)
+    pick = np.sort(rng.choice(idx, size=min(n, idx.size), replace=False))
+    return np.ascontiguousarray(flat[pick])
+
+
+def time_oracle(rows, te, fp, procs):
+    from oracle import fit_oracle as fo
+    t0 = time.perf_counter()
+    p, ok, nit, fun, _ = fo.fit_rows_oracle(rows, te, "gaussian", fp, False, False, mode="verbatim", procs=procs)
+    dt = time.perf_counter() - t0
+    return rows.shape[0] / dt, dt, p, ok
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference arm: scipy L-BFGS-B driven exactly as fit_voxel drives it, Pool over all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import fit_oracle as fo
+    _, fp = fo.preset("gaussian", "lf")
+    flat, idx, te = make_workload(0)
+    procs = os.cpu_count() or 1
+    probe = cpu_sample(flat, idx, te, fp, 256 * min(procs, 8), seed=5)
+    rate, _, _, _ = time_oracle(probe, te, fp, procs)
+    budget_s = float(os.environ.get("T2FIT_REF_BUDGET_S", "100"))
+    per_step = int(np.clip(budget_s * rate / max(1, args.steps + args.warmup), 256, 20000))
+    for w in range(args.warmup):
+        time_oracle(cpu_sample(flat, idx, te, fp, per_step, seed=100 + w), te, fp, procs)
+    t_tot, n_tot = 0.0, 0
+    for s in range(args.steps):
+        rows = cpu_sample(flat, idx, te, fp, per_step, seed=200 + s)
+        _, dt, _, _ = time_oracle(rows, te, fp, procs)
+        t_tot += dt
+        n_tot += rows.shape[0]
+    value = n_tot / t_tot
+    import scipy
+    sample = f"{per_step} masked voxels per step (seeded random sample of the {idx.size}-voxel mask), {args.steps} steps"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "masked_voxels": int(idx.size), "sample": sample,
+                       "scipy": scipy.__version__, "numpy": np.__version__},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # CPU baseline first: multiprocessing fork must happen before CUDA is initialised in this process
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import fit_oracle as fo
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+        os.environ.setdefault("OMP_NUM_THREADS", "1")
+        _, fp0 = fo.preset("gaussian", "lf")
+        flat0, idx0, te0 = make_workload(0)
+        procs = os.cpu_count() or 1
+        n_s = int(os.environ.get("T2FIT_CPU_SAMPLE", "12000"))
+        rows = cpu_sample(flat0, idx0, te0, fp0, n_s)
+        rate, dt, _, _ = time_oracle(rows, te0, fp0, procs)
+        import scipy
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
+                        "sample": f"{rows.shape[0]} seeded random masked voxels of the same volume, {dt:.1f} s, "
+                                  f"scipy {scipy.__version__} L-BFGS-B via multiprocessing.Pool({procs})"}
+        del flat0, idx0, rows
+    import torch
+    import torch.distributed as dist
+    import fetal_t2mapping_b200 as t2
+    from fetal_t2mapping_b200 import _abi
+    import ctypes as C
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = t2.init(local)
+    _, fp = t2.preset("gaussian", True)
+
+    flat, idx, te = make_workload(rank)
+    n_vox, n_echo = flat.shape
+    m = idx.size
+    y_d = torch.from_numpy(flat).to(dev)
+    idx_d = torch.from_numpy(idx).to(dev)
+    maps = torch.zeros((4, n_vox), dtype=torch.float32, device=dev)
+    fun_d = torch.empty(m, dtype=torch.float32, device=dev)
+    nit_d = torch.empty(m, dtype=torch.int32, device=dev)
+    st_d = torch.empty(m, dtype=torch.uint8, device=dev)
+
+    p, o = _abi.Problem(), _abi.Outputs()
+    from fetal_t2mapping_b200.api import _fill_problem
+    keep = _fill_problem(p, "gaussian", fp, te, False, False, 0, 0.0, "loglinear")
+    p.echoes, p.memory, p.layout, p.mask_idx = y_d.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_AOS, idx_d.data_ptr()
+    p.n_vox, p.n_fit = n_vox, m
+    o.t2, o.k, o.sigma, o.res = maps[0].data_ptr(), maps[1].data_ptr(), None, maps[3].data_ptr()
+    o.fun, o.nit, o.status, o.dense = fun_d.data_ptr(), nit_d.data_ptr(), st_d.data_ptr(), 1
+    stream = torch.cuda.current_stream(dev)
+
+    def step(ev=None):
+        maps.zero_()                                   # np.zeros_like x4 (run_t2mapping.py:415-418)
+        if ev is not None:
+            ev[0].record(stream)
+        rc = lib.t2fit_run(C.byref(p), C.byref(o), stream.cuda_stream)
+        if ev is not None:
+            ev[1].record(stream)
+        if rc:
+            raise RuntimeError(lib.t2fit_last_error())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record(stream)
+    for s in range(args.steps):
+        step(evs[s])
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    elapsed_ms = t_start.elapsed_time(t_end)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    if world > 1:
+        t = torch.tensor([elapsed_ms, kern_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, kern_ms = float(t[0]), float(t[1])
+        tot = torch.tensor([m], device=dev, dtype=torch.int64)
+        dist.all_reduce(tot)
+        m_total = int(tot[0])
+    else:
+        m_total = m
+    value = m_total * args.steps / (elapsed_ms * 1e-3)
+
+    # sanity of the timed result + work actually done (passes per voxel) for the roofline numerator
+    nit = nit_d.cpu().numpy().astype(np.int64)
+    status = st_d.cpu().numpy()
+    assert (status == 0).all(), "bench workload produced failed voxels"
+    t2v = maps[0][idx_d].cpu().numpy()
+    assert np.isfinite(t2v).all() and t2v.min() >= 10 and t2v.max() <= 2000
+    wm = t2.work_model("gaussian", n_echo)
+    passes = nit + 1                                    # iterations + the verifying pass
+    flops_launch = float((wm["flop_fixed"] + wm["flop_per_pass"] * passes).sum())
+    mufu_launch = float((wm["mufu_fixed"] + wm["mufu_per_pass"] * passes).sum())
+    bytes_launch = float(m) * (wm["bytes_per_voxel"] + 8 + 4 + 4)       # + int64 index, nit, fun
+    peaks = measured_peaks()
+    info = t2.device_info()
+    fp32_peak = info["sm_count"] * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12      # TFLOP/s at max clock
+    mufu_peak = info["sm_count"] * 16 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    ach_tf = flops_launch / (kern_ms * 1e-3) / 1e12
+    ach_gbs = bytes_launch / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tp):
+        traffic = json.load(open(tp)).get("fit_kernel_dram_bytes_per_launch")
+    roof_fp32 = {"bound": "fp32", "achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
+                 "traffic": traffic, "peak_src": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peaks['src']} clocks)",
+                 "mufu_frac": mufu_launch / (kern_ms * 1e-3) / 1e12 / mufu_peak,
+                 "passes_per_voxel": float(passes.mean()), "flop_per_voxel": flops_launch / m}
+    roof_hbm = {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_src": peaks["src"]}
+    roofline = dict(roof_fp32 if roof_fp32["frac"] >= roof_hbm["frac"] else roof_hbm)
+    roofline["kernel"] = "fit_kernel<mono2,E=5,AoS>"
+    roofline["kernel_ms"] = kern_ms
+
+    # end to end through the public API with host buffers (numpy in, numpy out)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        r = t2.fit_voxels_batch(flat, idx, te, "gaussian", fp, prior=False, norm=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r = t2.fit_voxels_batch(flat, idx, te, "gaussian", fp, prior=False, norm=False)
+        _ = float(r.res[0])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    assert np.array_equal(r.t2, t2v), "e2e path and device path disagree"
+    e2e = {"value": m_total * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(m * n_echo * 4),
+           "d2h_bytes_per_step": int(m * (4 * 4 + 4 + 1)), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps}
+
+    # final gather of the parameter maps (north_star: the only inter-GPU traffic), timed on its own
+    final_gather = None
+    if world > 1:
+        loc = torch.stack([maps[0][idx_d], maps[1][idx_d], maps[3][idx_d]]).contiguous()
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        sizes[rank] = m
+        dist.all_reduce(sizes)
+        mx = int(sizes.max())
+        pad = torch.zeros((3, mx), dtype=torch.float32, device=dev)
+        pad[:, :m] = loc
+        out = torch.empty((world, 3, mx), dtype=torch.float32, device=dev)
+        for _ in range(3):
+            dist.all_gather_into_tensor(out, pad)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        dist.all_gather_into_tensor(out, pad)
+        g1.record(stream)
+        barrier()
+        gms = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        final_gather = {"op": "nccl all_gather of (t2,k,res) slabs", "ms": float(gms[0]),
+                        "bytes_per_rank": int(3 * mx * 4), "checksum_ok": bool(torch.equal(out[rank, :, :m], loc))}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "masked_voxels_per_gpu": int(m), "volume_voxels_per_gpu": int(n_vox),
+                           "n_echo": int(n_echo), "l2": "inputs+outputs per step (603 MB) exceed the 126 MB L2",
+                           "partition": f"weak: one volume-sized slab per rank x {world}", "gather": "none in the timed step"},
+                "roofline": roofline, "roofline_fp32": roof_fp32, "roofline_hbm": roof_hbm, "cpu_baseline": cpu_baseline,
+                "e2e": e2e, "gpu_launches": int(args.steps), "clocks": clocks, "final_gather": final_gather,
+                "device": info["name"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    del keep
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,361 @@
+"""Host-side mirror of the reference's fit block, over the libt2fit C ABI.
+
+Drop-in for the call pair inside ``process_t2maps`` (run_t2mapping.py:430-461)::
+
+    all_results = pool.map(partial(fit_voxel, fit=, fit_params=, TEeffs=, reshaped_t2w=, prior=, norm=), mask_indices)
+    res_map     = compute_residuals(reshaped_t2w, TEeffs, fit, norm, k_map, t2_map, sigma_map, res_map, mask_indices, mask)
+
+``fit_voxels_batch`` takes exactly those arguments (same names, same meaning) and returns the
+same information for every masked voxel at once; ``t2map_volume`` wraps the whole hot block
+(mask union, flatten, fit, scatter, residual map; :383-386, :411-461, :471-473).
+
+numpy arrays are treated as host memory (the library stages them through pinned buffers);
+torch CUDA tensors are treated as device memory (zero-copy, asynchronous on the current torch
+stream).  The fit itself only exists as sm_100a CUDA kernels: without the built library or
+without a GPU these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi
+from .presets import NO_PRIOR_K_UB, NO_PRIOR_T2_BOUNDS
+
+__all__ = ["fit_voxels_batch", "t2map_volume", "compute_residuals", "FitResult", "init", "shutdown", "device_info",
+           "mask_indices_device", "work_model", "BOUNDS_ERROR"]
+
+BOUNDS_ERROR = "An upper bound is less than the corresponding lower bound."   # scipy's text
+
+_state = {"device": None}
+
+
+def init(device: int | None = None):
+    """Bind this process to one GPU (default: LOCAL_RANK, else torch's current device, else 0)."""
+    lib = _abi.load_library()
+    if device is None:
+        if _state["device"] is not None:
+            return lib
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if _state["device"] == device:
+        return lib
+    _abi.check(lib, lib.t2fit_init(int(device)), "t2fit_init")
+    _state["device"] = int(device)
+    return lib
+
+
+def shutdown():
+    if _state["device"] is not None:
+        _abi.load_library().t2fit_shutdown()
+        _state["device"] = None
+
+
+def device_info():
+    lib = init()
+    name = C.create_string_buffer(256)
+    sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+    _abi.check(lib, lib.t2fit_device_info(name, 256, C.byref(sm), C.byref(maj), C.byref(mnr)), "t2fit_device_info")
+    return {"name": name.value.decode(), "sm_count": sm.value, "cc": (maj.value, mnr.value), "device": _state["device"]}
+
+
+def work_model(fit: str, n_echo: int):
+    """Algorithmic work of the shipped kernel per voxel (roofline accounting)."""
+    lib = _abi.load_library()
+    v = [C.c_double() for _ in range(5)]
+    _abi.check(lib, lib.t2fit_work_model(_abi.MODELS[fit], n_echo, *[C.byref(x) for x in v]), "t2fit_work_model")
+    keys = ("flop_per_pass", "mufu_per_pass", "flop_fixed", "mufu_fixed", "bytes_per_voxel")
+    return {k: x.value for k, x in zip(keys, v)}
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+@dataclass
+class FitResult:
+    """Everything ``pool.map(fit_voxel)`` + ``compute_residuals`` produce, for all masked voxels.
+
+    ``results``            f64[M,P] in the reference order (k, T2[, sigma])       (:449)
+    ``convergence_flags``  bool[M]   == ``result.success``                        (:450)
+    ``num_iterations``     int32[M]  passes of the CUDA solver (not L-BFGS-B's)   (:451)
+    ``final_errors``       f64[M]    mean squared error at the solution           (:452)
+    ``res``                f32[M]    signed mean residual (compute_residuals)     (:461)
+    ``status``             uint8[M]  0 ok / 1 non-finite input / 2 iteration cap / 3 bad bounds
+    ``iteration_infos``    always ``[]`` per voxel: traces exist only for sampled voxels
+    For device calls the float fields are torch CUDA tensors (float32).
+    """
+    t2: object
+    k: object
+    sigma: object
+    res: object
+    fun: object
+    nit: object
+    status: object
+    fit: str
+    status_count: tuple = (0, 0, 0, 0)
+
+    @property
+    def results(self):
+        cols = [self.k, self.t2] + ([self.sigma] if self.fit != "gaussian" else [])
+        if _is_torch(self.k):
+            import torch
+            return torch.stack(cols, dim=1).double()
+        return np.stack(cols, axis=1).astype(np.float64)
+
+    @property
+    def convergence_flags(self):
+        return self.status == 0
+
+    @property
+    def num_iterations(self):
+        return self.nit
+
+    @property
+    def final_errors(self):
+        return self.fun.double() if _is_torch(self.fun) else self.fun.astype(np.float64)
+
+    def as_all_results(self):
+        """The list ``pool.map`` returned: one ``(params, success, nit, fun, iteration_info)`` per voxel."""
+        r = self.results.cpu().numpy() if _is_torch(self.k) else self.results
+        ok = np.asarray(self.convergence_flags.cpu() if _is_torch(self.status) else self.convergence_flags)
+        nit = np.asarray(self.nit.cpu() if _is_torch(self.nit) else self.nit)
+        fun = np.asarray(self.final_errors.cpu() if _is_torch(self.fun) else self.final_errors)
+        return [(r[i], bool(ok[i]), int(nit[i]), float(fun[i]), []) for i in range(r.shape[0])]
+
+
+def _fill_problem(p, fit, fit_params, TEeffs, prior, norm, max_iter, tol, init_mode):
+    if fit == "rician":
+        raise NotImplementedError("fit='rician' (Rician NLL, run_t2mapping.py:157-177) is not implemented on the GPU path")
+    if fit not in _abi.MODELS:
+        raise ValueError(f"unknown fit {fit!r}")
+    x0 = list(fit_params["initial_guess"])
+    bounds = list(fit_params["param_bounds"])
+    npar = 2 if fit == "gaussian" else 3
+    if len(x0) != npar:
+        raise ValueError(f"fit {fit!r} takes {npar} parameters, initial_guess has {len(x0)}")
+    if len(bounds) != len(x0):
+        raise ValueError("The number of bounds is not compatible with the length of `x0`.")   # scipy's text
+    te = np.ascontiguousarray(np.asarray(TEeffs, dtype=np.float64).reshape(-1))
+    p.n_echo = te.size
+    p.te_ms = te.ctypes.data_as(C.POINTER(C.c_double))
+    p.model = _abi.MODELS[fit]
+    for i in range(npar):
+        lo, hi = bounds[i]
+        p.x0[i] = float(x0[i])
+        p.lb[i] = -np.inf if lo is None else float(lo)
+        p.ub[i] = np.inf if hi is None else float(hi)
+    p.no_prior = 0 if prior else 1
+    p.no_prior_k_ub = NO_PRIOR_K_UB
+    p.no_prior_t2_lb, p.no_prior_t2_ub = NO_PRIOR_T2_BOUNDS
+    p.norm = int(bool(norm))
+    p.max_iter = int(max_iter)
+    p.tol = float(tol)
+    p.init = {"loglinear": _abi.INIT_LOGLINEAR, "preset": _abi.INIT_PRESET}[init_mode]
+    return te      # keep alive
+
+
+def _run(lib, p, o, stream):
+    rc = lib.t2fit_run(C.byref(p), C.byref(o), stream)
+    if rc != 0:
+        msg = (lib.t2fit_last_error() or b"").decode()
+        if rc == -1 and "upper bound" in msg:
+            raise ValueError(msg)
+        raise _abi.T2FitError(f"t2fit_run: {_abi.ERRORS.get(rc, rc)}: {msg}")
+
+
+def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=True, norm=False, *,
+                     max_iter=0, tol=0.0, init_mode="loglinear", check_bounds=True, dense_out=None,
+                     want=("nit", "fun", "status")) -> FitResult:
+    """Fit every voxel ``mask_indices[i]`` of ``reshaped_t2w`` (float32 ``[N, E]``, run_t2mapping.py:411).
+
+    Arguments as ``fit_voxel`` (run_t2mapping.py:120): ``fit`` in {'gaussian','gaussian_rician'},
+    ``fit_params`` the preset dict (``initial_guess``, ``param_bounds``), ``prior`` False =
+    ``--no_prior`` per-voxel bounds (:243-245), ``norm`` row-max normalisation (:237-240).
+    ``mask_indices`` None fits all rows.  Raises ``ValueError`` where scipy would (bounds with
+    lb > ub, including any masked voxel with S(TE0) > 10000 under ``--no_prior``).
+    """
+    lib = init()
+    p, o = _abi.Problem(), _abi.Outputs()
+    keep = [_fill_problem(p, fit, fit_params, TEeffs, prior, norm, max_iter, tol, init_mode)]
+    dev = _is_torch(reshaped_t2w)
+    if dev:
+        import torch
+        y = reshaped_t2w
+        if not y.is_cuda or y.dtype != torch.float32 or not y.is_contiguous() or y.dim() != 2:
+            raise ValueError("device input must be a contiguous float32 CUDA tensor [N, E]")
+        if y.device.index != _state["device"]:
+            raise ValueError(f"tensor on cuda:{y.device.index}, library bound to cuda:{_state['device']}")
+        n_vox, n_echo = y.shape
+        idx = mask_indices
+        if idx is not None:
+            if not _is_torch(idx):
+                idx = torch.as_tensor(np.ascontiguousarray(idx, dtype=np.int64), device=y.device)
+            if idx.dtype != torch.int64 or not idx.is_contiguous():
+                idx = idx.to(torch.int64).contiguous()
+        m = n_vox if idx is None else idx.numel()
+
+        def alloc(dt=torch.float32):
+            return torch.empty(m, dtype=dt, device=y.device)
+        out = {"t2": alloc(), "k": alloc(), "res": alloc(),
+               "sigma": alloc() if fit != "gaussian" else torch.zeros(m, dtype=torch.float32, device=y.device),
+               "fun": alloc() if "fun" in want else None,
+               "nit": alloc(torch.int32) if "nit" in want else None,
+               "status": alloc(torch.uint8) if "status" in want else None}
+        p.echoes, p.memory = y.data_ptr(), _abi.MEM_DEVICE
+        p.mask_idx = idx.data_ptr() if idx is not None else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        stream = torch.cuda.current_stream(y.device).cuda_stream
+        keep += [y, idx]
+    else:
+        y = np.asarray(reshaped_t2w)
+        if y.dtype != np.float32 or not y.flags.c_contiguous:
+            y = np.ascontiguousarray(y, dtype=np.float32)           # .astype(np.float32) of :411
+        if y.ndim != 2:
+            raise ValueError("reshaped_t2w must be [N, E]")
+        n_vox, n_echo = y.shape
+        idx = None if mask_indices is None else np.ascontiguousarray(mask_indices, dtype=np.int64)
+        m = n_vox if idx is None else idx.size
+        if idx is not None and m and (idx.min() < 0 or idx.max() >= n_vox):
+            raise IndexError("mask_indices out of range")
+        out = {"t2": np.empty(m, np.float32), "k": np.empty(m, np.float32), "res": np.empty(m, np.float32),
+               "sigma": np.empty(m, np.float32) if fit != "gaussian" else np.zeros(m, np.float32),
+               "fun": np.empty(m, np.float32) if "fun" in want else None,
+               "nit": np.empty(m, np.int32) if "nit" in want else None,
+               "status": np.empty(m, np.uint8) if "status" in want else None}
+        p.echoes, p.memory = y.ctypes.data, _abi.MEM_HOST
+        p.mask_idx = idx.ctypes.data if idx is not None else None
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        stream = None
+        keep += [y, idx]
+    if n_echo != p.n_echo:
+        raise ValueError(f"reshaped_t2w has {n_echo} echoes, TEeffs has {p.n_echo}")
+    p.layout, p.ld, p.n_vox, p.n_fit = _abi.LAYOUT_AOS, 0, n_vox, m
+    o.t2, o.k, o.res = ptr(out["t2"]), ptr(out["k"]), ptr(out["res"])
+    o.sigma = ptr(out["sigma"]) if fit != "gaussian" else None
+    o.fun, o.nit, o.status = ptr(out["fun"]), ptr(out["nit"]), ptr(out["status"])
+    o.dense = 0
+    _run(lib, p, o, stream)
+    if dev:
+        counts = None
+        if check_bounds:
+            cnt = (C.c_int64 * 4)()
+            _abi.check(lib, lib.t2fit_status_counts(stream, cnt), "t2fit_status_counts")
+            counts = (m - cnt[1] - cnt[2] - cnt[3], cnt[1], cnt[2], cnt[3])
+    else:
+        counts = tuple(o.status_count)
+    if counts is not None and counts[3] > 0:
+        # scipy raises inside the first such voxel and the reference's pool.map aborts the whole map
+        raise ValueError(BOUNDS_ERROR)
+    return FitResult(out["t2"], out["k"], out["sigma"], out["res"], out["fun"], out["nit"], out["status"], fit,
+                     counts if counts is not None else (0, 0, 0, 0))
+
+
+def mask_indices_device(mask, n_masks=None):
+    """``mask_indices`` of a device mask: union over the per-TE axis (``np.sum(mask, axis=3) > 0``,
+    run_t2mapping.py:383-384) and ascending C-order compaction (:412,:421).  ``mask`` is a uint8/bool
+    CUDA tensor ``[z,y,x]`` or ``[z,y,x,n_masks]``; returns an int64 CUDA tensor."""
+    import torch
+    lib = init()
+    mk = mask
+    if mk.dtype == torch.bool:
+        mk = mk.view(torch.uint8)
+    if mk.dtype != torch.uint8:
+        mk = (mk > 0).view(torch.uint8)
+    mk = mk.contiguous()
+    nm = 1 if mk.dim() == 3 else mk.shape[-1]
+    n_vox = mk.numel() // nm
+    idx = torch.empty(n_vox, dtype=torch.int64, device=mk.device)
+    n = C.c_int64()
+    stream = torch.cuda.current_stream(mk.device).cuda_stream
+    _abi.check(lib, lib.t2fit_mask_indices(mk.data_ptr(), n_vox, nm, idx.data_ptr(), C.byref(n), stream),
+               "t2fit_mask_indices")
+    return idx[:n.value]
+
+
+def t2map_volume(t2w, mask, TEeffs, fit, fit_params, prior=True, norm=False, **kw):
+    """Stacked per-TE volumes ``t2w[z,y,x,E]``, mask ``[z,y,x]`` or per-TE masks ``[z,y,x,E]`` and the
+    TE vector in; ``(t2_map, k_map, sigma_map, res_map)`` float32 ``[z,y,x]`` out, zeros off-mask --
+    the whole hot block of ``process_t2maps`` (run_t2mapping.py:383-386, :411-461, :471-473)."""
+    lib = init()
+    shape3 = tuple(t2w.shape[:3])
+    n_echo = t2w.shape[-1]
+    p, o = _abi.Problem(), _abi.Outputs()
+    keep = [_fill_problem(p, fit, fit_params, TEeffs, prior, norm, kw.get("max_iter", 0), kw.get("tol", 0.0),
+                          kw.get("init_mode", "loglinear"))]
+    if _is_torch(t2w):
+        import torch
+        y = t2w.reshape(-1, n_echo)
+        if y.dtype != torch.float32:
+            y = y.float()
+        y = y.contiguous()
+        idx = mask_indices_device(mask)
+        n_vox, m = y.shape[0], idx.numel()
+        maps = torch.zeros((4, n_vox), dtype=torch.float32, device=y.device)          # :415-418
+        p.echoes, p.memory, p.mask_idx = y.data_ptr(), _abi.MEM_DEVICE, idx.data_ptr()
+        stream = torch.cuda.current_stream(y.device).cuda_stream
+        mp = [maps[i].data_ptr() for i in range(4)]
+        keep += [y, idx]
+    else:
+        y = np.reshape(np.asarray(t2w), (-1, n_echo))
+        if y.dtype != np.float32 or not y.flags.c_contiguous:
+            y = np.ascontiguousarray(y, dtype=np.float32)                               # :411
+        mk = np.asarray(mask)
+        mk = (np.sum(mk, axis=3) > 0) if mk.ndim == 4 else (mk > 0)                     # :383-384
+        idx = np.flatnonzero(mk.reshape(-1)).astype(np.int64)                           # :412,:421
+        n_vox, m = y.shape[0], idx.size
+        maps = np.zeros((4, n_vox), np.float32)                                         # :415-418
+        p.echoes, p.memory, p.mask_idx = y.ctypes.data, _abi.MEM_HOST, idx.ctypes.data
+        stream = None
+        mp = [maps[i].ctypes.data for i in range(4)]
+        keep += [y, idx]
+    if n_echo != p.n_echo:
+        raise ValueError(f"t2w has {n_echo} echoes, TEeffs has {p.n_echo}")
+    p.layout, p.ld, p.n_vox, p.n_fit = _abi.LAYOUT_AOS, 0, n_vox, m
+    o.t2, o.k, o.res = mp[0], mp[1], mp[3]
+    o.sigma = mp[2] if fit != "gaussian" else None
+    o.dense = 1
+    _run(lib, p, o, stream)
+    if stream is not None:
+        cnt = (C.c_int64 * 4)()
+        _abi.check(lib, lib.t2fit_status_counts(stream, cnt), "t2fit_status_counts")
+        bad = cnt[3]
+    else:
+        bad = o.status_count[3]
+    if bad > 0:
+        raise ValueError(BOUNDS_ERROR)
+    return tuple(maps[i].reshape(shape3) for i in range(4))
+
+
+def compute_residuals(reshaped_t2w, TEeffs, fit, norm, k_map, t2_map, sigma_map, res_map, mask_indices, mask):
+    """Signature of the reference's ``compute_residuals`` (utils/t2map_utils.py:62-89) for callers that
+    keep the two-step structure (``fit_voxels_batch`` already returns the same residuals).  Runs the
+    stand-alone CUDA residual pass (``t2fit_residuals``); numpy inputs are staged through torch."""
+    import torch
+    lib = init()
+    dev = torch.device("cuda", _state["device"])
+    host = not _is_torch(reshaped_t2w)
+
+    def to_dev(a, dt):
+        t = a if _is_torch(a) else torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(device=dev, dtype=dt).contiguous()
+    y = to_dev(reshaped_t2w, torch.float32)
+    idx = to_dev(mask_indices, torch.int64)
+    k, t2, sg = (to_dev(a, torch.float32).reshape(-1) for a in (k_map, t2_map, sigma_map))
+    res = to_dev(res_map, torch.float32).reshape(-1).clone()
+    p = _abi.Problem()
+    dummy = {"initial_guess": [1.0, 100.0] + ([1.0] if fit != "gaussian" else []),
+             "param_bounds": [(0.0, 1e9), (1e-3, 1e9)] + ([(0.0, 1e9)] if fit != "gaussian" else [])}
+    keep = _fill_problem(p, fit, dummy, TEeffs, True, norm, 0, 0.0, "loglinear")
+    p.echoes, p.memory, p.layout, p.mask_idx = y.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_AOS, idx.data_ptr()
+    p.n_vox, p.n_fit = y.shape[0], idx.numel()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _abi.check(lib, lib.t2fit_residuals(C.byref(p), k.data_ptr(), t2.data_ptr(), sg.data_ptr(), res.data_ptr(), stream),
+               "t2fit_residuals")
+    del keep
+    shape3 = tuple(mask.shape[:3])
+    if host:
+        return res.cpu().numpy().reshape(shape3)
+    return res.reshape(shape3)

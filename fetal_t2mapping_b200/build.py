@@ -1,0 +1,48 @@
+"""In-tree build of libt2fit.so with nvcc for sm_100a (no JIT cache, no torch extension)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libt2fit.so")
+SOURCES = ["t2fit_kernels.cu"]
+HEADERS = ["t2fit_core.cuh", "t2fit_consts.h", os.path.join("..", "..", "include", "t2fit.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+
+
+def nvcc_path():
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isfile(p):
+        raise RuntimeError("nvcc not found")
+    return p
+
+
+def up_to_date():
+    if not os.path.isfile(LIB):
+        return False
+    t = os.path.getmtime(LIB)
+    return all(os.path.getmtime(os.path.join(CSRC, f)) <= t for f in SOURCES + HEADERS)
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu -> csrc/libt2fit.so (static cudart, sm_100a SASS, -lineinfo)."""
+    if not force and up_to_date():
+        return LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + SOURCES + ["-o", LIB]
+    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    with open(os.path.join(CSRC, "ptxas_report.txt"), "w") as f:
+        f.write(r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stderr[-4000:])
+    if verbose:
+        print(r.stderr[-2000:])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force=True))

@@ -1,0 +1,71 @@
+// Host side: validate a t2fit_problem and fold it into the launch constants (FitConsts).
+// Restates the parts of fit_voxel that do not depend on the voxel: which box is in force
+// (run_t2mapping.py:243-245), the scipy precondition len(bounds)==len(x0) and lb<=ub
+// (scipy/optimize/_minimize.py _validate_bounds -> ValueError), and x0 clipped into the box
+// (scipy/optimize/_lbfgsb_py.py: x0 = clip(x0, lb, ub)).
+#pragma once
+#include <math.h>
+#include <string>
+#include "../../include/t2fit.h"
+#include "t2fit_core.cuh"
+
+namespace t2fit {
+
+constexpr int kDefaultMaxIterMono = 24;
+constexpr int kDefaultMaxIterFloor = 64;
+constexpr float kDefaultTolMono = 1e-4f;
+constexpr float kDefaultTolFloor = 1e-5f;
+
+inline int n_params(int model) { return model == T2FIT_MODEL_GAUSSIAN ? 2 : 3; }
+
+inline int make_consts(const t2fit_problem& p, FitConsts& c, std::string& err) {
+    if (p.n_echo < 2 || p.n_echo > kMaxEcho) { err = "n_echo must be in [2, 32]"; return T2FIT_EINVAL; }
+    if (p.model != T2FIT_MODEL_GAUSSIAN && p.model != T2FIT_MODEL_GAUSSIAN_RICIAN) {
+        err = "unknown model"; return T2FIT_EINVAL;
+    }
+    if (!p.te_ms) { err = "te_ms is NULL"; return T2FIT_EINVAL; }
+    if (p.n_fit < 0 || p.n_vox < 0) { err = "negative size"; return T2FIT_EINVAL; }
+    const int np_ = n_params(p.model);
+    double lb[3] = {p.lb[0], p.lb[1], p.lb[2]}, ub[3] = {p.ub[0], p.ub[1], p.ub[2]};
+    if (p.no_prior) {                               // run_t2mapping.py:243-245
+        ub[0] = p.no_prior_k_ub;
+        lb[1] = p.no_prior_t2_lb;
+        ub[1] = p.no_prior_t2_ub;
+    }
+    for (int i = 0; i < np_; ++i) {
+        if (i == 0 && p.no_prior) continue;          // lb[0] is the voxel's first echo
+        if (!(lb[i] <= ub[i])) { err = "An upper bound is less than the corresponding lower bound."; return T2FIT_EINVAL; }
+    }
+    if (!(lb[1] > 0.0)) { err = "T2 lower bound must be positive"; return T2FIT_EINVAL; }
+    double mean_te = 0;
+    for (int e = 0; e < p.n_echo; ++e) {
+        if (!isfinite(p.te_ms[e])) { err = "non-finite echo time"; return T2FIT_EINVAL; }
+        mean_te += p.te_ms[e];
+    }
+    mean_te /= p.n_echo;
+    for (int e = 0; e < kMaxEcho; ++e) {
+        const double te = e < p.n_echo ? p.te_ms[e] : 0.0;
+        c.te[e] = (float)te;
+        c.nte2[e] = (float)(-te * 1.4426950408889634);
+        c.tec[e] = e < p.n_echo ? (float)(te - mean_te) : 0.f;
+    }
+    for (int i = 0; i < 3; ++i) {
+        c.x0[i] = i < np_ ? (float)p.x0[i] : 0.f;
+        c.lb[i] = i < np_ ? (float)lb[i] : 0.f;
+        c.ub[i] = i < np_ ? (float)ub[i] : 0.f;
+    }
+    c.r_lo = (float)(1.0 / ub[1]);
+    c.r_hi = (float)(1.0 / lb[1]);
+    double t2x0 = fmin(fmax(p.x0[1], lb[1]), ub[1]);
+    c.r_x0 = fminf(fmaxf((float)(1.0 / t2x0), c.r_lo), c.r_hi);
+    const bool mono = p.model == T2FIT_MODEL_GAUSSIAN;
+    c.tol = p.tol > 0.f ? p.tol : (mono ? kDefaultTolMono : kDefaultTolFloor);
+    c.max_iter = p.max_iter > 0 ? p.max_iter : (mono ? kDefaultMaxIterMono : kDefaultMaxIterFloor);
+    c.n_echo = p.n_echo;
+    c.no_prior = p.no_prior ? 1 : 0;
+    c.norm = p.norm ? 1 : 0;
+    c.init_mode = p.init;
+    return T2FIT_OK;
+}
+
+}  // namespace t2fit

@@ -1,0 +1,752 @@
+// libt2fit: sm_100a kernels + the C ABI of include/t2fit.h.
+//
+// Kernels (DESIGN.md has the data layout and the roofline of each):
+//   fit_kernel<MODEL,E,LAYOUT>   one thread per masked voxel: gather echoes (AoS rows through
+//                                mask_idx, or SoA planes), solve in registers (t2fit_core.cuh),
+//                                residual epilogue, write compact or scatter into dense maps.
+//                                Replaces pool.map(fit_voxel) + compute_residuals + the scatter
+//                                (run_t2mapping.py:430-461).
+//   mask_count / mask_scan / mask_write   mask union + ordered compaction (:383-384,:412,:421)
+//   pack_soa_kernel              AoS rows -> echo-contiguous SoA (pack_masked_soa)
+//   scatter_kernel               compact -> dense maps (:455-458)
+// Host side: per-process context (one GPU per process), pinned staging ring + worker threads for
+// the host-memory path (pack AoS rows to SoA while the previous chunk is in flight).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "t2fit_consts.h"
+
+using namespace t2fit;
+
+namespace {
+
+constexpr int kBlock = 256;
+
+struct KernelIO {
+    const float* echoes;
+    const int64_t* idx;   // may be null
+    int64_t ld;
+    int64_t n_fit;
+    float* t2;
+    float* k;
+    float* sigma;
+    float* res;
+    float* fun;
+    int32_t* nit;
+    uint8_t* status;
+    unsigned long long* counts;  // [4] per-status voxel counts of this launch (OK slot unused)
+    int dense;                   // outputs indexed by idx[i] instead of i (status/nit/fun stay compact)
+    int vec_ok;                  // AoS base pointer is 16-byte aligned
+};
+
+// ------------------------------------------------------------------------------------------------
+// echo loads
+// ------------------------------------------------------------------------------------------------
+template <int E>
+__device__ __forceinline__ void load_aos(const float* __restrict__ base, int64_t row, bool vec_ok, float (&y)[E]) {
+    const float* p = base + row * E;
+    if constexpr (E % 4 == 0) {
+        if (vec_ok) {
+            const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+            for (int q = 0; q < E / 4; ++q) {
+                const float4 v = __ldg(p4 + q);
+                y[4 * q] = v.x; y[4 * q + 1] = v.y; y[4 * q + 2] = v.z; y[4 * q + 3] = v.w;
+            }
+            return;
+        }
+    } else if constexpr (E % 2 == 0) {
+        if (vec_ok) {
+            const float2* p2 = reinterpret_cast<const float2*>(p);
+#pragma unroll
+            for (int q = 0; q < E / 2; ++q) {
+                const float2 v = __ldg(p2 + q);
+                y[2 * q] = v.x; y[2 * q + 1] = v.y;
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) y[e] = __ldg(p + e);
+}
+
+template <int E>
+__device__ __forceinline__ void load_soa(const float* __restrict__ base, int64_t ld, int64_t i, float (&y)[E]) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) y[e] = __ldg(base + (int64_t)e * ld + i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fit kernel
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int E, int LAYOUT>
+__global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ FitConsts c,
+                                                     const __grid_constant__ KernelIO io) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = i < io.n_fit;
+    const int64_t ii = valid ? i : io.n_fit - 1;       // whole warps stay in the solver (warp votes)
+    const int64_t row = io.idx ? __ldg(io.idx + ii) : ii;
+    float y[E];
+    if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row, io.vec_ok != 0, y);
+    else load_soa<E>(io.echoes, io.ld, ii, y);
+
+    const VoxelFit f = fit_voxel<float, MODEL, E>(y, c, valid);
+
+    if (valid) {
+        const int64_t o = io.dense ? row : i;
+        if (io.t2) io.t2[o] = f.t2;
+        if (io.k) io.k[o] = f.k;
+        if (MODEL != kMono2 && io.sigma) io.sigma[o] = f.sigma;
+        if (io.res) io.res[o] = f.res;
+        if (io.fun) io.fun[i] = f.fun;
+        if (io.nit) io.nit[i] = f.nit;
+        if (io.status) io.status[i] = (uint8_t)f.status;
+    }
+    // warp-aggregated status histogram: one atomic per warp per non-OK status (normally none)
+    const int st = valid ? f.status : 0;
+    const unsigned any_bad = __ballot_sync(0xffffffffu, st != 0);
+    if (any_bad && io.counts) {
+#pragma unroll
+        for (int s = 1; s < 4; ++s) {
+            const unsigned m = __ballot_sync(0xffffffffu, st == s);
+            if (m && (threadIdx.x & 31) == 0) atomicAdd(io.counts + s, (unsigned long long)__popc(m));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask union + ordered compaction: three small passes over the mask bytes
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaskTile = 2048;  // voxels per block (256 threads x 8)
+
+__device__ __forceinline__ bool mask_any(const uint8_t* __restrict__ masks, int64_t v, int n_masks) {
+    const uint8_t* p = masks + v * n_masks;
+    int acc = 0;
+    for (int m = 0; m < n_masks; ++m) acc |= p[m];      // np.sum(mask4, axis=3) > 0
+    return acc != 0;
+}
+
+__global__ void __launch_bounds__(256) mask_count_kernel(const uint8_t* __restrict__ masks, int64_t n_vox, int n_masks,
+                                                         int* __restrict__ tile_counts) {
+    const int64_t base = (int64_t)blockIdx.x * kMaskTile;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kMaskTile / 256; ++j) {
+        const int64_t v = base + j * 256 + threadIdx.x;
+        if (v < n_vox && mask_any(masks, v, n_masks)) ++cnt;
+    }
+    __shared__ int wsum[8];
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += wsum[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the tile counts (one block; tiles <= a few 100k)
+__global__ void __launch_bounds__(1024) mask_scan_kernel(const int* __restrict__ tile_counts, int64_t* __restrict__ tile_offsets,
+                                                         int n_tiles, int64_t* __restrict__ total) {
+    __shared__ int64_t wsum[32];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int t = base + threadIdx.x;
+        const int64_t v = t < n_tiles ? tile_counts[t] : 0;
+        int64_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += n;
+        }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int64_t w = wsum[threadIdx.x];
+            int64_t wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t n = __shfl_up_sync(0xffffffffu, wi, o);
+                if (threadIdx.x >= o) wi += n;
+            }
+            wsum[threadIdx.x] = wi - w;  // exclusive warp offsets
+        }
+        __syncthreads();
+        const int64_t excl = carry + wsum[threadIdx.x >> 5] + incl - v;
+        if (t < n_tiles) tile_offsets[t] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(256) mask_write_kernel(const uint8_t* __restrict__ masks, int64_t n_vox, int n_masks,
+                                                         const int64_t* __restrict__ tile_offsets, int64_t* __restrict__ idx_out) {
+    const int64_t base = (int64_t)blockIdx.x * kMaskTile;
+    __shared__ int wcnt[8];
+    __shared__ int running;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    const int64_t out0 = tile_offsets[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = 0; j < kMaskTile / 256; ++j) {          // keeps ascending order: j-major, thread-minor
+        const int64_t v = base + j * 256 + threadIdx.x;
+        const bool f = v < n_vox && mask_any(masks, v, n_masks);
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wcnt[warp] = __popc(b);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < 8; ++w) { if (w < warp) woff += wcnt[w]; tot += wcnt[w]; }
+        const int before = running;
+        if (f) idx_out[out0 + before + woff + __popc(b & ((1u << lane) - 1u))] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) running = before + tot;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack / scatter
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_soa_kernel(const float* __restrict__ aos, int n_echo, const int64_t* __restrict__ idx,
+                                                       int64_t n_fit, float* __restrict__ soa, int64_t ld) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_fit) return;
+    const int64_t row = idx ? __ldg(idx + i) : i;
+    const float* p = aos + row * n_echo;
+    for (int e = 0; e < n_echo; ++e) soa[(int64_t)e * ld + i] = __ldg(p + e);
+}
+
+struct ScatterArgs {
+    const float* src[4];
+    float* dst[4];
+    int n_maps;
+};
+
+__global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ ScatterArgs a, const int64_t* __restrict__ idx,
+                                                      int64_t n_fit) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_fit) return;
+    const int64_t o = __ldg(idx + i);
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+        if (m < a.n_maps) a.dst[m][o] = __ldg(a.src[m] + i);
+}
+
+// compute_residuals as a stand-alone pass (utils/t2map_utils.py:62-89): res[row] = sum_e (y_e - pred_e)/E from given maps
+__global__ void __launch_bounds__(256) residual_kernel(const __grid_constant__ FitConsts c, const float* __restrict__ aos,
+                                                       const int64_t* __restrict__ idx, int64_t n_fit, int model,
+                                                       const float* __restrict__ k_map, const float* __restrict__ t2_map,
+                                                       const float* __restrict__ sigma_map, float* __restrict__ res_map) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_fit) return;
+    const int64_t row = idx ? __ldg(idx + i) : i;
+    const float* p = aos + row * c.n_echo;
+    const float k = k_map[row], rr = 1.0f / t2_map[row];
+    const float s = (model != T2FIT_MODEL_GAUSSIAN && sigma_map) ? sigma_map[row] : 0.f;
+    float scale = 1.f;
+    if (c.norm) {
+        float mx = __ldg(p);
+        for (int e = 1; e < c.n_echo; ++e) mx = fmaxf(mx, __ldg(p + e));
+        scale = 1.0f / mx;
+    }
+    float acc = 0.f;
+    for (int e = 0; e < c.n_echo; ++e) {
+        float pred = k * fast_ex2(c.nte2[e] * rr);
+        if (model != T2FIT_MODEL_GAUSSIAN) pred = sqrtf(pred * pred + s * s);
+        acc += __ldg(p + e) * scale - pred;
+    }
+    res_map[row] = acc / (float)c.n_echo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch table
+// ------------------------------------------------------------------------------------------------
+using FitFn = void (*)(const FitConsts, const KernelIO);
+
+template <int MODEL, int LAYOUT>
+FitFn pick_e(int n_echo) {
+    switch (n_echo) {
+#define T2_CASE(E) case E: return fit_kernel<MODEL, E, LAYOUT>;
+        T2_CASE(2) T2_CASE(3) T2_CASE(4) T2_CASE(5) T2_CASE(6) T2_CASE(7) T2_CASE(8) T2_CASE(9) T2_CASE(10)
+        T2_CASE(11) T2_CASE(12) T2_CASE(13) T2_CASE(14) T2_CASE(15) T2_CASE(16) T2_CASE(17) T2_CASE(18)
+        T2_CASE(19) T2_CASE(20) T2_CASE(21) T2_CASE(22) T2_CASE(23) T2_CASE(24) T2_CASE(25) T2_CASE(26)
+        T2_CASE(27) T2_CASE(28) T2_CASE(29) T2_CASE(30) T2_CASE(31) T2_CASE(32)
+#undef T2_CASE
+        default: return nullptr;
+    }
+}
+
+FitFn pick_kernel(int model, int n_echo, int layout) {
+    if (model == T2FIT_MODEL_GAUSSIAN)
+        return layout == T2FIT_LAYOUT_AOS ? pick_e<kMono2, T2FIT_LAYOUT_AOS>(n_echo) : pick_e<kMono2, T2FIT_LAYOUT_SOA>(n_echo);
+    return layout == T2FIT_LAYOUT_AOS ? pick_e<kFloor3, T2FIT_LAYOUT_AOS>(n_echo) : pick_e<kFloor3, T2FIT_LAYOUT_SOA>(n_echo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host context
+// ------------------------------------------------------------------------------------------------
+thread_local std::string tl_err;
+
+int fail(int code, const std::string& msg) { tl_err = msg; return code; }
+
+#define CU_TRY(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return fail(T2FIT_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+// minimal fork-join pool for the host-memory path (pack / unpack of staging chunks)
+class Workers {
+  public:
+    explicit Workers(int n) : n_(std::max(1, n)) {
+        for (int t = 1; t < n_; ++t) threads_.emplace_back([this, t] { loop(t); });
+    }
+    ~Workers() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    int size() const { return n_; }
+    // fn(part, n_parts) on every worker, caller included; returns when all are done
+    void run(const std::function<void(int, int)>& fn) {
+        { std::lock_guard<std::mutex> g(m_); fn_ = &fn; pending_ = n_ - 1; ++gen_; }
+        cv_.notify_all();
+        fn(0, n_);
+        std::unique_lock<std::mutex> l(m_);
+        done_cv_.wait(l, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void loop(int t) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int, int)>* fn;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            if (fn) (*fn)(t, n_);
+            { std::lock_guard<std::mutex> g(m_); --pending_; }
+            done_cv_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int, int)>* fn_ = nullptr;
+    uint64_t gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+constexpr int kSlots = 3;
+constexpr int64_t kChunk = 1 << 18;  // voxels per staging chunk
+
+struct Slot {
+    float* h_in = nullptr;     // pinned [E_cap * kChunk]
+    float* d_in = nullptr;
+    float* h_out = nullptr;    // pinned [5 * kChunk] t2,k,sigma,res,fun
+    float* d_out = nullptr;
+    int32_t* h_nit = nullptr;  int32_t* d_nit = nullptr;
+    uint8_t* h_st = nullptr;   uint8_t* d_st = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    int64_t first = -1, count = 0;  // chunk in flight
+};
+
+struct Context {
+    int device = -1;
+    cudaDeviceProp prop{};
+    cudaStream_t stream = nullptr;           // default stream of the library
+    unsigned long long* d_counts = nullptr;  // [4]
+    unsigned long long* h_counts = nullptr;  // pinned [4]
+    Slot slots[kSlots];
+    int e_cap = 0;
+    Workers* workers = nullptr;
+    // scratch of t2fit_mask_indices
+    int* d_tile_counts = nullptr;
+    int64_t* d_tile_offsets = nullptr;
+    int64_t* d_total = nullptr;
+    int64_t* h_total = nullptr;
+    int64_t tiles_cap = 0;
+};
+
+Context* g_ctx = nullptr;
+std::mutex g_mu;
+
+void free_slots(Context* c) {
+    for (auto& s : c->slots) {
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.h_nit) cudaFreeHost(s.h_nit);
+        if (s.d_nit) cudaFree(s.d_nit);
+        if (s.h_st) cudaFreeHost(s.h_st);
+        if (s.d_st) cudaFree(s.d_st);
+        s.h_in = s.d_in = s.h_out = s.d_out = nullptr;
+        s.h_nit = s.d_nit = nullptr;
+        s.h_st = s.d_st = nullptr;
+    }
+    c->e_cap = 0;
+}
+
+int ensure_slots(Context* c, int n_echo) {
+    if (c->e_cap >= n_echo) return T2FIT_OK;
+    free_slots(c);
+    for (auto& s : c->slots) {
+        CU_TRY(cudaMallocHost(&s.h_in, sizeof(float) * n_echo * kChunk));
+        CU_TRY(cudaMalloc(&s.d_in, sizeof(float) * n_echo * kChunk));
+        CU_TRY(cudaMallocHost(&s.h_out, sizeof(float) * 5 * kChunk));
+        CU_TRY(cudaMalloc(&s.d_out, sizeof(float) * 5 * kChunk));
+        CU_TRY(cudaMallocHost(&s.h_nit, sizeof(int32_t) * kChunk));
+        CU_TRY(cudaMalloc(&s.d_nit, sizeof(int32_t) * kChunk));
+        CU_TRY(cudaMallocHost(&s.h_st, kChunk));
+        CU_TRY(cudaMalloc(&s.d_st, kChunk));
+        if (!s.stream) CU_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        if (!s.done) CU_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    c->e_cap = n_echo;
+    return T2FIT_OK;
+}
+
+int launch_fit(Context* c, const FitConsts& fc, KernelIO io, int model, int n_echo, int layout, cudaStream_t st) {
+    if (io.n_fit <= 0) return T2FIT_OK;
+    FitFn fn = pick_kernel(model, n_echo, layout);
+    if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
+    const int64_t blocks = (io.n_fit + kBlock - 1) / kBlock;
+    if (blocks > 0x7fffffffLL) return fail(T2FIT_EINVAL, "n_fit too large for one launch");
+    fn<<<(unsigned)blocks, kBlock, 0, st>>>(fc, io);
+    CU_TRY(cudaGetLastError());
+    return T2FIT_OK;
+}
+
+// host-memory path: stage chunks through pinned buffers; pack on worker threads while the GPU
+// works on the previous chunk; results come back compact and are copied / scattered on the host
+int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitConsts& fc) {
+    int rc = ensure_slots(c, p.n_echo);
+    if (rc) return rc;
+    const int E = p.n_echo;
+    const int64_t M = p.n_fit;
+    CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    const int64_t n_chunks = (M + kChunk - 1) / kChunk;
+
+    auto unpack = [&](Slot& s) {
+        if (s.first < 0) return;
+        const int64_t first = s.first, n = s.count;
+        float* outs[5] = {o.t2, o.k, o.sigma, o.res, o.fun};
+        c->workers->run([&](int part, int parts) {
+            const int64_t lo = n * part / parts, hi = n * (part + 1) / parts;
+            if (hi <= lo) return;
+            for (int m = 0; m < 5; ++m) {
+                float* dst = outs[m];
+                if (!dst) continue;
+                if (m == 2 && p.model == T2FIT_MODEL_GAUSSIAN) continue;   // sigma map stays as the caller zeroed it
+                const float* src = s.h_out + (int64_t)m * kChunk;
+                if (o.dense && m < 4) {
+                    if (p.mask_idx) for (int64_t i = lo; i < hi; ++i) dst[p.mask_idx[first + i]] = src[i];
+                    else memcpy(dst + first + lo, src + lo, sizeof(float) * (hi - lo));
+                } else {
+                    memcpy(dst + first + lo, src + lo, sizeof(float) * (hi - lo));
+                }
+            }
+            if (o.nit) memcpy(o.nit + first + lo, s.h_nit + lo, sizeof(int32_t) * (hi - lo));
+            if (o.status) memcpy(o.status + first + lo, s.h_st + lo, hi - lo);
+        });
+        s.first = -1;
+    };
+
+    for (int64_t ch = 0; ch < n_chunks; ++ch) {
+        Slot& s = c->slots[ch % kSlots];
+        if (s.first >= 0) {                       // slot still holds an older chunk: drain it
+            CU_TRY(cudaEventSynchronize(s.done));
+            unpack(s);
+        }
+        const int64_t first = ch * kChunk, n = std::min(kChunk, M - first);
+        // pack: rows (through mask_idx) -> SoA planes of the pinned buffer
+        c->workers->run([&](int part, int parts) {
+            const int64_t lo = n * part / parts, hi = n * (part + 1) / parts;
+            if (p.layout == T2FIT_LAYOUT_AOS) {
+                for (int64_t i = lo; i < hi; ++i) {
+                    const int64_t row = p.mask_idx ? p.mask_idx[first + i] : first + i;
+                    const float* src = p.echoes + row * E;
+                    for (int e = 0; e < E; ++e) s.h_in[(int64_t)e * kChunk + i] = src[e];
+                }
+            } else {
+                for (int e = 0; e < E; ++e)
+                    if (hi > lo) memcpy(s.h_in + (int64_t)e * kChunk + lo, p.echoes + (int64_t)e * p.ld + first + lo,
+                                        sizeof(float) * (hi - lo));
+            }
+        });
+        for (int e = 0; e < E; ++e)
+            CU_TRY(cudaMemcpyAsync(s.d_in + (int64_t)e * kChunk, s.h_in + (int64_t)e * kChunk, sizeof(float) * n,
+                                   cudaMemcpyHostToDevice, s.stream));
+        KernelIO io{};
+        io.echoes = s.d_in; io.idx = nullptr; io.ld = kChunk; io.n_fit = n;
+        io.t2 = s.d_out; io.k = s.d_out + kChunk; io.sigma = s.d_out + 2 * kChunk; io.res = s.d_out + 3 * kChunk;
+        io.fun = s.d_out + 4 * kChunk; io.nit = s.d_nit; io.status = s.d_st; io.counts = c->d_counts;
+        io.dense = 0; io.vec_ok = 1;
+        rc = launch_fit(c, fc, io, p.model, E, T2FIT_LAYOUT_SOA, s.stream);
+        if (rc) return rc;
+        for (int m = 0; m < 5; ++m) {
+            if (m == 2 && p.model == T2FIT_MODEL_GAUSSIAN) continue;
+            CU_TRY(cudaMemcpyAsync(s.h_out + (int64_t)m * kChunk, s.d_out + (int64_t)m * kChunk, sizeof(float) * n,
+                                   cudaMemcpyDeviceToHost, s.stream));
+        }
+        CU_TRY(cudaMemcpyAsync(s.h_nit, s.d_nit, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(cudaMemcpyAsync(s.h_st, s.d_st, n, cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(cudaEventRecord(s.done, s.stream));
+        s.first = first; s.count = n;
+    }
+    // drain in submission order
+    for (int64_t ch = std::max<int64_t>(0, n_chunks - kSlots); ch < n_chunks; ++ch) {
+        Slot& s = c->slots[ch % kSlots];
+        if (s.first >= 0) { CU_TRY(cudaEventSynchronize(s.done)); unpack(s); }
+    }
+    CU_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    int64_t bad = 0;
+    for (int s = 1; s < 4; ++s) { o.status_count[s] = (int64_t)c->h_counts[s]; bad += o.status_count[s]; }
+    o.status_count[0] = M - bad;
+    return T2FIT_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int t2fit_abi_version(void) { return T2FIT_ABI_VERSION; }
+
+const char* t2fit_last_error(void) { return tl_err.c_str(); }
+
+int t2fit_init(int device) {
+    std::lock_guard<std::mutex> g(g_mu);
+    if (g_ctx) {
+        if (g_ctx->device == device) return T2FIT_OK;
+        return fail(T2FIT_EINVAL, "already initialised on another device (one process per GPU)");
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(T2FIT_ENODEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                         " (libt2fit has no CPU implementation of the fit)");
+    if (device < 0 || device >= n) return fail(T2FIT_EINVAL, "device index out of range");
+    CU_TRY(cudaSetDevice(device));
+    Context* c = new Context();
+    c->device = device;
+    CU_TRY(cudaGetDeviceProperties(&c->prop, device));
+    if (c->prop.major < 10)
+        return fail(T2FIT_ENODEVICE, "libt2fit is built for sm_100a only; device is sm_" + std::to_string(c->prop.major) +
+                                         std::to_string(c->prop.minor));
+    CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaMalloc(&c->d_counts, 4 * sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(c->d_counts, 0, 4 * sizeof(unsigned long long)));
+    CU_TRY(cudaMallocHost(&c->h_counts, 4 * sizeof(unsigned long long)));
+    CU_TRY(cudaMalloc(&c->d_total, sizeof(int64_t)));
+    CU_TRY(cudaMallocHost(&c->h_total, sizeof(int64_t)));
+    unsigned hw = std::thread::hardware_concurrency();
+    const char* env = getenv("T2FIT_HOST_THREADS");
+    int nt = env ? atoi(env) : (int)std::min(16u, hw ? hw : 4u);
+    c->workers = new Workers(nt);
+    g_ctx = c;
+    return T2FIT_OK;
+}
+
+void t2fit_shutdown(void) {
+    std::lock_guard<std::mutex> g(g_mu);
+    Context* c = g_ctx;
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_slots(c);
+    for (auto& s : c->slots) {
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    if (c->d_counts) cudaFree(c->d_counts);
+    if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->d_tile_counts) cudaFree(c->d_tile_counts);
+    if (c->d_tile_offsets) cudaFree(c->d_tile_offsets);
+    if (c->d_total) cudaFree(c->d_total);
+    if (c->h_total) cudaFreeHost(c->h_total);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c->workers;
+    delete c;
+    g_ctx = nullptr;
+}
+
+int t2fit_device_info(char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor) {
+    if (!g_ctx) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
+    if (name && name_len > 0) { strncpy(name, g_ctx->prop.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = g_ctx->prop.multiProcessorCount;
+    if (cc_major) *cc_major = g_ctx->prop.major;
+    if (cc_minor) *cc_minor = g_ctx->prop.minor;
+    return T2FIT_OK;
+}
+
+int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
+    Context* c = g_ctx;
+    if (!c) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded (no CUDA device bound; there is no CPU fit)");
+    if (!p || !o) return fail(T2FIT_EINVAL, "NULL problem/outputs");
+    FitConsts fc;
+    memset(&fc, 0, sizeof(fc));
+    std::string err;
+    int rc = make_consts(*p, fc, err);
+    if (rc) return fail(rc, err);
+    if (p->n_fit == 0) { memset(o->status_count, 0, sizeof(o->status_count)); return T2FIT_OK; }
+    if (!p->echoes) return fail(T2FIT_EINVAL, "echoes is NULL");
+    if (p->layout != T2FIT_LAYOUT_AOS && p->layout != T2FIT_LAYOUT_SOA) return fail(T2FIT_EINVAL, "bad layout");
+    if (p->layout == T2FIT_LAYOUT_SOA && p->ld < p->n_fit) return fail(T2FIT_EINVAL, "ld < n_fit");
+    if (p->layout == T2FIT_LAYOUT_AOS && !p->mask_idx && p->n_fit > p->n_vox) return fail(T2FIT_EINVAL, "n_fit > n_vox");
+    if (o->dense && !p->mask_idx && p->n_fit > p->n_vox) return fail(T2FIT_EINVAL, "dense output needs n_vox >= n_fit");
+    CU_TRY(cudaSetDevice(c->device));
+    if (p->memory == T2FIT_MEM_HOST) return run_host(c, *p, *o, fc);
+    if (p->memory != T2FIT_MEM_DEVICE) return fail(T2FIT_EINVAL, "bad memory kind");
+
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), st));
+    KernelIO io{};
+    io.echoes = p->echoes; io.idx = p->mask_idx; io.ld = p->ld; io.n_fit = p->n_fit;
+    io.t2 = o->t2; io.k = o->k; io.sigma = o->sigma; io.res = o->res; io.fun = o->fun; io.nit = o->nit;
+    io.status = o->status; io.counts = c->d_counts; io.dense = o->dense;
+    io.vec_ok = (reinterpret_cast<uintptr_t>(p->echoes) % 16) == 0;
+    return launch_fit(c, fc, io, p->model, p->n_echo, p->layout, st);
+}
+
+int t2fit_status_counts(void* stream, int64_t counts[4]) {
+    Context* c = g_ctx;
+    if (!c) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
+    if (!counts) return fail(T2FIT_EINVAL, "NULL counts");
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    CU_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    for (int s = 0; s < 4; ++s) counts[s] = (int64_t)c->h_counts[s];
+    counts[0] = -1;  // OK count = n_fit - sum(others); the caller knows n_fit
+    return T2FIT_OK;
+}
+
+int t2fit_mask_indices(const uint8_t* masks, int64_t n_vox, int32_t n_masks, int64_t* idx_out, int64_t* n_out, void* stream) {
+    Context* c = g_ctx;
+    if (!c) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
+    if (!masks || !idx_out || !n_out || n_vox < 0 || n_masks < 1) return fail(T2FIT_EINVAL, "bad mask arguments");
+    if (n_vox == 0) { *n_out = 0; return T2FIT_OK; }
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const int64_t tiles = (n_vox + kMaskTile - 1) / kMaskTile;
+    if (tiles > 0x7fffffffLL) return fail(T2FIT_EINVAL, "volume too large");
+    if (tiles > c->tiles_cap) {
+        CU_TRY(cudaStreamSynchronize(st));
+        if (c->d_tile_counts) cudaFree(c->d_tile_counts);
+        if (c->d_tile_offsets) cudaFree(c->d_tile_offsets);
+        c->d_tile_counts = nullptr; c->d_tile_offsets = nullptr; c->tiles_cap = 0;
+        CU_TRY(cudaMalloc(&c->d_tile_counts, sizeof(int) * tiles));
+        CU_TRY(cudaMalloc(&c->d_tile_offsets, sizeof(int64_t) * tiles));
+        c->tiles_cap = tiles;
+    }
+    mask_count_kernel<<<(unsigned)tiles, 256, 0, st>>>(masks, n_vox, n_masks, c->d_tile_counts);
+    mask_scan_kernel<<<1, 1024, 0, st>>>(c->d_tile_counts, c->d_tile_offsets, (int)tiles, c->d_total);
+    mask_write_kernel<<<(unsigned)tiles, 256, 0, st>>>(masks, n_vox, n_masks, c->d_tile_offsets, idx_out);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(c->h_total, c->d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    *n_out = *c->h_total;
+    return T2FIT_OK;
+}
+
+int t2fit_pack_soa(const float* aos, int64_t n_vox, int32_t n_echo, const int64_t* mask_idx, int64_t n_fit, float* soa,
+                   int64_t ld, void* stream) {
+    Context* c = g_ctx;
+    if (!c) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
+    if (!aos || !soa || n_echo < 1 || ld < n_fit || n_fit < 0 || n_vox < 0) return fail(T2FIT_EINVAL, "bad pack arguments");
+    if (n_fit == 0) return T2FIT_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    pack_soa_kernel<<<(unsigned)((n_fit + 255) / 256), 256, 0, st>>>(aos, n_echo, mask_idx, n_fit, soa, ld);
+    CU_TRY(cudaGetLastError());
+    return T2FIT_OK;
+}
+
+int t2fit_scatter(const float* const* compact, float* const* dense, int32_t n_maps, const int64_t* mask_idx, int64_t n_fit,
+                  void* stream) {
+    Context* c = g_ctx;
+    if (!c) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
+    if (!compact || !dense || !mask_idx || n_maps < 1 || n_maps > 4 || n_fit < 0) return fail(T2FIT_EINVAL, "bad scatter arguments");
+    if (n_fit == 0) return T2FIT_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    ScatterArgs a{};
+    a.n_maps = n_maps;
+    for (int m = 0; m < n_maps; ++m) { a.src[m] = compact[m]; a.dst[m] = dense[m]; }
+    scatter_kernel<<<(unsigned)((n_fit + 255) / 256), 256, 0, st>>>(a, mask_idx, n_fit);
+    CU_TRY(cudaGetLastError());
+    return T2FIT_OK;
+}
+
+int t2fit_residuals(const t2fit_problem* p, const float* k_map, const float* t2_map, const float* sigma_map, float* res_map,
+                    void* stream) {
+    Context* c = g_ctx;
+    if (!c) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
+    if (!p || !k_map || !t2_map || !res_map || !p->echoes) return fail(T2FIT_EINVAL, "NULL argument");
+    if (p->memory != T2FIT_MEM_DEVICE || p->layout != T2FIT_LAYOUT_AOS) return fail(T2FIT_EINVAL, "device AOS input only");
+    FitConsts fc;
+    memset(&fc, 0, sizeof(fc));
+    std::string err;
+    int rc = make_consts(*p, fc, err);
+    if (rc) return fail(rc, err);
+    if (p->n_fit == 0) return T2FIT_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    residual_kernel<<<(unsigned)((p->n_fit + 255) / 256), 256, 0, st>>>(fc, p->echoes, p->mask_idx, p->n_fit, p->model, k_map,
+                                                                       t2_map, sigma_map, res_map);
+    CU_TRY(cudaGetLastError());
+    return T2FIT_OK;
+}
+
+int t2fit_work_model(int32_t model, int32_t n_echo, double* flop_per_pass, double* mufu_per_pass, double* flop_fixed,
+                     double* mufu_fixed, double* bytes_per_voxel) {
+    if (n_echo < 1) return fail(T2FIT_EINVAL, "bad n_echo");
+    const double E = n_echo;
+    // counts of the shipped device code (t2fit_core.cuh), FMA = 2 FLOP; see DESIGN.md "work model"
+    if (model == T2FIT_MODEL_GAUSSIAN) {
+        if (flop_per_pass) *flop_per_pass = 12.0 * E + 48.0;   // echo loop: 2 FMUL + 5 FFMA; solve/bracket ~48
+        if (mufu_per_pass) *mufu_per_pass = E + 4.0;           // EX2 per echo; RCP + divides in the solve
+        if (flop_fixed) *flop_fixed = (10.0 * E + 16.0) + (7.0 * E + 8.0);  // log-linear init + residual epilogue
+        if (mufu_fixed) *mufu_fixed = 2.0 * E + 4.0;           // LG2 per echo (init) + EX2 per echo (epilogue)
+        if (bytes_per_voxel) *bytes_per_voxel = 4.0 * E + 4.0 * 3 + 1;      // echoes in; t2,k,res + status out
+    } else if (model == T2FIT_MODEL_GAUSSIAN_RICIAN) {
+        if (flop_per_pass) *flop_per_pass = 33.0 * E + 110.0;  // echo loop: 13 mul/add + 10 FFMA; 3x3 solve ~110
+        if (mufu_per_pass) *mufu_per_pass = 2.0 * E + 5.0;     // EX2 + RSQ per echo; 3 RSQ + RCP in the solve
+        if (flop_fixed) *flop_fixed = (10.0 * E + 16.0) + (12.0 * E + 5.0) + (11.0 * E + 8.0);
+        if (mufu_fixed) *mufu_fixed = 4.0 * E + 4.0;
+        if (bytes_per_voxel) *bytes_per_voxel = 4.0 * E + 4.0 * 4 + 1;
+    } else {
+        return fail(T2FIT_EINVAL, "unknown model");
+    }
+    return T2FIT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+/* t2fit.h - C ABI of libt2fit: the B200 (sm_100a) per-voxel T2 relaxation fit.
+ *
+ * Drop-in boundary.  The reference (Medical-Image-Analysis-Laboratory/fetal_t2mapping) has no
+ * FFI; its hot path is the call pair inside process_t2maps:
+ *
+ *     all_results = pool.map(partial(fit_voxel, fit, fit_params, TEeffs, reshaped_t2w, prior, norm),
+ *                            mask_indices)                                 run_t2mapping.py:430-443
+ *     res_map     = compute_residuals(reshaped_t2w, TEeffs, fit, norm, k_map, t2_map, sigma_map,
+ *                                     res_map, mask_indices, mask)         run_t2mapping.py:461
+ *
+ * plus the glue around it (mask union :383-384, flatten :411-412, np.where :421, zero maps :415-418,
+ * scatter :455-458).  Each entry point below names the reference lines it replaces.  Plain
+ * pointers and sizes only; the caller owns every buffer; nothing here throws; every function
+ * returns 0 on success or a negative T2FIT_E* code, with text in t2fit_last_error().
+ * Per-voxel problems are reported in status[], never in the return code.
+ *
+ * There is NO CPU implementation of the fit behind this ABI: without a CUDA device
+ * t2fit_init() fails with T2FIT_ENODEVICE and every compute call fails with T2FIT_ENOTINIT.
+ */
+#ifndef T2FIT_H
+#define T2FIT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T2FIT_ABI_VERSION 1
+#define T2FIT_MAX_ECHO 32
+
+/* return codes */
+#define T2FIT_OK 0
+#define T2FIT_EINVAL (-1)    /* bad argument (sizes, NULL, n_echo out of range, len(bounds)) */
+#define T2FIT_ENODEVICE (-2) /* no usable CUDA device */
+#define T2FIT_ENOTINIT (-3)  /* t2fit_init() has not succeeded in this process */
+#define T2FIT_ECUDA (-4)     /* CUDA runtime error (text in t2fit_last_error) */
+#define T2FIT_ENOMEM (-5)
+
+/* fit model = the reference's `fit` string (run_t2mapping.py:37,48) */
+#define T2FIT_MODEL_GAUSSIAN 0        /* 'gaussian'        k exp(-te/T2)                   :129-131 */
+#define T2FIT_MODEL_GAUSSIAN_RICIAN 1 /* 'gaussian_rician' sqrt(k^2 exp(-2te/T2)+sigma^2)  :133-138 */
+
+/* echo layout */
+#define T2FIT_LAYOUT_AOS 0 /* reshaped_t2w: [n_vox, n_echo] row-major float32 (run_t2mapping.py:411) */
+#define T2FIT_LAYOUT_SOA 1 /* packed: [n_echo, ld] float32, column i = i-th fitted voxel            */
+
+/* where the data pointers of a call live */
+#define T2FIT_MEM_HOST 0   /* library stages through pinned buffers, copies results back */
+#define T2FIT_MEM_DEVICE 1 /* pointers are device memory on the initialised GPU; fully asynchronous */
+
+/* per-voxel status byte */
+#define T2FIT_ST_OK 0           /* result.success == True                                            */
+#define T2FIT_ST_NONFINITE 1    /* NaN/Inf echo: reference returns success False, x = clipped x0     */
+#define T2FIT_ST_NOTCONVERGED 2 /* iteration cap hit (reference: maxiter -> success False)           */
+#define T2FIT_ST_BADBOUNDS 3    /* --no_prior and S(TE0) > k upper bound: scipy raises ValueError    */
+
+/* initial guess of the iteration */
+#define T2FIT_INIT_LOGLINEAR 0 /* weighted log-linear fit of the echoes (default) */
+#define T2FIT_INIT_PRESET 1    /* the preset's initial_guess, clipped, as the reference starts */
+
+/* The fit of one call.  Mirrors fit_voxel's arguments (run_t2mapping.py:120). */
+typedef struct t2fit_problem {
+    const float *echoes;     /* see layout */
+    int32_t layout;          /* T2FIT_LAYOUT_* */
+    int32_t memory;          /* T2FIT_MEM_* (applies to echoes, mask_idx and every output pointer) */
+    int64_t ld;              /* SOA only: elements between consecutive echo planes (>= n_fit) */
+    const int64_t *mask_idx; /* [n_fit] ascending flat voxel indices = mask_indices (:421); NULL = rows 0..n_fit-1.
+                                AOS: row to read (and dense output slot).  SOA: dense output slot only. */
+    int64_t n_vox;           /* rows of the AOS array = length of dense maps */
+    int64_t n_fit;           /* voxels to fit (M) */
+    int32_t n_echo;          /* E, 2..T2FIT_MAX_ECHO */
+    int32_t model;           /* T2FIT_MODEL_* */
+    const double *te_ms;     /* HOST pointer, [n_echo] echo times in ms = TEeffs (:386) */
+    double x0[3];            /* fit_params['initial_guess'] (k, T2, sigma)          :38,49,74,85 */
+    double lb[3], ub[3];     /* fit_params['param_bounds']                          :39,50,75,86 */
+    int32_t no_prior;        /* prior == False: bounds[0]=(S(TE0), no_prior_k_ub), bounds[1]=(no_prior_t2_lb,_ub) :243-245 */
+    double no_prior_k_ub;    /* 10000 */
+    double no_prior_t2_lb;   /* 10    */
+    double no_prior_t2_ub;   /* 2000  */
+    int32_t norm;            /* divide each row by its maximum (:237-240; utils/t2map_utils.py:74-79) */
+    int32_t max_iter;        /* cap on passes over the echoes per voxel; 0 = default */
+    float tol;               /* relative step tolerance; 0 = default */
+    int32_t init;            /* T2FIT_INIT_* */
+} t2fit_problem;
+
+/* Results.  Any pointer may be NULL (that output is skipped).  Parameter maps follow the reference's
+ * (k, T2, sigma) naming: t2 = x[1], k = x[0], sigma = x[2] (run_t2mapping.py:455-458). */
+typedef struct t2fit_outputs {
+    float *t2, *k, *sigma, *res; /* dense != 0: [n_vox] maps, only masked slots written (caller zero-fills,
+                                    as :415-418); dense == 0: [n_fit] compact */
+    uint8_t *status;             /* [n_fit] T2FIT_ST_* (== 0  <=>  convergence_flags[i], :450) */
+    int32_t *nit;                /* [n_fit] passes used (num_iterations_array, :451; counts differ from L-BFGS-B) */
+    float *fun;                  /* [n_fit] mean squared error at the solution (final_errors_array, :452) */
+    int32_t dense;
+    int64_t status_count[4];     /* OUT (host): voxels per status; filled when the call is synchronous
+                                    (T2FIT_MEM_HOST) or by t2fit_status_counts() */
+} t2fit_outputs;
+
+/* Bind this process to one GPU (one process per GPU; device = LOCAL_RANK) and create its context
+ * (streams, pinned staging, counters).  Idempotent for the same device. */
+int t2fit_init(int device);
+void t2fit_shutdown(void);
+const char *t2fit_last_error(void);
+int t2fit_abi_version(void);
+/* name, SM count and clock of the bound device; any pointer may be NULL */
+int t2fit_device_info(char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor);
+
+/* The fit: replaces pool.map(fit_voxel) (:430-443) and compute_residuals (:461) in one launch.
+ * stream: a cudaStream_t (0 = the library's own stream).  T2FIT_MEM_DEVICE calls only enqueue work. */
+int t2fit_run(const t2fit_problem *p, t2fit_outputs *o, void *stream);
+
+/* Status histogram of the most recent t2fit_run on `stream` (synchronises that stream). */
+int t2fit_status_counts(void *stream, int64_t counts[4]);
+
+/* mask = np.sum(mask4, axis=3) > 0 (:383-384) and mask_indices = np.where(mask.flat) (:412,421):
+ * masks is [n_vox, n_masks] uint8 (n_masks = 1 for a plain mask).  Writes ascending indices to
+ * idx_out (capacity n_vox) and the count to *n_out (host).  Device pointers; synchronises stream. */
+int t2fit_mask_indices(const uint8_t *masks, int64_t n_vox, int32_t n_masks, int64_t *idx_out, int64_t *n_out,
+                       void *stream);
+
+/* pack_masked_soa: gather rows mask_idx[i] of the AOS array into the echo-contiguous SOA buffer
+ * soa[e*ld + i] (device pointers).  The host-memory path of t2fit_run does this on the CPU side
+ * while staging; this is the device-resident variant. */
+int t2fit_pack_soa(const float *aos, int64_t n_vox, int32_t n_echo, const int64_t *mask_idx, int64_t n_fit, float *soa,
+                   int64_t ld, void *stream);
+
+/* scatter_maps: dense[mask_idx[i]] = compact[i] for n_maps float maps (run_t2mapping.py:455-458).
+ * Device pointers. */
+int t2fit_scatter(const float *const *compact, float *const *dense, int32_t n_maps, const int64_t *mask_idx,
+                  int64_t n_fit, void *stream);
+
+/* compute_residuals (utils/t2map_utils.py:62-89) as a stand-alone pass for callers that keep the
+ * reference's two-step structure: res_map[row] = sum_e (y_e - model_e(k_map, t2_map, sigma_map)) / E on
+ * the masked rows.  Uses echoes/mask_idx/n_fit/n_echo/te_ms/model/norm of *p (device pointers, AOS);
+ * maps are dense [n_vox] device arrays.  t2fit_run already returns the same residuals. */
+int t2fit_residuals(const t2fit_problem *p, const float *k_map, const float *t2_map, const float *sigma_map,
+                    float *res_map, void *stream);
+
+/* Algorithmic work of the shipped kernels, for roofline accounting: FLOPs and MUFU ops
+ * of one pass over the echoes, and the fixed per-voxel part. */
+int t2fit_work_model(int32_t model, int32_t n_echo, double *flop_per_pass, double *mufu_per_pass,
+                     double *flop_fixed, double *mufu_fixed, double *bytes_per_voxel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2FIT_H */

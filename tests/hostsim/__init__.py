@@ -1,0 +1,72 @@
+"""Build + call the host simulation of the solver core (TEST TOOL ONLY, see hostsim.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from fetal_t2mapping_b200 import _abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libt2fit_hostsim.so")
+SRC = os.path.join(HERE, "hostsim.cpp")
+DEPS = [SRC] + [os.path.join(HERE, "..", "..", "fetal_t2mapping_b200", "csrc", f)
+                for f in ("t2fit_core.cuh", "t2fit_consts.h")] + [os.path.join(HERE, "..", "..", "include", "t2fit.h")]
+
+
+def build(force=False):
+    if not force and os.path.isfile(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in DEPS):
+        return SO
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", SRC, "-o", SO, "-lm"]
+    subprocess.run(cmd, check=True, cwd=HERE)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.hostsim_fit.restype = C.c_int
+        _lib.hostsim_last_error.restype = C.c_char_p
+    return _lib
+
+
+def make_problem(rows, te, fit, x0, bounds, prior, norm, max_iter=0, tol=0.0, init=0):
+    rows = np.ascontiguousarray(rows, np.float32)
+    te = np.ascontiguousarray(te, np.float64)
+    p = _abi.Problem()
+    p.echoes = rows.ctypes.data
+    p.layout = _abi.LAYOUT_AOS
+    p.memory = _abi.MEM_HOST
+    p.n_vox = rows.shape[0]
+    p.n_fit = rows.shape[0]
+    p.n_echo = rows.shape[1]
+    p.model = _abi.MODELS[fit]
+    p.te_ms = te.ctypes.data_as(C.POINTER(C.c_double))
+    for i in range(len(x0)):
+        p.x0[i] = float(x0[i])
+        p.lb[i] = float(bounds[i][0])
+        p.ub[i] = float(bounds[i][1])
+    p.no_prior = 0 if prior else 1
+    p.no_prior_k_ub, p.no_prior_t2_lb, p.no_prior_t2_ub = 10000.0, 10.0, 2000.0
+    p.norm = int(bool(norm))
+    p.max_iter = max_iter
+    p.tol = tol
+    p.init = init
+    return p, (rows, te)
+
+
+def fit(rows, te, fit, x0, bounds, prior, norm=False, use_double=False, **kw):
+    p, keep = make_problem(rows, te, fit, x0, bounds, prior, norm, **kw)
+    m = keep[0].shape[0]
+    out = {n: np.zeros(m, np.float32) for n in ("k", "t2", "sigma", "res", "fun")}
+    out["nit"] = np.zeros(m, np.int32)
+    out["status"] = np.zeros(m, np.uint8)
+    rc = lib().hostsim_fit(C.byref(p), int(use_double), *[out[n].ctypes.data_as(C.c_void_p) for n in
+                                                         ("k", "t2", "sigma", "res", "fun", "nit", "status")])
+    if rc:
+        raise ValueError(lib().hostsim_last_error().decode())
+    return out

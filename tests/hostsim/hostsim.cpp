@@ -1,0 +1,58 @@
+// Host simulation of the device solver core -- TEST TOOL ONLY.
+//
+// Compiles fetal_t2mapping_b200/csrc/t2fit_core.cuh with g++ (T2FIT_HOSTSIM) so the `-m "not gpu"`
+// suite can unit-test the solver LOGIC (bracketing, active set, status codes) on a GPU-less CI box,
+// in float (as shipped) and in double (to separate algorithmic from rounding effects).
+// It is never linked into libt2fit, never imported by the fetal_t2mapping_b200 package, and is
+// not a fallback: the product fails loudly without a CUDA device.
+#define T2FIT_HOSTSIM 1
+#include "../../fetal_t2mapping_b200/csrc/t2fit_consts.h"
+
+#include <string.h>
+#include <string>
+
+using namespace t2fit;
+
+template <typename R, int MODEL, int E>
+static void run_rows(const float* rows, int64_t m, const FitConsts& c, float* k, float* t2, float* sigma, float* res,
+                     float* fun, int32_t* nit, uint8_t* status) {
+    for (int64_t i = 0; i < m; ++i) {
+        R y[E];
+        for (int e = 0; e < E; ++e) y[e] = R(rows[i * E + e]);
+        const VoxelFit f = fit_voxel<R, MODEL, E>(y, c, true);
+        k[i] = f.k; t2[i] = f.t2; sigma[i] = f.sigma; res[i] = f.res; fun[i] = f.fun;
+        nit[i] = f.nit; status[i] = (uint8_t)f.status;
+    }
+}
+
+template <typename R, int MODEL>
+static int dispatch_e(int n_echo, const float* rows, int64_t m, const FitConsts& c, float* k, float* t2, float* sigma,
+                      float* res, float* fun, int32_t* nit, uint8_t* status) {
+    switch (n_echo) {
+#define CASE(E) case E: run_rows<R, MODEL, E>(rows, m, c, k, t2, sigma, res, fun, nit, status); return 0;
+        CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+        CASE(13) CASE(14) CASE(15) CASE(16)
+#undef CASE
+        default: return T2FIT_EINVAL;
+    }
+}
+
+static std::string g_err;
+
+extern "C" const char* hostsim_last_error() { return g_err.c_str(); }
+
+// rows: AoS [n_fit, n_echo] taken from p->echoes (mask_idx ignored: pass gathered rows).
+extern "C" int hostsim_fit(const t2fit_problem* p, int use_double, float* k, float* t2, float* sigma, float* res,
+                           float* fun, int32_t* nit, uint8_t* status) {
+    FitConsts c;
+    memset(&c, 0, sizeof(c));
+    int rc = make_consts(*p, c, g_err);
+    if (rc) return rc;
+    const bool mono = p->model == T2FIT_MODEL_GAUSSIAN;
+    if (use_double) {
+        return mono ? dispatch_e<double, kMono2>(p->n_echo, p->echoes, p->n_fit, c, k, t2, sigma, res, fun, nit, status)
+                    : dispatch_e<double, kFloor3>(p->n_echo, p->echoes, p->n_fit, c, k, t2, sigma, res, fun, nit, status);
+    }
+    return mono ? dispatch_e<float, kMono2>(p->n_echo, p->echoes, p->n_fit, c, k, t2, sigma, res, fun, nit, status)
+                : dispatch_e<float, kFloor3>(p->n_echo, p->echoes, p->n_fit, c, k, t2, sigma, res, fun, nit, status);
+}

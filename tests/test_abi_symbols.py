@@ -1,0 +1,71 @@
+"""The C-ABI library loads and exports every symbol include/t2fit.h declares; without a GPU it fails loudly."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from tests.conftest import ROOT
+from fetal_t2mapping_b200 import _abi, build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build_lib()
+    return _abi.load_library()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "t2fit.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(t2fit_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    names = declared_symbols()
+    assert len(names) >= 10
+    bound = {n for n, _, _ in _abi.SYMBOLS}
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/t2fit.h but not exported"
+        assert n in bound, f"{n} has no ctypes signature in _abi.SYMBOLS"
+    assert lib.t2fit_abi_version() == _abi.ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    # sizes computed from the C declaration (LP64): guards against drift between t2fit.h and _abi.py
+    assert C.sizeof(_abi.Problem) == 8 + 4 + 4 + 8 + 8 + 8 + 8 + 4 + 4 + 8 + 3 * 8 * 3 + 4 + 4 + 3 * 8 + 4 + 4 + 4 + 4
+    assert C.sizeof(_abi.Outputs) == 7 * 8 + 8 + 4 * 8
+
+
+def test_library_contains_sm100a_sass_only():
+    out = os.popen(f"cuobjdump -lelf {_abi.LIB_PATH} 2>/dev/null").read()
+    if not out.strip():
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(?!100a)\d+", out)
+
+
+def test_no_gpu_means_loud_failure(lib):
+    """There is no CPU fallback: without a device init reports ENODEVICE and compute calls ENOTINIT."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    assert lib.t2fit_init(0) == -2
+    assert b"no CPU implementation" in lib.t2fit_last_error()
+    p, o = _abi.Problem(), _abi.Outputs()
+    assert lib.t2fit_run(C.byref(p), C.byref(o), None) == -3
+    import numpy as np
+    import fetal_t2mapping_b200 as t2
+    with pytest.raises(_abi.T2FitError):
+        t2.fit_voxels_batch(np.ones((4, 3), np.float32), None, [1.0, 2.0, 3.0], "gaussian", t2.preset("gaussian")[1])
+
+
+def test_work_model_is_pure_and_consistent(lib):
+    import fetal_t2mapping_b200 as t2
+    a, b = t2.work_model("gaussian", 5), t2.work_model("gaussian", 10)
+    assert a["bytes_per_voxel"] == 5 * 4 + 12 + 1
+    assert b["flop_per_pass"] > a["flop_per_pass"] and t2.work_model("gaussian_rician", 5)["flop_per_pass"] > a["flop_per_pass"]
