@@ -13,7 +13,7 @@ namespace t2fit {
 
 constexpr int kDefaultMaxIterMono = 24;
 constexpr int kDefaultMaxIterFloor = 64;
-constexpr float kDefaultTolMono = 1e-4f;
+constexpr float kDefaultTolMono = 2e-3f;
 constexpr float kDefaultTolFloor = 1e-5f;
 
 inline int n_params(int model) { return model == T2FIT_MODEL_GAUSSIAN ? 2 : 3; }

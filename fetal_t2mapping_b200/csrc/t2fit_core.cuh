@@ -115,62 +115,75 @@ T2_HD R loglinear_rate(const R (&y)[E], const FitConsts& c) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// mono-exponential, 2 parameters (k, r).  k enters linearly, so every pass over the echoes yields
-// the 2x2 normal equations for ANY k:
+// mono-exponential, 2 parameters (k, r).  k enters linearly, so one pass over the echoes yields the
+// 2x2 normal equations for ANY k:
 //     A = sum u^2   B = sum y u   C = sum te u^2   D = sum te y u   F = sum te^2 u^2 ,  u = exp(-te r)
 //     J^T J = [[A, -kC], [-kC, k^2 F]]      J^T res = [B - kA,  -k (D - kC)]
-// The k-row is solved exactly (k = clamp(B/A)), the r-row by its Schur complement (k free) or its
-// own diagonal (k on a bound): a projected Gauss-Newton step, safeguarded by the sign bracket of
-// the reduced gradient g(r) = k (D - kC) and accelerated by the secant of g once two nearby
-// evaluations exist.  One MUFU.EX2 per echo per pass.
+// The k-row is solved exactly, k*(r) = clamp(B/A, kl, ku); what remains is the 1-D root of the reduced
+// gradient g(r) = k (D - kC) on [r_lo, r_hi].  Its Gauss-Newton slope is the Schur complement
+// k^2 (F - C^2/A) (k free) or k^2 F (k on a bound); with one more sum H = sum te^2 y u the exact slope
+//     g'(r) = k (2kF - H) - (D - 2kC)^2 / A      (second term only while k is free)
+// is available, so the iteration is a safeguarded Newton method (quadratic convergence): sign
+// bracket of g, regime-aware step across the kink where k*(r) meets a bound, geometric expansion
+// towards an unevaluated box bound, bisection when steps stop shrinking.  One MUFU.EX2 per echo per
+// pass.  The iteration stops WITHOUT a verifying pass once a genuine Newton step is below `tol`
+// (the error after the step is O(tol^2)); the epilogue evaluates k at the final r.
 // ---------------------------------------------------------------------------------------------
 template <typename R>
-struct MonoSums { R A, B, C, D, F; };
+struct MonoSums { R A, B, C, D, F, H; };
 
 template <typename R, int E>
 T2_HD MonoSums<R> mono_pass(const R (&y)[E], const FitConsts& c, R r) {
-    MonoSums<R> s{0, 0, 0, 0, 0};
+    MonoSums<R> s{0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const R u = fast_ex2(R(c.nte2[e]) * r);
         const R tu = R(c.te[e]) * u;
+        const R ty = R(c.te[e]) * y[e];
         s.A += u * u;
         s.B += y[e] * u;
         s.C += tu * u;
-        s.D += tu * y[e];
+        s.D += ty * u;
         s.F += tu * tu;
+        s.H += ty * tu;
     }
     return s;
 }
 
+template <typename R> T2_HD R fdiv(R a, R b) { return a * fast_rcp(b); }
+
 template <typename R, int E>
-T2_HD void solve_mono2(const R (&y)[E], const FitConsts& c, R kl, R ku, R r0, R& k_out, R& r_out, int& nit_out,
-                       int& status_out, bool lane_valid) {
+T2_HD void solve_mono2(const R (&y)[E], const FitConsts& c, R kl, R ku, R r0, R& r_out, int& nit_out, int& status_out,
+                       bool lane_valid) {
     const R r_lo = R(c.r_lo), r_hi = R(c.r_hi), tol = R(c.tol);
     R a = r_lo, b = r_hi;             // sign bracket of g:  g(a) < 0 < g(b) once evaluated
     bool ha = false, hb = false;      // bracket end has been evaluated (otherwise it is the box bound)
-    R r = r0, r_prev = 0, g_prev = 0;
-    int q_prev = 2;                   // regime of the previous evaluation (2 = none yet)
+    R r = r0;
     int run_len = 0;                  // consecutive steps towards a bracket end that is still the box bound
-    R k = 0;
+    R dx1 = r_hi, dx2 = r_hi;         // magnitudes of the last two steps (stagnation guard)
+    bool prev_small = false;
     int nit = 0;
-    int phase = lane_valid ? 0 : 2;   // 0 iterating, 1 this pass verifies convergence, 2 done
+    bool done = !lane_valid;
     int status = kOk;
     const int max_pass = c.max_iter;
     for (int it = 0; it < max_pass; ++it) {
-        if (!warp_any(phase != 2)) break;                 // convergence vote: whole warp leaves together
+        if (!warp_any(!done)) break;                      // convergence vote: whole warp leaves together
         const MonoSums<R> s = mono_pass<R, E>(y, c, r);
-        if (phase != 2) {
+        if (!done) {
+            ++nit;
             const R inv_a = s.A > R(0) ? fast_rcp(s.A) : R(0);
             const R kf = s.B * inv_a;                               // unconstrained linear parameter k*(r)
             const R dkf = (R(2) * kf * s.C - s.D) * inv_a;          // d k*/dr
             const int q = (kf <= kl) ? -1 : ((kf >= ku) ? 1 : 0);   // regime: k on lower bound / free / upper
-            k = clampr(kf, kl, ku);
-            // reduced gradient (1/2 d cost/dr at k) and Gauss-Newton curvature in the current regime:
-            // Schur complement of the 2x2 normal equations when k is free, the rr entry when k is fixed
-            const R g = k * (s.D - k * s.C);
-            const R h = k * k * (s.F - (q == 0 ? s.C * s.C * inv_a : R(0)));
-            R dr = (h > R(0)) ? -g / h : R(0);
+            const R k = clampr(kf, kl, ku);
+            const R g = k * (s.D - k * s.C);                        // 1/2 d cost/dr at k*(r)
+            const R schur = (q == 0) ? inv_a : R(0);
+            const R h_gn = k * k * (s.F - s.C * s.C * schur);       // Gauss-Newton slope (>= 0)
+            const R w2 = s.D - R(2) * k * s.C;
+            const R h_ex = k * (R(2) * k * s.F - s.H) - w2 * w2 * schur;   // exact slope g'(r)
+            const bool newton = h_ex > R(0.25) * h_gn;
+            const R h = newton ? h_ex : h_gn;
+            R dr = (h > R(0)) ? -fdiv(g, h) : R(0);
             // does the step cross the kink where k*(r) meets a bound?  then minimise the piecewise
             // quadratic model: other regime's step if it lands beyond the kink, else the kink itself
             const R kf_new = kf + dkf * dr;
@@ -179,55 +192,56 @@ T2_HD void solve_mono2(const R (&y)[E], const FitConsts& c, R kl, R ku, R r0, R&
             if (cross) {
                 const int qb = (q != 0) ? q : q_new;                // the bound involved
                 const R kb = qb < 0 ? kl : ku;
-                const R r_kink = r + (kb - kf) / dkf;
+                const R r_kink = r + fdiv(kb - kf, dkf);
                 const bool to_free = (q != 0);
                 const R k2 = to_free ? kf : kb;
                 const R g2 = k2 * (s.D - k2 * s.C);
                 const R h2 = k2 * k2 * (s.F - (to_free ? s.C * s.C * inv_a : R(0)));
-                const R r2 = (h2 > R(0)) ? r - g2 / h2 : r_kink;
+                const R r2 = (h2 > R(0)) ? r - fdiv(g2, h2) : r_kink;
                 const bool beyond = (dr > R(0)) ? (r2 > r_kink) : (r2 < r_kink);
                 dr = (beyond ? r2 : r_kink) - r;
             }
             R rn = r + dr;
 #ifdef T2FIT_TRACE
-            printf("it %d phase %d r %.9g T2 %.6f k %.6f q %d g %.6g h %.6g a %.6g b %.6g cross %d rn %.9g\n", it, phase,
-                   (double)r, 1.0 / (double)r, (double)k, q, (double)g, (double)h, (double)a, (double)b, (int)cross,
+            printf("it %d r %.9g T2 %.6f k %.6f q %d g %.6g hgn %.6g hex %.6g a %.6g b %.6g cross %d rn %.9g\n", it, (double)r,
+                   1.0 / (double)r, (double)k, q, (double)g, (double)h_gn, (double)h_ex, (double)a, (double)b, (int)cross,
                    (double)rn);
 #endif
             const bool at_lo = (r <= r_lo) && (g >= R(0));          // T2 on its upper bound, gradient outward
             const bool at_hi = (r >= r_hi) && (g <= R(0));          // T2 on its lower bound
-            const bool small = absr(rn - r) <= tol * r;
-            if (at_lo || at_hi || g == R(0) || (phase == 1 && small)) {
-                phase = 2;                                          // (k, r) is the evaluated point
+            if (at_lo || at_hi || g == R(0)) {
+                done = true;                                        // r is final
             } else if (it == max_pass - 1) {
-                phase = 2;
+                done = true;
                 status = kNotConverged;
             } else {
-                ++nit;
                 if (g > R(0)) { b = r; hb = true; } else { a = r; ha = true; }
+                bool guarded = cross;
                 if (ha && hb) {
                     run_len = 0;
-                    if (q_prev == q && !cross) {                    // root bracketed: secant of g within one regime
-                        const R rs = r - g * (r - r_prev) / (g - g_prev);
-                        const bool close = absr(r - r_prev) <= R(0.25) * r;
-                        if (close && rs > a && rs < b) rn = rs;
-                    }
-                } else if (q_prev != 2 && !cross) {                 // still walking towards an unevaluated bound:
+                    if (absr(rn - r) > R(0.5) * dx2) { rn = R(0.5) * (a + b); guarded = true; }   // steps not shrinking
+                } else if (it > 0 && !cross && absr(rn - r) > R(0.5) * dx1) {   // walking towards an unevaluated bound:
                     run_len = run_len < 4 ? run_len + 1 : 4;        // expand the step geometrically
                     rn = r + (rn - r) * R(1 << run_len);
+                    guarded = true;
                 }
                 if (!(rn > a && rn < b)) {                          // leave the bracket: bound or bisection
                     if (rn <= a) rn = ha ? R(0.5) * (a + b) : a;
                     else if (rn >= b) rn = hb ? R(0.5) * (a + b) : b;
                     else rn = R(0.5) * (a + b);
+                    guarded = true;
                 }
-                phase = (absr(rn - r) <= tol * r) ? 1 : 0;
-                r_prev = r; g_prev = g; q_prev = q;
+                const bool small = absr(rn - r) <= tol * r;
+                // a genuine Newton step below tol: error after it is O(tol^2) -> accept rn unevaluated.
+                // Gauss-Newton / guarded small steps need a second small step in a row.
+                if (small && ((newton && !guarded) || prev_small)) done = true;
+                prev_small = small;
+                dx2 = dx1; dx1 = absr(rn - r);
                 r = rn;
             }
         }
     }
-    k_out = k; r_out = r; nit_out = nit; status_out = status;
+    r_out = r; nit_out = nit; status_out = status;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -407,7 +421,7 @@ T2_HD VoxelFit fit_voxel(R (&y)[E], const FitConsts& c, bool lane_valid) {
     int nit = 0, st = kOk;
     if (MODEL == kMono2) {
         const R r0 = (c.init_mode == kInitPreset) ? R(c.r_x0) : loglinear_rate<R, E>(yy, c);
-        solve_mono2<R, E>(yy, c, kl_s, ku_s, r0, k, r, nit, st, run);
+        solve_mono2<R, E>(yy, c, kl_s, ku_s, r0, r, nit, st, run);
     } else {
         R r0 = R(c.r_x0), k0 = R(c.x0[0]), s0 = R(c.x0[2]), cost = 0;
         if (c.init_mode != kInitPreset) {
@@ -418,9 +432,10 @@ T2_HD VoxelFit fit_voxel(R (&y)[E], const FitConsts& c, bool lane_valid) {
         solve_floor3<R, E>(yy, c, kl_s, ku_s, k0, r0, s0, k, r, s, cost, nit, st, run);
     }
     R t2;
-    if (status == kOk) {
+    const bool solved = (status == kOk);
+    if (solved) {
         status = st;
-        t2 = R(1) / r;
+        t2 = fast_rcp(r);
         if (r <= R(c.r_lo)) t2 = R(c.ub[1]);
         if (r >= R(c.r_hi)) t2 = R(c.lb[1]);
     } else {
@@ -433,14 +448,24 @@ T2_HD VoxelFit fit_voxel(R (&y)[E], const FitConsts& c, bool lane_valid) {
         nit = 0;
         if (status == kBadBounds) { k = t2 = R(NAN); if (MODEL != kMono2) s = R(NAN); }
     }
-    // residual epilogue on the stored (float32) parameters, as compute_residuals does
-    const float kf = float(k), t2f = float(t2), sf = float(s);
-    const R rr = R(1) / R(t2f);
+    // epilogue on the stored (float32) T2, as compute_residuals does: decay factors once, then (mono)
+    // the linear parameter k = clamp(B/A) at exactly this T2, then the residual sums
+    const float t2f = float(t2), sf = float(s);
+    const R rr = fast_rcp(R(t2f));
+    R u[E];
+    R sa = 0, sb = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        u[e] = fast_ex2(R(c.nte2[e]) * rr);
+        sa += u[e] * u[e];
+        sb += y[e] * u[e];
+    }
+    if (MODEL == kMono2 && solved) k = clampr(sa > R(0) ? fdiv(sb, sa) : R(0), kl, ku);
+    const float kf = float(k);
     R rsum = 0, csum = 0;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        const R u = fast_ex2(R(c.nte2[e]) * rr);
-        R pred = R(kf) * u;
+        R pred = R(kf) * u[e];
         if (MODEL != kMono2) {
             const R w = pred * pred + R(sf) * R(sf);
             pred = w > R(0) ? w * fast_rsqrt(w) : R(0);

@@ -627,7 +627,7 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     if (p->memory == T2FIT_MEM_HOST) return run_host(c, *p, *o, fc);
     if (p->memory != T2FIT_MEM_DEVICE) return fail(T2FIT_EINVAL, "bad memory kind");
 
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
     CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), st));
     KernelIO io{};
     io.echoes = p->echoes; io.idx = p->mask_idx; io.ld = p->ld; io.n_fit = p->n_fit;
@@ -641,7 +641,7 @@ int t2fit_status_counts(void* stream, int64_t counts[4]) {
     Context* c = g_ctx;
     if (!c) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
     if (!counts) return fail(T2FIT_EINVAL, "NULL counts");
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
     CU_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     for (int s = 0; s < 4; ++s) counts[s] = (int64_t)c->h_counts[s];
@@ -655,7 +655,7 @@ int t2fit_mask_indices(const uint8_t* masks, int64_t n_vox, int32_t n_masks, int
     if (!masks || !idx_out || !n_out || n_vox < 0 || n_masks < 1) return fail(T2FIT_EINVAL, "bad mask arguments");
     if (n_vox == 0) { *n_out = 0; return T2FIT_OK; }
     CU_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
     const int64_t tiles = (n_vox + kMaskTile - 1) / kMaskTile;
     if (tiles > 0x7fffffffLL) return fail(T2FIT_EINVAL, "volume too large");
     if (tiles > c->tiles_cap) {
@@ -684,7 +684,7 @@ int t2fit_pack_soa(const float* aos, int64_t n_vox, int32_t n_echo, const int64_
     if (!aos || !soa || n_echo < 1 || ld < n_fit || n_fit < 0 || n_vox < 0) return fail(T2FIT_EINVAL, "bad pack arguments");
     if (n_fit == 0) return T2FIT_OK;
     CU_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
     pack_soa_kernel<<<(unsigned)((n_fit + 255) / 256), 256, 0, st>>>(aos, n_echo, mask_idx, n_fit, soa, ld);
     CU_TRY(cudaGetLastError());
     return T2FIT_OK;
@@ -697,7 +697,7 @@ int t2fit_scatter(const float* const* compact, float* const* dense, int32_t n_ma
     if (!compact || !dense || !mask_idx || n_maps < 1 || n_maps > 4 || n_fit < 0) return fail(T2FIT_EINVAL, "bad scatter arguments");
     if (n_fit == 0) return T2FIT_OK;
     CU_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
     ScatterArgs a{};
     a.n_maps = n_maps;
     for (int m = 0; m < n_maps; ++m) { a.src[m] = compact[m]; a.dst[m] = dense[m]; }
@@ -719,7 +719,7 @@ int t2fit_residuals(const t2fit_problem* p, const float* k_map, const float* t2_
     if (rc) return fail(rc, err);
     if (p->n_fit == 0) return T2FIT_OK;
     CU_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
     residual_kernel<<<(unsigned)((p->n_fit + 255) / 256), 256, 0, st>>>(fc, p->echoes, p->mask_idx, p->n_fit, p->model, k_map,
                                                                        t2_map, sigma_map, res_map);
     CU_TRY(cudaGetLastError());

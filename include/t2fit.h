@@ -107,7 +107,9 @@ int t2fit_abi_version(void);
 int t2fit_device_info(char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor);
 
 /* The fit: replaces pool.map(fit_voxel) (:430-443) and compute_residuals (:461) in one launch.
- * stream: a cudaStream_t (0 = the library's own stream).  T2FIT_MEM_DEVICE calls only enqueue work. */
+ * stream: a cudaStream_t (NULL = the legacy default stream, as everywhere in CUDA).  T2FIT_MEM_DEVICE
+ * calls only enqueue work on it; T2FIT_MEM_HOST calls ignore it (internal staging streams) and return
+ * when the results are in the caller's buffers. */
 int t2fit_run(const t2fit_problem *p, t2fit_outputs *o, void *stream);
 
 /* Status histogram of the most recent t2fit_run on `stream` (synchronises that stream). */

@@ -125,11 +125,19 @@ def test_edge_cases_failed_sets(gpu_lib, fit, prior):
 
 
 def test_norm_path(gpu_lib):
+    """--norm (run_t2mapping.py:237-240).  With a unit-max signal the reference's ftol=1e-6 acts on
+    max(|f|,1)=1, so the reference itself stops far from its minimiser; compare with the exact bounded
+    LSQ minimiser of the same normalised objective instead, and loosely with the reference."""
+    from oracle import fit_oracle as fo
     g = load_golden("norm_gaussian")
     o = run_rows(gpu_lib, g, True)
     assert (o["status"] == 0).all()
+    fp = fit_params_of(g)
+    ex = np.array([fo.fit_voxel_exact(i, "gaussian", fp, g["te"], g["rows"], True, True)[0] for i in range(120)])
+    rel_e = np.abs(o["t2"][:120] - ex[:, 1]) / ex[:, 1]
+    assert rel_e.max() <= T2_RTOL
     rel = np.abs(o["t2"] - g["ref_params"][:, 1]) / g["ref_params"][:, 1]
-    assert np.median(rel) < 1e-4 and (rel <= T2_RTOL).mean() >= 0.97
+    assert np.median(rel) < 5e-3
 
 
 def test_kat_notebook(gpu_lib):
@@ -209,7 +217,7 @@ def test_full_size_c2_properties(gpu_lib):
     # scale-free first-order optimality: |g_i| * param_i / (2 * sum y^2), projected on the box
     s = 2 * (rows ** 2).sum(1)
     kl = rows[:, 0]
-    pg_k = np.where((k <= kl * (1 + 1e-6)) & (gk > 0), 0, np.where((k >= 1e4) & (gk < 0), 0, gk))
+    pg_k = np.where((k <= kl + 1e-6 * np.abs(kl) + 1e-9) & (gk > 0), 0, np.where((k >= 1e4) & (gk < 0), 0, gk))
     pg_t = np.where((t2 <= 10) & (gt > 0), 0, np.where((t2 >= 2000) & (gt < 0), 0, gt))
     opt = np.maximum(np.abs(pg_k * k), np.abs(pg_t * t2)) / s
     assert np.quantile(opt, 0.999) < 2e-5 and opt.max() < 2e-3, (np.quantile(opt, 0.999), opt.max())
