@@ -133,19 +133,18 @@ template <typename R>
 struct MonoSums { R A, B, C, D, F, H; };
 
 template <typename R, int E>
-T2_HD MonoSums<R> mono_pass(const R (&y)[E], const FitConsts& c, R r) {
+T2_HD MonoSums<R> mono_pass(const R (&y)[E], const R (&ty)[E], const FitConsts& c, R r) {
     MonoSums<R> s{0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
+    for (int e = 0; e < E; ++e) {                 // per echo: FMUL, MUFU.EX2, FMUL, 6 FFMA
         const R u = fast_ex2(R(c.nte2[e]) * r);
         const R tu = R(c.te[e]) * u;
-        const R ty = R(c.te[e]) * y[e];
         s.A += u * u;
         s.B += y[e] * u;
         s.C += tu * u;
-        s.D += ty * u;
+        s.D += ty[e] * u;
         s.F += tu * tu;
-        s.H += ty * tu;
+        s.H += ty[e] * tu;
     }
     return s;
 }
@@ -156,6 +155,9 @@ template <typename R, int E>
 T2_HD void solve_mono2(const R (&y)[E], const FitConsts& c, R kl, R ku, R r0, R& r_out, int& nit_out, int& status_out,
                        bool lane_valid) {
     const R r_lo = R(c.r_lo), r_hi = R(c.r_hi), tol = R(c.tol);
+    R ty[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) ty[e] = R(c.te[e]) * y[e];
     R a = r_lo, b = r_hi;             // sign bracket of g:  g(a) < 0 < g(b) once evaluated
     bool ha = false, hb = false;      // bracket end has been evaluated (otherwise it is the box bound)
     R r = r0;
@@ -168,76 +170,100 @@ T2_HD void solve_mono2(const R (&y)[E], const FitConsts& c, R kl, R ku, R r0, R&
     const int max_pass = c.max_iter;
     for (int it = 0; it < max_pass; ++it) {
         if (!warp_any(!done)) break;                      // convergence vote: whole warp leaves together
-        const MonoSums<R> s = mono_pass<R, E>(y, c, r);
+        const MonoSums<R> s = mono_pass<R, E>(y, ty, c, r);
         if (!done) {
             ++nit;
-            const R inv_a = s.A > R(0) ? fast_rcp(s.A) : R(0);
+            const R inv_a = fast_rcp(s.A);
             const R kf = s.B * inv_a;                               // unconstrained linear parameter k*(r)
-            const R dkf = (R(2) * kf * s.C - s.D) * inv_a;          // d k*/dr
-            const int q = (kf <= kl) ? -1 : ((kf >= ku) ? 1 : 0);   // regime: k on lower bound / free / upper
             const R k = clampr(kf, kl, ku);
-            const R g = k * (s.D - k * s.C);                        // 1/2 d cost/dr at k*(r)
-            const R schur = (q == 0) ? inv_a : R(0);
-            const R h_gn = k * k * (s.F - s.C * s.C * schur);       // Gauss-Newton slope (>= 0)
-            const R w2 = s.D - R(2) * k * s.C;
-            const R h_ex = k * (R(2) * k * s.F - s.H) - w2 * w2 * schur;   // exact slope g'(r)
+            const bool free = (kf > kl) && (kf < ku);               // regime: k free / on a bound
+            const R schur = free ? inv_a : R(0);
+            const R kc = k * s.C;
+            const R w = s.D - kc;
+            const R g = k * w;                                      // 1/2 d cost/dr at k*(r)
+            const R w2 = w - kc;                                    // D - 2kC
+            const R h_gn = (k * k) * (s.F - s.C * (s.C * schur));   // Gauss-Newton slope (>= 0)
+            const R h_ex = k * ((k + k) * s.F - s.H) - (w2 * w2) * schur;   // exact slope g'(r)
             const bool newton = h_ex > R(0.25) * h_gn;
             const R h = newton ? h_ex : h_gn;
-            R dr = (h > R(0)) ? -fdiv(g, h) : R(0);
-            // does the step cross the kink where k*(r) meets a bound?  then minimise the piecewise
-            // quadratic model: other regime's step if it lands beyond the kink, else the kink itself
+            const R dr = (h > R(0)) ? -(g * fast_rcp(h)) : R(0);
+            const R dkf = -(w2 * inv_a);                            // d k*/dr
             const R kf_new = kf + dkf * dr;
-            const int q_new = (kf_new <= kl) ? -1 : ((kf_new >= ku) ? 1 : 0);
-            const bool cross = (q_new != q) && (dkf != R(0));
-            if (cross) {
-                const int qb = (q != 0) ? q : q_new;                // the bound involved
-                const R kb = qb < 0 ? kl : ku;
-                const R r_kink = r + fdiv(kb - kf, dkf);
-                const bool to_free = (q != 0);
-                const R k2 = to_free ? kf : kb;
-                const R g2 = k2 * (s.D - k2 * s.C);
-                const R h2 = k2 * k2 * (s.F - (to_free ? s.C * s.C * inv_a : R(0)));
-                const R r2 = (h2 > R(0)) ? r - fdiv(g2, h2) : r_kink;
-                const bool beyond = (dr > R(0)) ? (r2 > r_kink) : (r2 < r_kink);
-                dr = (beyond ? r2 : r_kink) - r;
-            }
-            R rn = r + dr;
+            const bool free_new = (kf_new > kl) && (kf_new < ku);
+            const R adr = absr(dr);
+            const bool brk = ha && hb;
+            // the plain case: interior point, genuine Newton step, same regime after the step, step inside the
+            // bracket and shrinking -- everything else goes through the guarded path below
+            const bool interior = (r > r_lo) && (r < r_hi);
+            const R a_n = (g > R(0)) ? a : r, b_n = (g > R(0)) ? r : b;
+            const R rn_p = r + dr;
+            const bool plain = newton && interior && (free == free_new) && (rn_p > a_n) && (rn_p < b_n) &&
+                               (brk ? !(adr > R(0.5) * dx2) : !(it > 0 && adr > R(0.5) * dx1)) && (it < max_pass - 1);
 #ifdef T2FIT_TRACE
-            printf("it %d r %.9g T2 %.6f k %.6f q %d g %.6g hgn %.6g hex %.6g a %.6g b %.6g cross %d rn %.9g\n", it, (double)r,
-                   1.0 / (double)r, (double)k, q, (double)g, (double)h_gn, (double)h_ex, (double)a, (double)b, (int)cross,
-                   (double)rn);
+            printf("it %d r %.9g T2 %.6f k %.6f free %d g %.6g hgn %.6g hex %.6g a %.6g b %.6g plain %d rn %.9g\n", it,
+                   (double)r, 1.0 / (double)r, (double)k, (int)free, (double)g, (double)h_gn, (double)h_ex, (double)a,
+                   (double)b, (int)plain, (double)rn_p);
 #endif
-            const bool at_lo = (r <= r_lo) && (g >= R(0));          // T2 on its upper bound, gradient outward
-            const bool at_hi = (r >= r_hi) && (g <= R(0));          // T2 on its lower bound
-            if (at_lo || at_hi || g == R(0)) {
-                done = true;                                        // r is final
-            } else if (it == max_pass - 1) {
-                done = true;
-                status = kNotConverged;
-            } else {
-                if (g > R(0)) { b = r; hb = true; } else { a = r; ha = true; }
-                bool guarded = cross;
-                if (ha && hb) {
-                    run_len = 0;
-                    if (absr(rn - r) > R(0.5) * dx2) { rn = R(0.5) * (a + b); guarded = true; }   // steps not shrinking
-                } else if (it > 0 && !cross && absr(rn - r) > R(0.5) * dx1) {   // walking towards an unevaluated bound:
-                    run_len = run_len < 4 ? run_len + 1 : 4;        // expand the step geometrically
-                    rn = r + (rn - r) * R(1 << run_len);
-                    guarded = true;
-                }
-                if (!(rn > a && rn < b)) {                          // leave the bracket: bound or bisection
-                    if (rn <= a) rn = ha ? R(0.5) * (a + b) : a;
-                    else if (rn >= b) rn = hb ? R(0.5) * (a + b) : b;
-                    else rn = R(0.5) * (a + b);
-                    guarded = true;
-                }
-                const bool small = absr(rn - r) <= tol * r;
-                // a genuine Newton step below tol: error after it is O(tol^2) -> accept rn unevaluated.
-                // Gauss-Newton / guarded small steps need a second small step in a row.
-                if (small && ((newton && !guarded) || prev_small)) done = true;
+            if (plain) {
+                a = a_n; b = b_n;
+                if (g > R(0)) hb = true; else ha = true;
+                run_len = 0;
+                const bool small = adr <= tol * r;
+                done = small;             // Newton step below tol: the error after it is O(tol^2)
                 prev_small = small;
-                dx2 = dx1; dx1 = absr(rn - r);
-                r = rn;
+                dx2 = dx1; dx1 = adr;
+                r = rn_p;
+            } else {
+                const bool at_lo = (r <= r_lo) && (g >= R(0));      // T2 on its upper bound, gradient outward
+                const bool at_hi = (r >= r_hi) && (g <= R(0));      // T2 on its lower bound
+                if (at_lo || at_hi || g == R(0)) {
+                    done = true;                                    // r is final
+                } else if (it == max_pass - 1) {
+                    done = true;
+                    status = kNotConverged;
+                } else {
+                    // does the step cross the kink where k*(r) meets a bound?  then minimise the piecewise
+                    // quadratic model: other regime's step if it lands beyond the kink, else the kink itself
+                    R rn = rn_p;
+                    const int q = (kf <= kl) ? -1 : ((kf >= ku) ? 1 : 0);
+                    const int q_new = (kf_new <= kl) ? -1 : ((kf_new >= ku) ? 1 : 0);
+                    const bool cross = (q_new != q) && (dkf != R(0));
+                    if (cross) {
+                        const int qb = (q != 0) ? q : q_new;        // the bound involved
+                        const R kb = qb < 0 ? kl : ku;
+                        const R r_kink = r + fdiv(kb - kf, dkf);
+                        const bool to_free = (q != 0);
+                        const R k2 = to_free ? kf : kb;
+                        const R g2 = k2 * (s.D - k2 * s.C);
+                        const R h2 = k2 * k2 * (s.F - (to_free ? s.C * s.C * inv_a : R(0)));
+                        const R r2 = (h2 > R(0)) ? r - fdiv(g2, h2) : r_kink;
+                        const bool beyond = (dr > R(0)) ? (r2 > r_kink) : (r2 < r_kink);
+                        rn = beyond ? r2 : r_kink;
+                    }
+                    a = a_n; b = b_n;
+                    if (g > R(0)) hb = true; else ha = true;
+                    bool guarded = cross;
+                    if (ha && hb) {
+                        run_len = 0;
+                        if (absr(rn - r) > R(0.5) * dx2) { rn = R(0.5) * (a + b); guarded = true; }   // steps not shrinking
+                    } else if (it > 0 && !cross && absr(rn - r) > R(0.5) * dx1) {   // walking towards an unevaluated bound:
+                        run_len = run_len < 4 ? run_len + 1 : 4;                    // expand the step geometrically
+                        rn = r + (rn - r) * R(1 << run_len);
+                        guarded = true;
+                    }
+                    if (!(rn > a && rn < b)) {                      // leave the bracket: bound or bisection
+                        if (rn <= a) rn = ha ? R(0.5) * (a + b) : a;
+                        else if (rn >= b) rn = hb ? R(0.5) * (a + b) : b;
+                        else rn = R(0.5) * (a + b);
+                        guarded = true;
+                    }
+                    const bool small = absr(rn - r) <= tol * r;
+                    // Gauss-Newton / guarded small steps need a second small step in a row
+                    if (small && ((newton && !guarded) || prev_small)) done = true;
+                    prev_small = small;
+                    dx2 = dx1; dx1 = absr(rn - r);
+                    r = rn;
+                }
             }
         }
     }
@@ -390,46 +416,44 @@ template <typename R, int MODEL, int E>
 T2_HD VoxelFit fit_voxel(R (&y)[E], const FitConsts& c, bool lane_valid) {
     VoxelFit out;
     const R y0_raw = y[0];
-    bool finite = true;
-    R ymax = y[0];
+    R fin = 0;                                              // 0 if every echo is finite, NaN otherwise
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        finite = finite && finite_r(y[e]);
-        ymax = rmax(ymax, y[e]);
-    }
+    for (int e = 0; e < E; ++e) fin += y[e] * R(0);
     if (c.norm) {                                           // run_t2mapping.py:237-240
-        const R inv = R(1) / ymax;
+        R ymax = y[0];
 #pragma unroll
-        for (int e = 0; e < E; ++e) y[e] *= inv;
+        for (int e = 1; e < E; ++e) ymax = rmax(ymax, y[e]);
+        const R inv = fast_rcp(ymax);
+        fin = 0;
 #pragma unroll
-        for (int e = 0; e < E; ++e) finite = finite && finite_r(y[e]);
+        for (int e = 0; e < E; ++e) { y[e] *= inv; fin += y[e] * R(0); }
     }
     const R kl = c.no_prior ? y0_raw : R(c.lb[0]);          // run_t2mapping.py:243-245
     const R ku = R(c.ub[0]);
     int status = kOk;
     if (c.no_prior && (y0_raw > ku)) status = kBadBounds;   // scipy: "An upper bound is less than ..."
-    else if (!finite) status = kNonFinite;
-    const bool run = lane_valid && status == kOk;
-
-    // sanitise the registers of lanes that do not run so the shared loop stays finite
-    R yy[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) yy[e] = run ? y[e] : R(1);
-    const R kl_s = run ? kl : R(0), ku_s = run ? ku : R(1);
+    else if (!(fin == R(0))) status = kNonFinite;
+    const bool run = lane_valid && status == kOk;           // lanes that do not run start as `done`
 
     R k = 0, r = R(c.r_x0), s = 0;
     int nit = 0, st = kOk;
     if (MODEL == kMono2) {
-        const R r0 = (c.init_mode == kInitPreset) ? R(c.r_x0) : loglinear_rate<R, E>(yy, c);
-        solve_mono2<R, E>(yy, c, kl_s, ku_s, r0, r, nit, st, run);
+        const R r0 = (c.init_mode == kInitPreset) ? R(c.r_x0) : loglinear_rate<R, E>(y, c);
+        solve_mono2<R, E>(y, c, kl, ku, r0, r, nit, st, run);
     } else {
         R r0 = R(c.r_x0), k0 = R(c.x0[0]), s0 = R(c.x0[2]), cost = 0;
         if (c.init_mode != kInitPreset) {
-            r0 = loglinear_rate<R, E>(yy, c);
-            const MonoSums<R> ms = mono_pass<R, E>(yy, c, r0);
-            k0 = ms.A > R(0) ? ms.B / ms.A : k0;
+            r0 = loglinear_rate<R, E>(y, c);
+            R sa = 0, sb = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const R u = fast_ex2(R(c.nte2[e]) * r0);
+                sa += u * u;
+                sb += y[e] * u;
+            }
+            k0 = sa > R(0) ? fdiv(sb, sa) : k0;
         }
-        solve_floor3<R, E>(yy, c, kl_s, ku_s, k0, r0, s0, k, r, s, cost, nit, st, run);
+        solve_floor3<R, E>(y, c, kl, ku, k0, r0, s0, k, r, s, cost, nit, st, run);
     }
     R t2;
     const bool solved = (status == kOk);

@@ -1,0 +1,66 @@
+"""N > 1 host logic on CPU: world_size-2 gloo processes partition the masked list into slabs, fit their
+slab (stand-in fit function: the host simulation -- test tool, the product fit is CUDA) and all-gather."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fetal_t2mapping_b200 import distributed as D
+from tests.conftest import ROOT
+
+
+def test_slab_bounds_properties():
+    for n in (0, 1, 127, 128, 129, 1000, 1619960, 134217728):
+        for w in (1, 2, 3, 4, 8):
+            b = D.slab_bounds(n, w)
+            assert len(b) == w and b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))          # contiguous, ordered
+            assert all(x % 128 == 0 for x, _ in b[1:] if x < n)               # aligned interior cuts
+            sizes = [y - x for x, y in b]
+            assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 128 + (n % 128 > 0) * 128
+
+
+class _R:
+    pass
+
+
+def _hostsim_fit(rows, idx, te, fit, fp, prior, norm, **kw):
+    from tests import hostsim
+    o = hostsim.fit(rows[idx], te, fit, fp["initial_guess"], fp["param_bounds"], prior, norm)
+    r = _R()
+    r.t2, r.k, r.sigma, r.res, r.status = o["t2"], o["k"], o["sigma"], o["res"], o["status"]
+    return r
+
+
+def _worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fetal_t2mapping_b200 import presets, synth
+    y, mask, te, _ = synth.make_volume("c1", scale=0.3)
+    flat = y.reshape(-1, te.size)
+    idx = np.flatnonzero(mask.reshape(-1))
+    _, fp = presets.preset("gaussian", True)
+    out = D.fit_voxels_sharded(flat, idx, te, "gaussian", fp, prior=False, fit_fn=_hostsim_fit)
+    np.save(os.path.join(tmp, f"t2_{rank}.npy"), out["t2"].numpy())
+    np.save(os.path.join(tmp, f"st_{rank}.npy"), out["status"].numpy())
+    if rank == 0:
+        single = _hostsim_fit(flat, idx, te, "gaussian", fp, False, False)
+        np.save(os.path.join(tmp, "single.npy"), single.t2)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_fit_equals_single(tmp_path):
+    world, port = 2, 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    single = np.load(tmp_path / "single.npy")
+    for r in range(world):
+        got = np.load(tmp_path / f"t2_{r}.npy")
+        assert got.shape == single.shape and np.array_equal(got, single)      # every rank holds the full vector
+        assert (np.load(tmp_path / f"st_{r}.npy") == 0).all()

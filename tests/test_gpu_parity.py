@@ -222,7 +222,7 @@ def test_full_size_c2_properties(gpu_lib):
     opt = np.maximum(np.abs(pg_k * k), np.abs(pg_t * t2)) / s
     assert np.quantile(opt, 0.999) < 2e-5 and opt.max() < 2e-3, (np.quantile(opt, 0.999), opt.max())
     # (b) idempotence on the noise-free model of the fitted parameters (interior voxels)
-    inner = np.flatnonzero((t2 > 11) & (t2 < 1900) & (k > kl * 1.001) & (k < 9990))[:200000]
+    inner = np.flatnonzero((t2 > 11) & (t2 < 1900) & (k > 50) & (k > kl * 1.001) & (k < 9990))[:200000]
     clean = (k[inner, None] * u[inner]).astype(np.float32)
     fr = gpu_lib.fit_voxels_batch(torch.from_numpy(clean).cuda(), None, te, "gaussian",
                                   {"initial_guess": [650, 165], "param_bounds": [(0, 10000), (10, 2000)]}, prior=True)
