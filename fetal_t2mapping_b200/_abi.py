@@ -65,6 +65,7 @@ class Outputs(C.Structure):
         ("fun", C.c_void_p),
         ("dense", C.c_int32),
         ("status_count", C.c_int64 * 4),
+        ("zero_fill_mask", C.c_void_p),
     ]
 
 

@@ -285,19 +285,25 @@ def t2map_volume(t2w, mask, TEeffs, fit, fit_params, prior=True, norm=False, **k
     p, o = _abi.Problem(), _abi.Outputs()
     keep = [_fill_problem(p, fit, fit_params, TEeffs, prior, norm, kw.get("max_iter", 0), kw.get("tol", 0.0),
                           kw.get("init_mode", "loglinear"))]
+    fused_mask = None
     if _is_torch(t2w):
         import torch
         y = t2w.reshape(-1, n_echo)
         if y.dtype != torch.float32:
             y = y.float()
         y = y.contiguous()
-        idx = mask_indices_device(mask)
+        mk = mask if mask.dim() == 3 else (mask != 0).any(dim=3)                       # :383-384
+        mk = (mk if mk.dtype in (torch.bool, torch.uint8) else (mk != 0)).contiguous()
+        mk = mk.view(torch.uint8) if mk.dtype == torch.bool else mk
+        idx = mask_indices_device(mk)                                                   # :412,:421
         n_vox, m = y.shape[0], idx.numel()
-        maps = torch.zeros((4, n_vox), dtype=torch.float32, device=y.device)          # :415-418
+        # the four maps are zero-filled by the fit launch itself (fill-role blocks, :415-418)
+        maps = torch.empty((4, n_vox), dtype=torch.float32, device=y.device)
+        fused_mask = mk.reshape(-1)
         p.echoes, p.memory, p.mask_idx = y.data_ptr(), _abi.MEM_DEVICE, idx.data_ptr()
         stream = torch.cuda.current_stream(y.device).cuda_stream
         mp = [maps[i].data_ptr() for i in range(4)]
-        keep += [y, idx]
+        keep += [y, idx, mk]
     else:
         y = np.reshape(np.asarray(t2w), (-1, n_echo))
         if y.dtype != np.float32 or not y.flags.c_contiguous:
@@ -315,8 +321,10 @@ def t2map_volume(t2w, mask, TEeffs, fit, fit_params, prior=True, norm=False, **k
         raise ValueError(f"t2w has {n_echo} echoes, TEeffs has {p.n_echo}")
     p.layout, p.ld, p.n_vox, p.n_fit = _abi.LAYOUT_AOS, 0, n_vox, m
     o.t2, o.k, o.res = mp[0], mp[1], mp[3]
-    o.sigma = mp[2] if fit != "gaussian" else None
+    o.sigma = mp[2] if (fit != "gaussian" or fused_mask is not None) else None
     o.dense = 1
+    if fused_mask is not None:
+        o.zero_fill_mask = fused_mask.data_ptr()
     _run(lib, p, o, stream)
     if stream is not None:
         cnt = (C.c_int64 * 4)()

@@ -48,6 +48,12 @@ struct KernelIO {
     unsigned long long* counts;  // [4] per-status voxel counts of this launch (OK slot unused)
     int dense;                   // outputs indexed by idx[i] instead of i (status/nit/fun stay compact)
     int vec_ok;                  // AoS base pointer is 16-byte aligned
+    // fused zero-fill of the dense maps (np.zeros_like x4, run_t2mapping.py:415-418): blocks with the
+    // fill role zero every slot whose mask byte is 0 while the other blocks fit the masked slots
+    const uint8_t* mask;         // dense [n_vox] union mask (1 byte per voxel) or null = no fused fill
+    int64_t n_vox;
+    unsigned fill_blocks;        // F; grid = fit blocks + F, roles interleaved by block index
+    unsigned fit_blocks;         // B
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -90,10 +96,75 @@ __device__ __forceinline__ void load_soa(const float* __restrict__ base, int64_t
 // ------------------------------------------------------------------------------------------------
 // the fit kernel
 // ------------------------------------------------------------------------------------------------
+constexpr int kFillSpan = 16384;   // dense voxels zero-filled by one fill-role block (4 rounds of 256 thr x 16 voxels)
+
+// Fill role: zero the unmasked slots of the dense maps.  Per round a warp covers 512 consecutive voxels:
+// lane l loads mask word (j*32 + l) (4 voxels) and, if none of the 4 is masked, issues one coalesced
+// 16-byte store per map (512 B per warp instruction); mixed words fall back to per-voxel stores.
+// The sigma map of the 2-parameter model is never written by the fit, so it is zeroed unconditionally.
+template <int MODEL>
+__device__ __forceinline__ void fill_role(const KernelIO& io, unsigned fill_id) {
+    const int64_t span0 = (int64_t)fill_id * kFillSpan;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* maps[4] = {io.t2, io.k, io.res, io.sigma};
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int round = 0; round < kFillSpan / (kBlock * 16); ++round) {
+        const int64_t wbase = span0 + (int64_t)round * (kBlock * 16) + warp * 512;   // first voxel of this warp's chunk
+        if (wbase >= io.n_vox) break;
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t v = wbase + (int64_t)(j * 32 + lane) * 4;
+            w[j] = (v + 3 < io.n_vox) ? __ldg(reinterpret_cast<const uint32_t*>(io.mask + v)) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t v = wbase + (int64_t)(j * 32 + lane) * 4;
+            if (v + 3 < io.n_vox) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    float* dst = maps[m];
+                    if (!dst) continue;
+                    const bool all_slots = (m == 3 && MODEL == kMono2);      // sigma of the gaussian fit
+                    if (w[j] == 0u || all_slots) {
+                        *reinterpret_cast<float4*>(dst + v) = z4;
+                    } else if (w[j] != 0x01010101u) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (((w[j] >> (8 * q)) & 0xffu) == 0u) dst[v + q] = 0.f;
+                    }
+                }
+            } else {                                                          // ragged tail of the volume
+                for (int q = 0; q < 4; ++q) {
+                    const int64_t vv = v + q;
+                    if (vv < io.n_vox) {
+                        const bool unmasked = io.mask[vv] == 0;
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+                            if (maps[m] && (unmasked || (m == 3 && MODEL == kMono2))) maps[m][vv] = 0.f;
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int MODEL, int E, int LAYOUT>
 __global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ FitConsts c,
                                                      const __grid_constant__ KernelIO io) {
-    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    unsigned fit_id = blockIdx.x;
+    if (io.fill_blocks) {          // block role, interleaved so that both kinds of work progress together
+        const unsigned long long total = (unsigned long long)io.fill_blocks + io.fit_blocks;
+        const unsigned fills_before = (unsigned)(((unsigned long long)blockIdx.x * io.fill_blocks) / total);
+        const unsigned fills_after = (unsigned)(((unsigned long long)(blockIdx.x + 1) * io.fill_blocks) / total);
+        if (fills_after > fills_before) {
+            fill_role<MODEL>(io, fills_before);
+            return;
+        }
+        fit_id = blockIdx.x - fills_before;
+    }
+    const int64_t i = (int64_t)fit_id * kBlock + threadIdx.x;
     const bool valid = i < io.n_fit;
     const int64_t ii = valid ? i : io.n_fit - 1;       // whole warps stay in the solver (warp votes)
     const int64_t row = io.idx ? __ldg(io.idx + ii) : ii;
@@ -431,12 +502,19 @@ int ensure_slots(Context* c, int n_echo) {
 }
 
 int launch_fit(Context* c, const FitConsts& fc, KernelIO io, int model, int n_echo, int layout, cudaStream_t st) {
-    if (io.n_fit <= 0) return T2FIT_OK;
+    if (io.n_fit <= 0 && !io.mask) return T2FIT_OK;
     FitFn fn = pick_kernel(model, n_echo, layout);
     if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
-    const int64_t blocks = (io.n_fit + kBlock - 1) / kBlock;
-    if (blocks > 0x7fffffffLL) return fail(T2FIT_EINVAL, "n_fit too large for one launch");
-    fn<<<(unsigned)blocks, kBlock, 0, st>>>(fc, io);
+    const int64_t fit_blocks = (io.n_fit + kBlock - 1) / kBlock;
+    int64_t fill_blocks = 0;
+    if (io.mask && io.dense) fill_blocks = (io.n_vox + kFillSpan - 1) / kFillSpan;
+    else io.mask = nullptr;
+    if (fit_blocks + fill_blocks > 0x7fffffffLL) return fail(T2FIT_EINVAL, "problem too large for one launch");
+    if (fit_blocks + fill_blocks == 0) return T2FIT_OK;
+    io.fit_blocks = (unsigned)fit_blocks;
+    io.fill_blocks = (unsigned)fill_blocks;
+    if (io.n_fit <= 0) io.n_fit = 0;
+    fn<<<(unsigned)(fit_blocks + fill_blocks), kBlock, 0, st>>>(fc, io);
     CU_TRY(cudaGetLastError());
     return T2FIT_OK;
 }
@@ -628,12 +706,21 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     if (p->memory != T2FIT_MEM_DEVICE) return fail(T2FIT_EINVAL, "bad memory kind");
 
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
-    CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), st));
     KernelIO io{};
     io.echoes = p->echoes; io.idx = p->mask_idx; io.ld = p->ld; io.n_fit = p->n_fit;
     io.t2 = o->t2; io.k = o->k; io.sigma = o->sigma; io.res = o->res; io.fun = o->fun; io.nit = o->nit;
     io.status = o->status; io.counts = c->d_counts; io.dense = o->dense;
     io.vec_ok = (reinterpret_cast<uintptr_t>(p->echoes) % 16) == 0;
+    if (o->dense && o->zero_fill_mask) {
+        // fused np.zeros_like (:415-418): needs 4-byte aligned mask and 16-byte aligned maps
+        bool ok = (reinterpret_cast<uintptr_t>(o->zero_fill_mask) % 4) == 0;
+        float* mp[4] = {o->t2, o->k, o->sigma, o->res};
+        for (float* q : mp) ok = ok && (reinterpret_cast<uintptr_t>(q) % 16) == 0;
+        if (!ok) return fail(T2FIT_EINVAL, "zero_fill_mask needs a 4-byte aligned mask and 16-byte aligned maps");
+        io.mask = o->zero_fill_mask;
+        io.n_vox = p->n_vox;
+        io.sigma = o->sigma;   // zeroed by the fill role even for the 2-parameter model
+    }
     return launch_fit(c, fc, io, p->model, p->n_echo, p->layout, st);
 }
 
@@ -646,6 +733,7 @@ int t2fit_status_counts(void* stream, int64_t counts[4]) {
     CU_TRY(cudaStreamSynchronize(st));
     for (int s = 0; s < 4; ++s) counts[s] = (int64_t)c->h_counts[s];
     counts[0] = -1;  // OK count = n_fit - sum(others); the caller knows n_fit
+    CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), st));   // counts are "since the last query"
     return T2FIT_OK;
 }
 

@@ -95,6 +95,11 @@ typedef struct t2fit_outputs {
     int32_t dense;
     int64_t status_count[4];     /* OUT (host): voxels per status; filled when the call is synchronous
                                     (T2FIT_MEM_HOST) or by t2fit_status_counts() */
+    const uint8_t *zero_fill_mask; /* device calls with dense != 0 only: the [n_vox] uint8 mask (1 byte per voxel,
+                                    nonzero = masked, consistent with mask_idx).  When given, the same launch
+                                    also zero-fills every unmasked slot of the four maps (np.zeros_like, :415-418)
+                                    -- and all of sigma for the 2-parameter model -- so the caller need not
+                                    pre-zero them.  NULL = caller zero-fills. */
 } t2fit_outputs;
 
 /* Bind this process to one GPU (one process per GPU; device = LOCAL_RANK) and create its context
@@ -112,7 +117,8 @@ int t2fit_device_info(char *name, int name_len, int *sm_count, int *cc_major, in
  * when the results are in the caller's buffers. */
 int t2fit_run(const t2fit_problem *p, t2fit_outputs *o, void *stream);
 
-/* Status histogram of the most recent t2fit_run on `stream` (synchronises that stream). */
+/* Status histogram of the device-memory t2fit_run calls enqueued on `stream` since the previous query
+ * (synchronises that stream, then resets the counters). */
 int t2fit_status_counts(void *stream, int64_t counts[4]);
 
 /* mask = np.sum(mask4, axis=3) > 0 (:383-384) and mask_indices = np.where(mask.flat) (:412,421):

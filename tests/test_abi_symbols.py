@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_struct_layout_matches_header():
     # sizes computed from the C declaration (LP64): guards against drift between t2fit.h and _abi.py
     assert C.sizeof(_abi.Problem) == 8 + 4 + 4 + 8 + 8 + 8 + 8 + 4 + 4 + 8 + 3 * 8 * 3 + 4 + 4 + 3 * 8 + 4 + 4 + 4 + 4
-    assert C.sizeof(_abi.Outputs) == 7 * 8 + 8 + 4 * 8
+    assert C.sizeof(_abi.Outputs) == 7 * 8 + 8 + 4 * 8 + 8
 
 
 def test_library_contains_sm100a_sass_only():

@@ -236,3 +236,47 @@ def test_full_size_c2_properties(gpu_lib):
                                         procs=4)
     rel = np.abs(t2[pick] - p[:, 1]) / p[:, 1]
     assert ok.all() and (rel <= T2_RTOL).mean() >= 0.995
+
+
+@pytest.mark.parametrize("fit", ["gaussian", "gaussian_rician"])
+@pytest.mark.parametrize("shape", [(13, 11, 7), (40, 37, 29), (64, 64, 5)])
+def test_fused_zero_fill_ragged_volumes(gpu_lib, fit, shape):
+    """The fill-role blocks of the fit launch must zero every unmasked slot (and all of sigma for the
+    2-parameter model) whatever the volume size, starting from NaN-poisoned maps, and must never touch a
+    masked slot; mask bytes other than 1 count as masked."""
+    import ctypes as C
+    import torch
+    from fetal_t2mapping_b200 import _abi
+    from fetal_t2mapping_b200.api import _fill_problem
+    rng = np.random.default_rng(sum(shape))
+    n = int(np.prod(shape))
+    te = np.array([114.0, 150.0, 202.0, 299.0])
+    t2 = rng.uniform(60, 300, n)
+    y = (rng.uniform(300, 900, n)[:, None] * np.exp(-te[None, :] / t2[:, None]) + rng.normal(0, 5, (n, 4))).astype(np.float32)
+    mask = (rng.random(n) < 0.35).astype(np.uint8) * rng.choice([1, 255, 7], n).astype(np.uint8)
+    idx = np.flatnonzero(mask)
+    _, fp = gpu_lib.preset(fit, True)
+    lib = gpu_lib.init()
+    p, o = _abi.Problem(), _abi.Outputs()
+    keep = _fill_problem(p, fit, fp, te, False, False, 0, 0.0, "loglinear")
+    yd, idxd, md = torch.from_numpy(y).cuda(), torch.from_numpy(idx).cuda(), torch.from_numpy(mask).cuda()
+    maps = torch.full((4, n), float("nan"), device="cuda")
+    p.echoes, p.memory, p.layout, p.mask_idx, p.n_vox, p.n_fit = yd.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_AOS, idxd.data_ptr(), n, idx.size
+    o.t2, o.k, o.sigma, o.res, o.dense = maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), maps[3].data_ptr(), 1
+    o.zero_fill_mask = md.data_ptr()
+    rc = lib.t2fit_run(C.byref(p), C.byref(o), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.t2fit_last_error()
+    torch.cuda.synchronize()
+    m = maps.cpu().numpy()
+    assert not np.isnan(m).any()
+    off = mask == 0
+    assert (m[:, off] == 0).all()
+    ref = gpu_lib.fit_voxels_batch(yd, idxd, te, fit, fp, prior=False)
+    torch.cuda.synchronize()
+    assert np.array_equal(m[0, idx], ref.t2.cpu().numpy()) and np.array_equal(m[1, idx], ref.k.cpu().numpy())
+    assert np.array_equal(m[3, idx], ref.res.cpu().numpy())
+    if fit == "gaussian":
+        assert (m[2] == 0).all()
+    else:
+        assert np.array_equal(m[2, idx], ref.sigma.cpu().numpy())
+    del keep
