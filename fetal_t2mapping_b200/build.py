@@ -12,7 +12,7 @@ SOURCES = ["t2fit_kernels.cu"]
 HEADERS = ["t2fit_core.cuh", "t2fit_consts.h", os.path.join("..", "..", "include", "t2fit.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "--split-compile", "0"]
 
 
 def nvcc_path():

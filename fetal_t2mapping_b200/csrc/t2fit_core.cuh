@@ -80,6 +80,7 @@ T2_HD double fast_lg2(double x) { return log2(x); }
 T2_HD double fast_rcp(double x) { return 1.0 / x; }
 T2_HD double fast_rsqrt(double x) { return 1.0 / sqrt(x); }
 
+template <typename R> T2_HD R fdiv(R a, R b) { return a * fast_rcp(b); }
 template <typename R> T2_HD R rmin(R a, R b) { return a < b ? a : b; }
 template <typename R> T2_HD R rmax(R a, R b) { return a > b ? a : b; }
 template <typename R> T2_HD R clampr(R x, R lo, R hi) { return rmin(rmax(x, lo), hi); }
@@ -109,7 +110,7 @@ T2_HD R loglinear_rate(const R (&y)[E], const FitConsts& c) {
     }
     const R den = sw * swtt - swt * swt;
     const R num = sw * swtl - swt * swl;
-    R r = -R(0.69314718055994531) * num / den;      // slope is in log2 units per ms
+    R r = -R(0.69314718055994531) * num * fast_rcp(den);      // slope is in log2 units per ms
     if (!(den > R(0)) || !finite_r(r)) r = R(c.r_x0);
     return clampr(r, R(c.r_lo), R(c.r_hi));
 }
@@ -148,8 +149,6 @@ T2_HD MonoSums<R> mono_pass(const R (&y)[E], const R (&ty)[E], const FitConsts& 
     }
     return s;
 }
-
-template <typename R> T2_HD R fdiv(R a, R b) { return a * fast_rcp(b); }
 
 template <typename R, int E>
 T2_HD void solve_mono2(const R (&y)[E], const FitConsts& c, R kl, R ku, R r0, R& r_out, int& nit_out, int& status_out,
@@ -330,10 +329,10 @@ T2_HD void solve_floor3(const R (&y)[E], const FitConsts& c, R kl, R ku, R k0, R
             R step_rel = 0, dec_rel = 1;
             if (!have_cur || t.cost <= cur.cost) {          // accept (the first pass always)
                 if (have_cur) {
-                    dec_rel = (cur.cost - t.cost) / rmax(t.cost, R(1e-30));
+                    dec_rel = (cur.cost - t.cost) * fast_rcp(rmax(t.cost, R(1e-30)));
 #pragma unroll
                     for (int i = 0; i < 3; ++i)
-                        step_rel = rmax(step_rel, absr(xt[i] - x[i]) / rmax(absr(x[i]), R(1e-12)));
+                        step_rel = rmax(step_rel, absr(xt[i] - x[i]) * fast_rcp(rmax(absr(x[i]), R(1e-12))));
                     lambda = rmax(lambda * R(0.2), R(1e-9));
                     ++nit;
                 }
@@ -387,7 +386,7 @@ T2_HD void solve_floor3(const R (&y)[E], const FitConsts& c, R kl, R ku, R k0, R
                 for (int i = 0; i < 3; ++i) {
                     R xn = clampr(x[i] + d[i], lo[i], hi[i]);
                     if (!finite_r(xn)) xn = x[i];
-                    prop = rmax(prop, absr(xn - x[i]) / rmax(absr(x[i]), R(1e-12)));
+                    prop = rmax(prop, absr(xn - x[i]) * fast_rcp(rmax(absr(x[i]), R(1e-12))));
                     xt[i] = xn;
                 }
                 if (all_fixed || prop <= tol * R(0.01)) {

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -23,6 +24,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "t2fit_consts.h"
@@ -52,8 +54,9 @@ struct KernelIO {
     // fill role zero every slot whose mask byte is 0 while the other blocks fit the masked slots
     const uint8_t* mask;         // dense [n_vox] union mask (1 byte per voxel) or null = no fused fill
     int64_t n_vox;
-    unsigned fill_blocks;        // F; grid = fit blocks + F, roles interleaved by block index
+    unsigned fill_blocks;        // F; grid = fit blocks + F, roles interleaved by block index (one-shot kernel)
     unsigned fit_blocks;         // B
+    int fill_vec;                // maps are 16-byte aligned: 16-byte zero stores, else scalar
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -97,56 +100,85 @@ __device__ __forceinline__ void load_soa(const float* __restrict__ base, int64_t
 // the fit kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kFillSpan = 16384;   // dense voxels zero-filled by one fill-role block (4 rounds of 256 thr x 16 voxels)
+constexpr int kFillChunk = 512;    // dense voxels zero-filled by one warp per fill round (32 lanes x 4 words x 4 voxels)
 
-// Fill role: zero the unmasked slots of the dense maps.  Per round a warp covers 512 consecutive voxels:
-// lane l loads mask word (j*32 + l) (4 voxels) and, if none of the 4 is masked, issues one coalesced
-// 16-byte store per map (512 B per warp instruction); mixed words fall back to per-voxel stores.
+// Zero-fill of one warp chunk [wbase, wbase+512) of the dense maps (np.zeros_like x4, run_t2mapping.py:415-418).
+// Lane l owns mask word (j*32 + l), j = 0..3 (4 voxels each); if none of the 4 is masked it issues one
+// coalesced 16-byte store per map (512 B per warp instruction); mixed words fall back to per-voxel stores.
 // The sigma map of the 2-parameter model is never written by the fit, so it is zeroed unconditionally.
+__device__ __forceinline__ void fill_load_words(const KernelIO& io, int64_t wbase, int lane, uint32_t (&w)[4]) {
+    if (wbase >= 0 && wbase + kFillChunk <= io.n_vox) {              // whole chunk in range (warp-uniform)
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(io.mask + wbase) + lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = __ldg(p + j * 32);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t v = wbase + (int64_t)(j * 32 + lane) * 4;
+            w[j] = (wbase >= 0 && v + 3 < io.n_vox) ? __ldg(reinterpret_cast<const uint32_t*>(io.mask + v)) : 0xffffffffu;
+        }
+    }
+}
+
+// slow path of one mask word: per-voxel zero stores (mask boundary, unaligned maps, ragged tail)
+template <int MODEL>
+__device__ __forceinline__ void fill_word_slow(const KernelIO& io, int64_t v, uint32_t w) {
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+        const int64_t vv = v + q;
+        if (vv >= io.n_vox) break;
+        const bool unmasked = (v + 3 < io.n_vox) ? (((w >> (8 * q)) & 0xffu) == 0u) : (io.mask[vv] == 0);
+        if (unmasked) {
+            if (io.t2) io.t2[vv] = 0.f;
+            if (io.k) io.k[vv] = 0.f;
+            if (io.res) io.res[vv] = 0.f;
+        }
+        if (io.sigma && (unmasked || MODEL == kMono2)) io.sigma[vv] = 0.f;
+    }
+}
+
+template <int MODEL>
+__device__ __forceinline__ void fill_store_chunk(const KernelIO& io, int64_t wbase, int lane, const uint32_t (&w)[4]) {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool fast = io.fill_vec && (wbase + kFillChunk <= io.n_vox) && io.t2 && io.k && io.res && io.sigma;   // warp-uniform
+    if (fast) {
+        const int64_t off = wbase + lane * 4;
+        float4* p0 = reinterpret_cast<float4*>(io.t2 + off);
+        float4* p1 = reinterpret_cast<float4*>(io.k + off);
+        float4* p2 = reinterpret_cast<float4*>(io.res + off);
+        float4* p3 = reinterpret_cast<float4*>(io.sigma + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                                 // +32 float4 per j: immediate offsets
+            if (MODEL == kMono2) p3[j * 32] = z4;                     // sigma of the gaussian fit: every slot
+            if (w[j] == 0u) {
+                p0[j * 32] = z4; p1[j * 32] = z4; p2[j * 32] = z4;
+                if (MODEL != kMono2) p3[j * 32] = z4;
+            }
+        }
+        // mask boundaries (rare): words with both masked and unmasked voxels
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j)
+            if (w[j] != 0u && w[j] != 0x01010101u) fill_word_slow<MODEL>(io, off + j * 128, w[j]);
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int64_t v = wbase + (int64_t)(j * 32 + lane) * 4;
+            if (v < io.n_vox) fill_word_slow<MODEL>(io, v, w[j]);
+        }
+    }
+}
+
 template <int MODEL>
 __device__ __forceinline__ void fill_role(const KernelIO& io, unsigned fill_id) {
     const int64_t span0 = (int64_t)fill_id * kFillSpan;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* maps[4] = {io.t2, io.k, io.res, io.sigma};
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int round = 0; round < kFillSpan / (kBlock * 16); ++round) {
-        const int64_t wbase = span0 + (int64_t)round * (kBlock * 16) + warp * 512;   // first voxel of this warp's chunk
+        const int64_t wbase = span0 + (int64_t)round * (kBlock * 16) + warp * kFillChunk;
         if (wbase >= io.n_vox) break;
         uint32_t w[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t v = wbase + (int64_t)(j * 32 + lane) * 4;
-            w[j] = (v + 3 < io.n_vox) ? __ldg(reinterpret_cast<const uint32_t*>(io.mask + v)) : 0xffffffffu;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t v = wbase + (int64_t)(j * 32 + lane) * 4;
-            if (v + 3 < io.n_vox) {
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    float* dst = maps[m];
-                    if (!dst) continue;
-                    const bool all_slots = (m == 3 && MODEL == kMono2);      // sigma of the gaussian fit
-                    if (w[j] == 0u || all_slots) {
-                        *reinterpret_cast<float4*>(dst + v) = z4;
-                    } else if (w[j] != 0x01010101u) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (((w[j] >> (8 * q)) & 0xffu) == 0u) dst[v + q] = 0.f;
-                    }
-                }
-            } else {                                                          // ragged tail of the volume
-                for (int q = 0; q < 4; ++q) {
-                    const int64_t vv = v + q;
-                    if (vv < io.n_vox) {
-                        const bool unmasked = io.mask[vv] == 0;
-#pragma unroll
-                        for (int m = 0; m < 4; ++m)
-                            if (maps[m] && (unmasked || (m == 3 && MODEL == kMono2))) maps[m][vv] = 0.f;
-                    }
-                }
-            }
-        }
+        fill_load_words(io, wbase, lane, w);
+        fill_store_chunk<MODEL>(io, wbase, lane, w);
     }
 }
 
@@ -192,6 +224,100 @@ __global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ Fit
         for (int s = 1; s < 4; ++s) {
             const unsigned m = __ballot_sync(0xffffffffu, st == s);
             if (m && (threadIdx.x & 31) == 0) atomicAdd(io.counts + s, (unsigned long long)__popc(m));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent variant: grid = SMs x resident blocks, every thread walks the masked list with a grid
+// stride.  Software pipeline per thread: the index of voxel t+2 and the echoes of voxel t+1 are in
+// flight while voxel t is being solved, and the zero-fill of the dense maps is spread over the same
+// iterations (each warp owns every W-th 512-voxel chunk), so the HBM-bound fill hides under the
+// compute-bound fit inside one instruction stream.
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int E, int LAYOUT>
+__global__ void __launch_bounds__(kBlock) fit_persistent_kernel(const __grid_constant__ FitConsts c,
+                                                                const __grid_constant__ KernelIO io) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    const int64_t gtid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t last = io.n_fit > 0 ? io.n_fit - 1 : 0;
+    int64_t n_iter = (io.n_fit + stride - 1) / stride;                 // identical for every thread
+    // fill schedule of this warp
+    const int64_t n_warps = stride >> 5, gwarp = gtid >> 5;
+    int64_t n_fill = 0;
+    if (io.mask) {
+        const int64_t chunks = (io.n_vox + kFillChunk - 1) / kFillChunk;
+        n_fill = chunks > gwarp ? (chunks - gwarp + n_warps - 1) / n_warps : 0;
+    }
+    int64_t fill_done = 0;
+    uint32_t wnext[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    if (n_fill > 0) fill_load_words(io, gwarp * kFillChunk, lane, wnext);
+    if (n_iter == 0) n_iter = 1;
+
+    // prologue of the voxel pipeline
+    auto slot_of = [&](int64_t i) -> int64_t {
+        const int64_t ic = i < io.n_fit ? i : last;
+        return (io.idx && io.n_fit > 0) ? __ldg(io.idx + ic) : ic;
+    };
+    int64_t row1 = slot_of(gtid), row2 = slot_of(gtid + stride);
+    float yn[E];
+    {
+        const int64_t ic = gtid < io.n_fit ? gtid : last;
+        if (io.n_fit > 0) {
+            if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row1, io.vec_ok != 0, yn);
+            else load_soa<E>(io.echoes, io.ld, ic, yn);
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) yn[e] = 1.f;
+        }
+    }
+    for (int64_t t = 0; t < n_iter; ++t) {
+        const int64_t i = gtid + t * stride;
+        const bool valid = i < io.n_fit;
+        const int64_t row = row1;
+        float y[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) y[e] = yn[e];
+        // issue the loads of the next two voxels
+        row1 = row2;
+        row2 = slot_of(i + 2 * stride);
+        if (t + 1 < n_iter) {
+            const int64_t inx = i + stride;
+            const int64_t ic = inx < io.n_fit ? inx : last;
+            if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row1, io.vec_ok != 0, yn);
+            else load_soa<E>(io.echoes, io.ld, ic, yn);
+        }
+        // zero-fill rounds due before this iteration (spread evenly over the n_iter iterations)
+        const int64_t due = ((t + 1) * n_fill + n_iter - 1) / n_iter;
+        while (fill_done < due) {
+            const int64_t wbase = (gwarp + fill_done * n_warps) * kFillChunk;
+            uint32_t w[4] = {wnext[0], wnext[1], wnext[2], wnext[3]};
+            ++fill_done;
+            if (fill_done < n_fill) fill_load_words(io, (gwarp + fill_done * n_warps) * kFillChunk, lane, wnext);
+            fill_store_chunk<MODEL>(io, wbase, lane, w);
+        }
+
+        const VoxelFit f = fit_voxel<float, MODEL, E>(y, c, valid);
+
+        if (valid) {
+            const int64_t o = io.dense ? row : i;
+            if (io.t2) io.t2[o] = f.t2;
+            if (io.k) io.k[o] = f.k;
+            if (MODEL != kMono2 && io.sigma) io.sigma[o] = f.sigma;
+            if (io.res) io.res[o] = f.res;
+            if (io.fun) io.fun[i] = f.fun;
+            if (io.nit) io.nit[i] = f.nit;
+            if (io.status) io.status[i] = (uint8_t)f.status;
+        }
+        const int st = valid ? f.status : 0;
+        const unsigned any_bad = __ballot_sync(0xffffffffu, st != 0);
+        if (any_bad && io.counts) {
+#pragma unroll
+            for (int s = 1; s < 4; ++s) {
+                const unsigned m = __ballot_sync(0xffffffffu, st == s);
+                if (m && lane == 0) atomicAdd(io.counts + s, (unsigned long long)__popc(m));
+            }
         }
     }
 }
@@ -361,6 +487,25 @@ FitFn pick_e(int n_echo) {
     }
 }
 
+template <int MODEL, int LAYOUT>
+FitFn pick_e_persistent(int n_echo) {
+    switch (n_echo) {
+#define T2_CASE(E) case E: return fit_persistent_kernel<MODEL, E, LAYOUT>;
+        T2_CASE(2) T2_CASE(3) T2_CASE(4) T2_CASE(5) T2_CASE(6) T2_CASE(7) T2_CASE(8) T2_CASE(9) T2_CASE(10)
+        T2_CASE(11) T2_CASE(12) T2_CASE(13) T2_CASE(14) T2_CASE(15) T2_CASE(16)
+#undef T2_CASE
+        default: return nullptr;       // E > 16: one-shot kernel only
+    }
+}
+
+FitFn pick_persistent(int model, int n_echo, int layout) {
+    if (model == T2FIT_MODEL_GAUSSIAN)
+        return layout == T2FIT_LAYOUT_AOS ? pick_e_persistent<kMono2, T2FIT_LAYOUT_AOS>(n_echo)
+                                          : pick_e_persistent<kMono2, T2FIT_LAYOUT_SOA>(n_echo);
+    return layout == T2FIT_LAYOUT_AOS ? pick_e_persistent<kFloor3, T2FIT_LAYOUT_AOS>(n_echo)
+                                      : pick_e_persistent<kFloor3, T2FIT_LAYOUT_SOA>(n_echo);
+}
+
 FitFn pick_kernel(int model, int n_echo, int layout) {
     if (model == T2FIT_MODEL_GAUSSIAN)
         return layout == T2FIT_LAYOUT_AOS ? pick_e<kMono2, T2FIT_LAYOUT_AOS>(n_echo) : pick_e<kMono2, T2FIT_LAYOUT_SOA>(n_echo);
@@ -460,6 +605,8 @@ struct Context {
     int64_t* d_total = nullptr;
     int64_t* h_total = nullptr;
     int64_t tiles_cap = 0;
+    std::mutex occ_mu;
+    std::unordered_map<const void*, int> occ;   // resident blocks per SM of each persistent kernel
 };
 
 Context* g_ctx = nullptr;
@@ -501,19 +648,54 @@ int ensure_slots(Context* c, int n_echo) {
     return T2FIT_OK;
 }
 
+// kernel variant: 0 = one-shot grid (one thread per voxel, fill-role blocks interleaved),
+//                 1 = persistent software-pipelined grid.  T2FIT_KERNEL=oneshot|persistent overrides.
+int kernel_variant() {
+    static int v = [] {
+        const char* e = getenv("T2FIT_KERNEL");
+        if (e && !strcmp(e, "oneshot")) return 0;
+        if (e && !strcmp(e, "persistent")) return 1;
+        return 1;
+    }();
+    return v;
+}
+
 int launch_fit(Context* c, const FitConsts& fc, KernelIO io, int model, int n_echo, int layout, cudaStream_t st) {
     if (io.n_fit <= 0 && !io.mask) return T2FIT_OK;
+    if (!(io.mask && io.dense)) io.mask = nullptr;
+    if (io.n_fit <= 0) io.n_fit = 0;
+    const int64_t fit_blocks = (io.n_fit + kBlock - 1) / kBlock;
+    FitFn pfn = kernel_variant() == 1 ? pick_persistent(model, n_echo, layout) : nullptr;
+    if (pfn) {
+        int occ = 0;
+        {
+            std::lock_guard<std::mutex> g(c->occ_mu);
+            auto it = c->occ.find((const void*)pfn);
+            if (it == c->occ.end()) {
+                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pfn, kBlock, 0));
+                c->occ[(const void*)pfn] = occ;
+            } else {
+                occ = it->second;
+            }
+        }
+        const int64_t resident = (int64_t)c->prop.multiProcessorCount * std::max(occ, 1);
+        int64_t want = fit_blocks;
+        if (io.mask) want = std::max<int64_t>(want, (io.n_vox + kFillChunk * (kBlock / 32) - 1) / (kFillChunk * (kBlock / 32)));
+        const int64_t grid = std::max<int64_t>(1, std::min(resident, want));
+        io.fit_blocks = (unsigned)grid;
+        io.fill_blocks = 0;
+        pfn<<<(unsigned)grid, kBlock, 0, st>>>(fc, io);
+        CU_TRY(cudaGetLastError());
+        return T2FIT_OK;
+    }
     FitFn fn = pick_kernel(model, n_echo, layout);
     if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
-    const int64_t fit_blocks = (io.n_fit + kBlock - 1) / kBlock;
     int64_t fill_blocks = 0;
-    if (io.mask && io.dense) fill_blocks = (io.n_vox + kFillSpan - 1) / kFillSpan;
-    else io.mask = nullptr;
+    if (io.mask) fill_blocks = (io.n_vox + kFillSpan - 1) / kFillSpan;
     if (fit_blocks + fill_blocks > 0x7fffffffLL) return fail(T2FIT_EINVAL, "problem too large for one launch");
     if (fit_blocks + fill_blocks == 0) return T2FIT_OK;
     io.fit_blocks = (unsigned)fit_blocks;
     io.fill_blocks = (unsigned)fill_blocks;
-    if (io.n_fit <= 0) io.n_fit = 0;
     fn<<<(unsigned)(fit_blocks + fill_blocks), kBlock, 0, st>>>(fc, io);
     CU_TRY(cudaGetLastError());
     return T2FIT_OK;
@@ -695,8 +877,9 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     std::string err;
     int rc = make_consts(*p, fc, err);
     if (rc) return fail(rc, err);
-    if (p->n_fit == 0) { memset(o->status_count, 0, sizeof(o->status_count)); return T2FIT_OK; }
-    if (!p->echoes) return fail(T2FIT_EINVAL, "echoes is NULL");
+    const bool fill_only = p->n_fit == 0 && p->memory == T2FIT_MEM_DEVICE && o->dense && o->zero_fill_mask;
+    if (p->n_fit == 0 && !fill_only) { memset(o->status_count, 0, sizeof(o->status_count)); return T2FIT_OK; }
+    if (!p->echoes && !fill_only) return fail(T2FIT_EINVAL, "echoes is NULL");
     if (p->layout != T2FIT_LAYOUT_AOS && p->layout != T2FIT_LAYOUT_SOA) return fail(T2FIT_EINVAL, "bad layout");
     if (p->layout == T2FIT_LAYOUT_SOA && p->ld < p->n_fit) return fail(T2FIT_EINVAL, "ld < n_fit");
     if (p->layout == T2FIT_LAYOUT_AOS && !p->mask_idx && p->n_fit > p->n_vox) return fail(T2FIT_EINVAL, "n_fit > n_vox");
@@ -713,10 +896,11 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     io.vec_ok = (reinterpret_cast<uintptr_t>(p->echoes) % 16) == 0;
     if (o->dense && o->zero_fill_mask) {
         // fused np.zeros_like (:415-418): needs 4-byte aligned mask and 16-byte aligned maps
-        bool ok = (reinterpret_cast<uintptr_t>(o->zero_fill_mask) % 4) == 0;
+        if ((reinterpret_cast<uintptr_t>(o->zero_fill_mask) % 4) != 0)
+            return fail(T2FIT_EINVAL, "zero_fill_mask must be 4-byte aligned");
         float* mp[4] = {o->t2, o->k, o->sigma, o->res};
-        for (float* q : mp) ok = ok && (reinterpret_cast<uintptr_t>(q) % 16) == 0;
-        if (!ok) return fail(T2FIT_EINVAL, "zero_fill_mask needs a 4-byte aligned mask and 16-byte aligned maps");
+        io.fill_vec = 1;
+        for (float* q : mp) if ((reinterpret_cast<uintptr_t>(q) % 16) != 0) io.fill_vec = 0;   // scalar zero stores
         io.mask = o->zero_fill_mask;
         io.n_vox = p->n_vox;
         io.sigma = o->sigma;   // zeroed by the fill role even for the 2-parameter model

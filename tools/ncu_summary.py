@@ -1,0 +1,30 @@
+"""Print the metrics that matter from an `ncu --page raw --csv` export."""
+import csv
+import sys
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__occupancy_limit_registers", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+        "smsp__warps_eligible.avg.per_cycle_active", "lts__t_sectors_op_write.sum", "lts__t_sectors_op_read.sum",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "sm__sass_thread_inst_executed_op_ffma_pred_on.sum", "smsp__sass_thread_inst_executed_op_fp32_pred_on.sum"]
+
+
+def main(path):
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        print("== ", r[hdr.index("Kernel Name")][:70], " grid", r[hdr.index("Grid Size")], " block", r[hdr.index("Block Size")])
+        for i, h in enumerate(hdr):
+            if h in WANT or "issue_stalled" in h and h.endswith("per_issue_active.ratio"):
+                print(f"  {h:86s} {units[i]:16s} {r[i]}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
