@@ -24,7 +24,6 @@
 #include <mutex>
 #include <string>
 #include <thread>
-#include <unordered_map>
 #include <vector>
 
 #include "t2fit_consts.h"
@@ -50,13 +49,6 @@ struct KernelIO {
     unsigned long long* counts;  // [4] per-status voxel counts of this launch (OK slot unused)
     int dense;                   // outputs indexed by idx[i] instead of i (status/nit/fun stay compact)
     int vec_ok;                  // AoS base pointer is 16-byte aligned
-    // fused zero-fill of the dense maps (np.zeros_like x4, run_t2mapping.py:415-418): blocks with the
-    // fill role zero every slot whose mask byte is 0 while the other blocks fit the masked slots
-    const uint8_t* mask;         // dense [n_vox] union mask (1 byte per voxel) or null = no fused fill
-    int64_t n_vox;
-    unsigned fill_blocks;        // F; grid = fit blocks + F, roles interleaved by block index (one-shot kernel)
-    unsigned fit_blocks;         // B
-    int fill_vec;                // maps are 16-byte aligned: 16-byte zero stores, else scalar
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -99,104 +91,76 @@ __device__ __forceinline__ void load_soa(const float* __restrict__ base, int64_t
 // ------------------------------------------------------------------------------------------------
 // the fit kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kFillSpan = 16384;   // dense voxels zero-filled by one fill-role block (4 rounds of 256 thr x 16 voxels)
-constexpr int kFillChunk = 512;    // dense voxels zero-filled by one warp per fill round (32 lanes x 4 words x 4 voxels)
+constexpr int kFillChunk = 512;    // dense voxels zero-filled by one warp per round (32 lanes x 4 words x 4 voxels)
 
-// Zero-fill of one warp chunk [wbase, wbase+512) of the dense maps (np.zeros_like x4, run_t2mapping.py:415-418).
-// Lane l owns mask word (j*32 + l), j = 0..3 (4 voxels each); if none of the 4 is masked it issues one
-// coalesced 16-byte store per map (512 B per warp instruction); mixed words fall back to per-voxel stores.
-// The sigma map of the 2-parameter model is never written by the fit, so it is zeroed unconditionally.
-__device__ __forceinline__ void fill_load_words(const KernelIO& io, int64_t wbase, int lane, uint32_t (&w)[4]) {
-    if (wbase >= 0 && wbase + kFillChunk <= io.n_vox) {              // whole chunk in range (warp-uniform)
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(io.mask + wbase) + lane;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = __ldg(p + j * 32);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t v = wbase + (int64_t)(j * 32 + lane) * 4;
-            w[j] = (wbase >= 0 && v + 3 < io.n_vox) ? __ldg(reinterpret_cast<const uint32_t*>(io.mask + v)) : 0xffffffffu;
-        }
+// ------------------------------------------------------------------------------------------------
+// zero_fill_kernel: np.zeros_like x4 (run_t2mapping.py:415-418) restricted to the slots the fit will
+// NOT write.  Runs on a side stream concurrently with fit_kernel (no ordering needed: the two kernels
+// write disjoint slots), so the HBM-bound fill hides under the compute-bound fit.
+// Persistent grid (a couple of blocks per SM); per round a warp covers 512 consecutive voxels: lane l
+// loads mask word (j*32+l), j = 0..3 (4 voxels each) and, where none of the 4 is masked, issues one
+// coalesced 16-byte store per map (512 B per warp instruction).  Words with both masked and unmasked
+// voxels (mask boundary), unaligned maps and the ragged tail take a per-voxel path.
+// SIGMA_ALL: the 2-parameter model never writes sigma, so that map is zeroed everywhere.
+// ------------------------------------------------------------------------------------------------
+struct FillArgs {
+    float* t2; float* k; float* res; float* sigma;   // any may be null
+    const uint8_t* mask;                            // [n_vox], nonzero = masked
+    int64_t n_vox;
+    int vec;                                        // every non-null map is 16-byte aligned
+};
+
+template <bool SIGMA_ALL>
+__device__ __forceinline__ void fill_voxel(const FillArgs& a, int64_t v, bool unmasked) {
+    if (unmasked) {
+        if (a.t2) a.t2[v] = 0.f;
+        if (a.k) a.k[v] = 0.f;
+        if (a.res) a.res[v] = 0.f;
     }
+    if (a.sigma && (unmasked || SIGMA_ALL)) a.sigma[v] = 0.f;
 }
 
-// slow path of one mask word: per-voxel zero stores (mask boundary, unaligned maps, ragged tail)
-template <int MODEL>
-__device__ __forceinline__ void fill_word_slow(const KernelIO& io, int64_t v, uint32_t w) {
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-        const int64_t vv = v + q;
-        if (vv >= io.n_vox) break;
-        const bool unmasked = (v + 3 < io.n_vox) ? (((w >> (8 * q)) & 0xffu) == 0u) : (io.mask[vv] == 0);
-        if (unmasked) {
-            if (io.t2) io.t2[vv] = 0.f;
-            if (io.k) io.k[vv] = 0.f;
-            if (io.res) io.res[vv] = 0.f;
-        }
-        if (io.sigma && (unmasked || MODEL == kMono2)) io.sigma[vv] = 0.f;
-    }
-}
-
-template <int MODEL>
-__device__ __forceinline__ void fill_store_chunk(const KernelIO& io, int64_t wbase, int lane, const uint32_t (&w)[4]) {
+template <bool SIGMA_ALL>
+__global__ void __launch_bounds__(256) zero_fill_kernel(const __grid_constant__ FillArgs a) {
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool fast = io.fill_vec && (wbase + kFillChunk <= io.n_vox) && io.t2 && io.k && io.res && io.sigma;   // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * 256) >> 5;
+    const int64_t full_chunks = a.n_vox / kFillChunk;
+    const bool fast = a.vec && a.t2 && a.k && a.res && a.sigma;
     if (fast) {
-        const int64_t off = wbase + lane * 4;
-        float4* p0 = reinterpret_cast<float4*>(io.t2 + off);
-        float4* p1 = reinterpret_cast<float4*>(io.k + off);
-        float4* p2 = reinterpret_cast<float4*>(io.res + off);
-        float4* p3 = reinterpret_cast<float4*>(io.sigma + off);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {                                 // +32 float4 per j: immediate offsets
-            if (MODEL == kMono2) p3[j * 32] = z4;                     // sigma of the gaussian fit: every slot
-            if (w[j] == 0u) {
-                p0[j * 32] = z4; p1[j * 32] = z4; p2[j * 32] = z4;
-                if (MODEL != kMono2) p3[j * 32] = z4;
+        for (int64_t c = gw; c < full_chunks; c += nw) {
+            const int64_t off = c * kFillChunk + lane * 4;
+            const uint32_t* pm = reinterpret_cast<const uint32_t*>(a.mask + c * kFillChunk) + lane;
+            uint32_t w0 = __ldg(pm), w1 = __ldg(pm + 32), w2 = __ldg(pm + 64), w3 = __ldg(pm + 96);
+            float4* p0 = reinterpret_cast<float4*>(a.t2 + off);
+            float4* p1 = reinterpret_cast<float4*>(a.k + off);
+            float4* p2 = reinterpret_cast<float4*>(a.res + off);
+            float4* p3 = reinterpret_cast<float4*>(a.sigma + off);
+#define T2_FILL_WORD(W, J)                                                                                  \
+            if (SIGMA_ALL) p3[(J) * 32] = z4;                                                               \
+            if ((W) == 0u) { p0[(J) * 32] = z4; p1[(J) * 32] = z4; p2[(J) * 32] = z4; if (!SIGMA_ALL) p3[(J) * 32] = z4; } \
+            else if ((W) != 0x01010101u) {                                                                  \
+                for (int q = 0; q < 4; ++q) fill_voxel<SIGMA_ALL>(a, off + (J) * 128 + q, (((W) >> (8 * q)) & 0xffu) == 0u); \
             }
-        }
-        // mask boundaries (rare): words with both masked and unmasked voxels
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j)
-            if (w[j] != 0u && w[j] != 0x01010101u) fill_word_slow<MODEL>(io, off + j * 128, w[j]);
-    } else {
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-            const int64_t v = wbase + (int64_t)(j * 32 + lane) * 4;
-            if (v < io.n_vox) fill_word_slow<MODEL>(io, v, w[j]);
+            T2_FILL_WORD(w0, 0) T2_FILL_WORD(w1, 1) T2_FILL_WORD(w2, 2) T2_FILL_WORD(w3, 3)
+#undef T2_FILL_WORD
         }
     }
+    // per-voxel path: everything if not `fast`, else only the ragged tail after the last full chunk
+    const int64_t v0 = fast ? full_chunks * kFillChunk : 0;
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x, nt = (int64_t)gridDim.x * 256;
+    for (int64_t v = v0 + t; v < a.n_vox; v += nt) fill_voxel<SIGMA_ALL>(a, v, a.mask[v] == 0);
 }
 
-template <int MODEL>
-__device__ __forceinline__ void fill_role(const KernelIO& io, unsigned fill_id) {
-    const int64_t span0 = (int64_t)fill_id * kFillSpan;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int round = 0; round < kFillSpan / (kBlock * 16); ++round) {
-        const int64_t wbase = span0 + (int64_t)round * (kBlock * 16) + warp * kFillChunk;
-        if (wbase >= io.n_vox) break;
-        uint32_t w[4];
-        fill_load_words(io, wbase, lane, w);
-        fill_store_chunk<MODEL>(io, wbase, lane, w);
-    }
+// resident blocks per SM the register allocator is asked to allow (256 threads each)
+constexpr int min_blocks(int model, int e) {
+    return model == kMono2 ? (e <= 6 ? 5 : e <= 12 ? 4 : e <= 16 ? 3 : 2) : (e <= 8 ? 4 : e <= 16 ? 3 : 2);
 }
 
 template <int MODEL, int E, int LAYOUT>
-__global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ FitConsts c,
+__global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const __grid_constant__ FitConsts c,
                                                      const __grid_constant__ KernelIO io) {
-    unsigned fit_id = blockIdx.x;
-    if (io.fill_blocks) {          // block role, interleaved so that both kinds of work progress together
-        const unsigned long long total = (unsigned long long)io.fill_blocks + io.fit_blocks;
-        const unsigned fills_before = (unsigned)(((unsigned long long)blockIdx.x * io.fill_blocks) / total);
-        const unsigned fills_after = (unsigned)(((unsigned long long)(blockIdx.x + 1) * io.fill_blocks) / total);
-        if (fills_after > fills_before) {
-            fill_role<MODEL>(io, fills_before);
-            return;
-        }
-        fit_id = blockIdx.x - fills_before;
-    }
-    const int64_t i = (int64_t)fit_id * kBlock + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool valid = i < io.n_fit;
     const int64_t ii = valid ? i : io.n_fit - 1;       // whole warps stay in the solver (warp votes)
     const int64_t row = io.idx ? __ldg(io.idx + ii) : ii;
@@ -224,100 +188,6 @@ __global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ Fit
         for (int s = 1; s < 4; ++s) {
             const unsigned m = __ballot_sync(0xffffffffu, st == s);
             if (m && (threadIdx.x & 31) == 0) atomicAdd(io.counts + s, (unsigned long long)__popc(m));
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// persistent variant: grid = SMs x resident blocks, every thread walks the masked list with a grid
-// stride.  Software pipeline per thread: the index of voxel t+2 and the echoes of voxel t+1 are in
-// flight while voxel t is being solved, and the zero-fill of the dense maps is spread over the same
-// iterations (each warp owns every W-th 512-voxel chunk), so the HBM-bound fill hides under the
-// compute-bound fit inside one instruction stream.
-// ------------------------------------------------------------------------------------------------
-template <int MODEL, int E, int LAYOUT>
-__global__ void __launch_bounds__(kBlock) fit_persistent_kernel(const __grid_constant__ FitConsts c,
-                                                                const __grid_constant__ KernelIO io) {
-    const int64_t stride = (int64_t)gridDim.x * kBlock;
-    const int64_t gtid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int64_t last = io.n_fit > 0 ? io.n_fit - 1 : 0;
-    int64_t n_iter = (io.n_fit + stride - 1) / stride;                 // identical for every thread
-    // fill schedule of this warp
-    const int64_t n_warps = stride >> 5, gwarp = gtid >> 5;
-    int64_t n_fill = 0;
-    if (io.mask) {
-        const int64_t chunks = (io.n_vox + kFillChunk - 1) / kFillChunk;
-        n_fill = chunks > gwarp ? (chunks - gwarp + n_warps - 1) / n_warps : 0;
-    }
-    int64_t fill_done = 0;
-    uint32_t wnext[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-    if (n_fill > 0) fill_load_words(io, gwarp * kFillChunk, lane, wnext);
-    if (n_iter == 0) n_iter = 1;
-
-    // prologue of the voxel pipeline
-    auto slot_of = [&](int64_t i) -> int64_t {
-        const int64_t ic = i < io.n_fit ? i : last;
-        return (io.idx && io.n_fit > 0) ? __ldg(io.idx + ic) : ic;
-    };
-    int64_t row1 = slot_of(gtid), row2 = slot_of(gtid + stride);
-    float yn[E];
-    {
-        const int64_t ic = gtid < io.n_fit ? gtid : last;
-        if (io.n_fit > 0) {
-            if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row1, io.vec_ok != 0, yn);
-            else load_soa<E>(io.echoes, io.ld, ic, yn);
-        } else {
-#pragma unroll
-            for (int e = 0; e < E; ++e) yn[e] = 1.f;
-        }
-    }
-    for (int64_t t = 0; t < n_iter; ++t) {
-        const int64_t i = gtid + t * stride;
-        const bool valid = i < io.n_fit;
-        const int64_t row = row1;
-        float y[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) y[e] = yn[e];
-        // issue the loads of the next two voxels
-        row1 = row2;
-        row2 = slot_of(i + 2 * stride);
-        if (t + 1 < n_iter) {
-            const int64_t inx = i + stride;
-            const int64_t ic = inx < io.n_fit ? inx : last;
-            if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row1, io.vec_ok != 0, yn);
-            else load_soa<E>(io.echoes, io.ld, ic, yn);
-        }
-        // zero-fill rounds due before this iteration (spread evenly over the n_iter iterations)
-        const int64_t due = ((t + 1) * n_fill + n_iter - 1) / n_iter;
-        while (fill_done < due) {
-            const int64_t wbase = (gwarp + fill_done * n_warps) * kFillChunk;
-            uint32_t w[4] = {wnext[0], wnext[1], wnext[2], wnext[3]};
-            ++fill_done;
-            if (fill_done < n_fill) fill_load_words(io, (gwarp + fill_done * n_warps) * kFillChunk, lane, wnext);
-            fill_store_chunk<MODEL>(io, wbase, lane, w);
-        }
-
-        const VoxelFit f = fit_voxel<float, MODEL, E>(y, c, valid);
-
-        if (valid) {
-            const int64_t o = io.dense ? row : i;
-            if (io.t2) io.t2[o] = f.t2;
-            if (io.k) io.k[o] = f.k;
-            if (MODEL != kMono2 && io.sigma) io.sigma[o] = f.sigma;
-            if (io.res) io.res[o] = f.res;
-            if (io.fun) io.fun[i] = f.fun;
-            if (io.nit) io.nit[i] = f.nit;
-            if (io.status) io.status[i] = (uint8_t)f.status;
-        }
-        const int st = valid ? f.status : 0;
-        const unsigned any_bad = __ballot_sync(0xffffffffu, st != 0);
-        if (any_bad && io.counts) {
-#pragma unroll
-            for (int s = 1; s < 4; ++s) {
-                const unsigned m = __ballot_sync(0xffffffffu, st == s);
-                if (m && lane == 0) atomicAdd(io.counts + s, (unsigned long long)__popc(m));
-            }
         }
     }
 }
@@ -487,25 +357,6 @@ FitFn pick_e(int n_echo) {
     }
 }
 
-template <int MODEL, int LAYOUT>
-FitFn pick_e_persistent(int n_echo) {
-    switch (n_echo) {
-#define T2_CASE(E) case E: return fit_persistent_kernel<MODEL, E, LAYOUT>;
-        T2_CASE(2) T2_CASE(3) T2_CASE(4) T2_CASE(5) T2_CASE(6) T2_CASE(7) T2_CASE(8) T2_CASE(9) T2_CASE(10)
-        T2_CASE(11) T2_CASE(12) T2_CASE(13) T2_CASE(14) T2_CASE(15) T2_CASE(16)
-#undef T2_CASE
-        default: return nullptr;       // E > 16: one-shot kernel only
-    }
-}
-
-FitFn pick_persistent(int model, int n_echo, int layout) {
-    if (model == T2FIT_MODEL_GAUSSIAN)
-        return layout == T2FIT_LAYOUT_AOS ? pick_e_persistent<kMono2, T2FIT_LAYOUT_AOS>(n_echo)
-                                          : pick_e_persistent<kMono2, T2FIT_LAYOUT_SOA>(n_echo);
-    return layout == T2FIT_LAYOUT_AOS ? pick_e_persistent<kFloor3, T2FIT_LAYOUT_AOS>(n_echo)
-                                      : pick_e_persistent<kFloor3, T2FIT_LAYOUT_SOA>(n_echo);
-}
-
 FitFn pick_kernel(int model, int n_echo, int layout) {
     if (model == T2FIT_MODEL_GAUSSIAN)
         return layout == T2FIT_LAYOUT_AOS ? pick_e<kMono2, T2FIT_LAYOUT_AOS>(n_echo) : pick_e<kMono2, T2FIT_LAYOUT_SOA>(n_echo);
@@ -605,8 +456,8 @@ struct Context {
     int64_t* d_total = nullptr;
     int64_t* h_total = nullptr;
     int64_t tiles_cap = 0;
-    std::mutex occ_mu;
-    std::unordered_map<const void*, int> occ;   // resident blocks per SM of each persistent kernel
+    cudaStream_t fill_stream = nullptr;      // side stream of the zero-fill kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 Context* g_ctx = nullptr;
@@ -648,56 +499,32 @@ int ensure_slots(Context* c, int n_echo) {
     return T2FIT_OK;
 }
 
-// kernel variant: 0 = one-shot grid (one thread per voxel, fill-role blocks interleaved),
-//                 1 = persistent software-pipelined grid.  T2FIT_KERNEL=oneshot|persistent overrides.
-int kernel_variant() {
-    static int v = [] {
-        const char* e = getenv("T2FIT_KERNEL");
-        if (e && !strcmp(e, "oneshot")) return 0;
-        if (e && !strcmp(e, "persistent")) return 1;
-        return 1;
-    }();
-    return v;
-}
-
 int launch_fit(Context* c, const FitConsts& fc, KernelIO io, int model, int n_echo, int layout, cudaStream_t st) {
-    if (io.n_fit <= 0 && !io.mask) return T2FIT_OK;
-    if (!(io.mask && io.dense)) io.mask = nullptr;
-    if (io.n_fit <= 0) io.n_fit = 0;
-    const int64_t fit_blocks = (io.n_fit + kBlock - 1) / kBlock;
-    FitFn pfn = kernel_variant() == 1 ? pick_persistent(model, n_echo, layout) : nullptr;
-    if (pfn) {
-        int occ = 0;
-        {
-            std::lock_guard<std::mutex> g(c->occ_mu);
-            auto it = c->occ.find((const void*)pfn);
-            if (it == c->occ.end()) {
-                CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pfn, kBlock, 0));
-                c->occ[(const void*)pfn] = occ;
-            } else {
-                occ = it->second;
-            }
-        }
-        const int64_t resident = (int64_t)c->prop.multiProcessorCount * std::max(occ, 1);
-        int64_t want = fit_blocks;
-        if (io.mask) want = std::max<int64_t>(want, (io.n_vox + kFillChunk * (kBlock / 32) - 1) / (kFillChunk * (kBlock / 32)));
-        const int64_t grid = std::max<int64_t>(1, std::min(resident, want));
-        io.fit_blocks = (unsigned)grid;
-        io.fill_blocks = 0;
-        pfn<<<(unsigned)grid, kBlock, 0, st>>>(fc, io);
-        CU_TRY(cudaGetLastError());
-        return T2FIT_OK;
-    }
+    if (io.n_fit <= 0) return T2FIT_OK;
     FitFn fn = pick_kernel(model, n_echo, layout);
     if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
-    int64_t fill_blocks = 0;
-    if (io.mask) fill_blocks = (io.n_vox + kFillSpan - 1) / kFillSpan;
-    if (fit_blocks + fill_blocks > 0x7fffffffLL) return fail(T2FIT_EINVAL, "problem too large for one launch");
-    if (fit_blocks + fill_blocks == 0) return T2FIT_OK;
-    io.fit_blocks = (unsigned)fit_blocks;
-    io.fill_blocks = (unsigned)fill_blocks;
-    fn<<<(unsigned)(fit_blocks + fill_blocks), kBlock, 0, st>>>(fc, io);
+    const int64_t blocks = (io.n_fit + kBlock - 1) / kBlock;
+    if (blocks > 0x7fffffffLL) return fail(T2FIT_EINVAL, "n_fit too large for one launch");
+    fn<<<(unsigned)blocks, kBlock, 0, st>>>(fc, io);
     CU_TRY(cudaGetLastError());
+    return T2FIT_OK;
+}
+
+// zero-fill of the dense maps on the side stream, forked from and joined back into `st`
+int launch_zero_fill(Context* c, const FillArgs& fa, bool sigma_all, cudaStream_t st, bool* forked) {
+    *forked = false;
+    if (fa.n_vox <= 0) return T2FIT_OK;
+    CU_TRY(cudaEventRecord(c->ev_fork, st));
+    CU_TRY(cudaStreamWaitEvent(c->fill_stream, c->ev_fork, 0));
+    const int64_t chunks = (fa.n_vox + kFillChunk - 1) / kFillChunk;
+    const int64_t want = (chunks + 7) / 8;                                  // 8 warps per block
+    static const int per_sm = [] { const char* e = getenv("T2FIT_FILL_BLOCKS_PER_SM"); return e ? std::max(1, atoi(e)) : 2; }();
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)per_sm * c->prop.multiProcessorCount));
+    if (sigma_all) zero_fill_kernel<true><<<grid, 256, 0, c->fill_stream>>>(fa);
+    else zero_fill_kernel<false><<<grid, 256, 0, c->fill_stream>>>(fa);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(c->ev_join, c->fill_stream));
+    *forked = true;
     return T2FIT_OK;
 }
 
@@ -823,6 +650,9 @@ int t2fit_init(int device) {
         return fail(T2FIT_ENODEVICE, "libt2fit is built for sm_100a only; device is sm_" + std::to_string(c->prop.major) +
                                          std::to_string(c->prop.minor));
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->fill_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CU_TRY(cudaMalloc(&c->d_counts, 4 * sizeof(unsigned long long)));
     CU_TRY(cudaMemset(c->d_counts, 0, 4 * sizeof(unsigned long long)));
     CU_TRY(cudaMallocHost(&c->h_counts, 4 * sizeof(unsigned long long)));
@@ -854,6 +684,9 @@ void t2fit_shutdown(void) {
     if (c->d_total) cudaFree(c->d_total);
     if (c->h_total) cudaFreeHost(c->h_total);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->fill_stream) cudaStreamDestroy(c->fill_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c->workers;
     delete c;
     g_ctx = nullptr;
@@ -894,18 +727,22 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     io.t2 = o->t2; io.k = o->k; io.sigma = o->sigma; io.res = o->res; io.fun = o->fun; io.nit = o->nit;
     io.status = o->status; io.counts = c->d_counts; io.dense = o->dense;
     io.vec_ok = (reinterpret_cast<uintptr_t>(p->echoes) % 16) == 0;
+    bool forked = false;
     if (o->dense && o->zero_fill_mask) {
-        // fused np.zeros_like (:415-418): needs 4-byte aligned mask and 16-byte aligned maps
+        // np.zeros_like x4 (:415-418) on the side stream, concurrent with the fit (disjoint slots)
         if ((reinterpret_cast<uintptr_t>(o->zero_fill_mask) % 4) != 0)
             return fail(T2FIT_EINVAL, "zero_fill_mask must be 4-byte aligned");
+        FillArgs fa{};
+        fa.t2 = o->t2; fa.k = o->k; fa.res = o->res; fa.sigma = o->sigma;
+        fa.mask = o->zero_fill_mask; fa.n_vox = p->n_vox; fa.vec = 1;
         float* mp[4] = {o->t2, o->k, o->sigma, o->res};
-        io.fill_vec = 1;
-        for (float* q : mp) if ((reinterpret_cast<uintptr_t>(q) % 16) != 0) io.fill_vec = 0;   // scalar zero stores
-        io.mask = o->zero_fill_mask;
-        io.n_vox = p->n_vox;
-        io.sigma = o->sigma;   // zeroed by the fill role even for the 2-parameter model
+        for (float* q : mp) if (q && (reinterpret_cast<uintptr_t>(q) % 16) != 0) fa.vec = 0;
+        rc = launch_zero_fill(c, fa, p->model == T2FIT_MODEL_GAUSSIAN, st, &forked);
+        if (rc) return rc;
     }
-    return launch_fit(c, fc, io, p->model, p->n_echo, p->layout, st);
+    rc = launch_fit(c, fc, io, p->model, p->n_echo, p->layout, st);
+    if (forked) CU_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));           // join: results complete on `st`
+    return rc;
 }
 
 int t2fit_status_counts(void* stream, int64_t counts[4]) {

@@ -96,10 +96,12 @@ typedef struct t2fit_outputs {
     int64_t status_count[4];     /* OUT (host): voxels per status; filled when the call is synchronous
                                     (T2FIT_MEM_HOST) or by t2fit_status_counts() */
     const uint8_t *zero_fill_mask; /* device calls with dense != 0 only: the [n_vox] uint8 mask (1 byte per voxel,
-                                    nonzero = masked, consistent with mask_idx).  When given, the same launch
-                                    also zero-fills every unmasked slot of the four maps (np.zeros_like, :415-418)
-                                    -- and all of sigma for the 2-parameter model -- so the caller need not
-                                    pre-zero them.  NULL = caller zero-fills. */
+                                    nonzero = masked, consistent with mask_idx).  When given, the call also
+                                    zero-fills every unmasked slot of the four maps (np.zeros_like, :415-418)
+                                    -- and all of sigma for the 2-parameter model -- with a kernel on a side
+                                    stream that runs concurrently with the fit (forked from / joined into
+                                    `stream`), so the caller need not pre-zero them.  NULL = caller zero-fills.
+                                    One such call at a time per process (the fork/join events are shared). */
 } t2fit_outputs;
 
 /* Bind this process to one GPU (one process per GPU; device = LOCAL_RANK) and create its context

@@ -64,6 +64,10 @@ def main():
         return f
 
     res = {}
+    if os.environ.get("MB_ONLY") == "fill":
+        p, o, k1 = problem(0, True, True)
+        print("fill only", timeit(runner(p, o), reps=10))
+        return
     res["torch zero_ 4 maps"] = timeit(lambda: maps.zero_())
     p, o, k1 = problem(0, True, True); res["fill only (fused kernel, n_fit=0)"] = timeit(runner(p, o))
     p, o, k2 = problem(m, False, False); res["fit only, compact out"] = timeit(runner(p, o))
