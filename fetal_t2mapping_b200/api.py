@@ -74,6 +74,20 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
+def _host_array(n, dtype, zero=False):
+    """Result array in page-locked host memory when torch is importable (the library then copies D2H
+    straight into it, no staging copy); plain numpy otherwise."""
+    try:
+        import torch
+        t = torch.empty(n, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+        a = t.numpy()
+        if zero:
+            a[:] = 0
+        return a
+    except Exception:
+        return np.zeros(n, dtype) if zero else np.empty(n, dtype)
+
+
 @dataclass
 class FitResult:
     """Everything ``pool.map(fit_voxel)`` + ``compute_residuals`` produce, for all masked voxels.
@@ -220,11 +234,11 @@ def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=
         m = n_vox if idx is None else idx.size
         if idx is not None and m and (idx.min() < 0 or idx.max() >= n_vox):
             raise IndexError("mask_indices out of range")
-        out = {"t2": np.empty(m, np.float32), "k": np.empty(m, np.float32), "res": np.empty(m, np.float32),
-               "sigma": np.empty(m, np.float32) if fit != "gaussian" else np.zeros(m, np.float32),
-               "fun": np.empty(m, np.float32) if "fun" in want else None,
-               "nit": np.empty(m, np.int32) if "nit" in want else None,
-               "status": np.empty(m, np.uint8) if "status" in want else None}
+        out = {"t2": _host_array(m, np.float32), "k": _host_array(m, np.float32), "res": _host_array(m, np.float32),
+               "sigma": _host_array(m, np.float32) if fit != "gaussian" else np.zeros(m, np.float32),
+               "fun": _host_array(m, np.float32) if "fun" in want else None,
+               "nit": _host_array(m, np.int32) if "nit" in want else None,
+               "status": _host_array(m, np.uint8) if "status" in want else None}
         p.echoes, p.memory = y.ctypes.data, _abi.MEM_HOST
         p.mask_idx = idx.ctypes.data if idx is not None else None
         ptr = lambda a: a.ctypes.data if a is not None else None

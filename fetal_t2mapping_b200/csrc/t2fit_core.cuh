@@ -196,8 +196,12 @@ T2_HD void solve_mono2(const R (&y)[E], const FitConsts& c, R kl, R ku, R r0, R&
             const bool interior = (r > r_lo) && (r < r_hi);
             const R a_n = (g > R(0)) ? a : r, b_n = (g > R(0)) ? r : b;
             const R rn_p = r + dr;
-            const bool plain = newton && interior && (free == free_new) && (rn_p > a_n) && (rn_p < b_n) &&
-                               (brk ? !(adr > R(0.5) * dx2) : !(it > 0 && adr > R(0.5) * dx1)) && (it < max_pass - 1);
+            const bool small_p = adr <= tol * r;
+            // a Newton step below tol ends the iteration whatever the bracket says (at a converged point the
+            // step can round to zero, rn_p == r); larger steps must stay inside the bracket and keep shrinking
+            const bool plain = newton && interior && (free == free_new) && (it < max_pass - 1) &&
+                               (small_p || ((rn_p > a_n) && (rn_p < b_n) &&
+                                            (brk ? !(adr > R(0.5) * dx2) : !(it > 0 && adr > R(0.5) * dx1))));
 #ifdef T2FIT_TRACE
             printf("it %d r %.9g T2 %.6f k %.6f free %d g %.6g hgn %.6g hex %.6g a %.6g b %.6g plain %d rn %.9g\n", it,
                    (double)r, 1.0 / (double)r, (double)k, (int)free, (double)g, (double)h_gn, (double)h_ex, (double)a,
@@ -207,9 +211,8 @@ T2_HD void solve_mono2(const R (&y)[E], const FitConsts& c, R kl, R ku, R r0, R&
                 a = a_n; b = b_n;
                 if (g > R(0)) hb = true; else ha = true;
                 run_len = 0;
-                const bool small = adr <= tol * r;
-                done = small;             // Newton step below tol: the error after it is O(tol^2)
-                prev_small = small;
+                done = small_p;           // Newton step below tol: the error after it is O(tol^2)
+                prev_small = small_p;
                 dx2 = dx1; dx1 = adr;
                 r = rn_p;
             } else {
@@ -256,9 +259,11 @@ T2_HD void solve_mono2(const R (&y)[E], const FitConsts& c, R kl, R ku, R r0, R&
                         else rn = R(0.5) * (a + b);
                         guarded = true;
                     }
-                    const bool small = absr(rn - r) <= tol * r;
-                    // Gauss-Newton / guarded small steps need a second small step in a row
-                    if (small && ((newton && !guarded) || prev_small)) done = true;
+                    const R step = absr(rn - r);
+                    const bool small = step <= tol * r;
+                    // guarded / Gauss-Newton steps converge linearly at best: stop on a step 16x below tol,
+                    // or on two consecutive steps below tol
+                    if (step <= R(0.0625) * tol * r || (small && prev_small)) done = true;
                     prev_small = small;
                     dx2 = dx1; dx1 = absr(rn - r);
                     r = rn;

@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -128,27 +129,41 @@ __global__ void __launch_bounds__(256) zero_fill_kernel(const __grid_constant__ 
     const int64_t full_chunks = a.n_vox / kFillChunk;
     const bool fast = a.vec && a.t2 && a.k && a.res && a.sigma;
     if (fast) {
+#pragma unroll 1
         for (int64_t c = gw; c < full_chunks; c += nw) {
             const int64_t off = c * kFillChunk + lane * 4;
             const uint32_t* pm = reinterpret_cast<const uint32_t*>(a.mask + c * kFillChunk) + lane;
-            uint32_t w0 = __ldg(pm), w1 = __ldg(pm + 32), w2 = __ldg(pm + 64), w3 = __ldg(pm + 96);
-            float4* p0 = reinterpret_cast<float4*>(a.t2 + off);
-            float4* p1 = reinterpret_cast<float4*>(a.k + off);
-            float4* p2 = reinterpret_cast<float4*>(a.res + off);
-            float4* p3 = reinterpret_cast<float4*>(a.sigma + off);
-#define T2_FILL_WORD(W, J)                                                                                  \
-            if (SIGMA_ALL) p3[(J) * 32] = z4;                                                               \
-            if ((W) == 0u) { p0[(J) * 32] = z4; p1[(J) * 32] = z4; p2[(J) * 32] = z4; if (!SIGMA_ALL) p3[(J) * 32] = z4; } \
-            else if ((W) != 0x01010101u) {                                                                  \
-                for (int q = 0; q < 4; ++q) fill_voxel<SIGMA_ALL>(a, off + (J) * 128 + q, (((W) >> (8 * q)) & 0xffu) == 0u); \
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = __ldg(pm + j * 32);
+            float* q0 = a.t2 + off;
+            float* q1 = a.k + off;
+            float* q2 = a.res + off;
+            float* q3 = a.sigma + off;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t wj = w[j];
+                if (SIGMA_ALL || wj == 0u) *reinterpret_cast<float4*>(q3 + j * 128) = z4;
+                if (wj == 0u) {
+                    *reinterpret_cast<float4*>(q0 + j * 128) = z4;
+                    *reinterpret_cast<float4*>(q1 + j * 128) = z4;
+                    *reinterpret_cast<float4*>(q2 + j * 128) = z4;
+                } else if (wj != 0x01010101u) {             // mask boundary inside the word: predicated scalar stores
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (((wj >> (8 * q)) & 0xffu) == 0u) {
+                            q0[j * 128 + q] = 0.f; q1[j * 128 + q] = 0.f; q2[j * 128 + q] = 0.f;
+                            if (!SIGMA_ALL) q3[j * 128 + q] = 0.f;
+                        }
+                    }
+                }
             }
-            T2_FILL_WORD(w0, 0) T2_FILL_WORD(w1, 1) T2_FILL_WORD(w2, 2) T2_FILL_WORD(w3, 3)
-#undef T2_FILL_WORD
         }
     }
     // per-voxel path: everything if not `fast`, else only the ragged tail after the last full chunk
     const int64_t v0 = fast ? full_chunks * kFillChunk : 0;
     const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x, nt = (int64_t)gridDim.x * 256;
+#pragma unroll 1
     for (int64_t v = v0 + t; v < a.n_vox; v += nt) fill_voxel<SIGMA_ALL>(a, v, a.mask[v] == 0);
 }
 
@@ -430,16 +445,18 @@ constexpr int kSlots = 3;
 constexpr int64_t kChunk = 1 << 18;  // voxels per staging chunk
 
 struct Slot {
-    float* h_in = nullptr;     // pinned [E_cap * kChunk]
+    float* h_in = nullptr;     // pinned, E_cap * kChunk floats: gathered rows [n, E] (AoS) or planes [E, n] (SoA)
     float* d_in = nullptr;
-    float* h_out = nullptr;    // pinned [5 * kChunk] t2,k,sigma,res,fun
-    float* d_out = nullptr;
-    int32_t* h_nit = nullptr;  int32_t* d_nit = nullptr;
-    uint8_t* h_st = nullptr;   uint8_t* d_st = nullptr;
+    // results of one chunk, the same layout on both sides so that one copy moves everything:
+    //   [t2 | k | sigma | res | fun] 5 x kChunk float, [nit] kChunk int32, [status] kChunk uint8
+    uint8_t* h_out = nullptr;  // pinned
+    uint8_t* d_out = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     int64_t first = -1, count = 0;  // chunk in flight
+    bool direct = false;            // results were copied straight into the caller's (pinned) arrays
 };
+constexpr size_t kOutBytes = (size_t)kChunk * (5 * sizeof(float) + sizeof(int32_t) + 1);
 
 struct Context {
     int device = -1;
@@ -456,6 +473,7 @@ struct Context {
     int64_t* d_total = nullptr;
     int64_t* h_total = nullptr;
     int64_t tiles_cap = 0;
+    bool counts_dirty = false;               // device-memory launches may have bumped d_counts
     cudaStream_t fill_stream = nullptr;      // side stream of the zero-fill kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
@@ -469,13 +487,8 @@ void free_slots(Context* c) {
         if (s.d_in) cudaFree(s.d_in);
         if (s.h_out) cudaFreeHost(s.h_out);
         if (s.d_out) cudaFree(s.d_out);
-        if (s.h_nit) cudaFreeHost(s.h_nit);
-        if (s.d_nit) cudaFree(s.d_nit);
-        if (s.h_st) cudaFreeHost(s.h_st);
-        if (s.d_st) cudaFree(s.d_st);
-        s.h_in = s.d_in = s.h_out = s.d_out = nullptr;
-        s.h_nit = s.d_nit = nullptr;
-        s.h_st = s.d_st = nullptr;
+        s.h_in = s.d_in = nullptr;
+        s.h_out = s.d_out = nullptr;
     }
     c->e_cap = 0;
 }
@@ -486,12 +499,8 @@ int ensure_slots(Context* c, int n_echo) {
     for (auto& s : c->slots) {
         CU_TRY(cudaMallocHost(&s.h_in, sizeof(float) * n_echo * kChunk));
         CU_TRY(cudaMalloc(&s.d_in, sizeof(float) * n_echo * kChunk));
-        CU_TRY(cudaMallocHost(&s.h_out, sizeof(float) * 5 * kChunk));
-        CU_TRY(cudaMalloc(&s.d_out, sizeof(float) * 5 * kChunk));
-        CU_TRY(cudaMallocHost(&s.h_nit, sizeof(int32_t) * kChunk));
-        CU_TRY(cudaMalloc(&s.d_nit, sizeof(int32_t) * kChunk));
-        CU_TRY(cudaMallocHost(&s.h_st, kChunk));
-        CU_TRY(cudaMalloc(&s.d_st, kChunk));
+        CU_TRY(cudaMallocHost(&s.h_out, kOutBytes));
+        CU_TRY(cudaMalloc(&s.d_out, kOutBytes));
         if (!s.stream) CU_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         if (!s.done) CU_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
@@ -518,7 +527,7 @@ int launch_zero_fill(Context* c, const FillArgs& fa, bool sigma_all, cudaStream_
     CU_TRY(cudaStreamWaitEvent(c->fill_stream, c->ev_fork, 0));
     const int64_t chunks = (fa.n_vox + kFillChunk - 1) / kFillChunk;
     const int64_t want = (chunks + 7) / 8;                                  // 8 warps per block
-    static const int per_sm = [] { const char* e = getenv("T2FIT_FILL_BLOCKS_PER_SM"); return e ? std::max(1, atoi(e)) : 2; }();
+    static const int per_sm = [] { const char* e = getenv("T2FIT_FILL_BLOCKS_PER_SM"); return e ? std::max(1, atoi(e)) : 1; }();
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)per_sm * c->prop.multiProcessorCount));
     if (sigma_all) zero_fill_kernel<true><<<grid, 256, 0, c->fill_stream>>>(fa);
     else zero_fill_kernel<false><<<grid, 256, 0, c->fill_stream>>>(fa);
@@ -528,94 +537,151 @@ int launch_zero_fill(Context* c, const FillArgs& fa, bool sigma_all, cudaStream_
     return T2FIT_OK;
 }
 
-// host-memory path: stage chunks through pinned buffers; pack on worker threads while the GPU
-// works on the previous chunk; results come back compact and are copied / scattered on the host
+// host-memory path: stage chunks through pinned buffers.  Worker threads gather the masked rows of the
+// next chunk (run-aware memcpy: consecutive mask indices are contiguous rows) while the GPU works on
+// the previous ones; per chunk ONE H2D copy, one kernel, and either direct D2H copies into the caller's
+// arrays (when those are page-locked) or one D2H into pinned staging + a threaded unpack / scatter.
+bool is_pinned(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
 int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitConsts& fc) {
     int rc = ensure_slots(c, p.n_echo);
     if (rc) return rc;
     const int E = p.n_echo;
     const int64_t M = p.n_fit;
-    CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), c->stream));
-    CU_TRY(cudaStreamSynchronize(c->stream));
+    static const bool profile = getenv("T2FIT_HOST_PROFILE") != nullptr;
+    double t_pack = 0, t_wait = 0, t_unpack = 0, t0 = now_ms();
+    if (c->counts_dirty) {                        // device-memory calls since the last query left counts behind
+        CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), c->slots[0].stream));
+        CU_TRY(cudaStreamSynchronize(c->slots[0].stream));
+        c->counts_dirty = false;
+    }
     const int64_t n_chunks = (M + kChunk - 1) / kChunk;
+    const bool mono = p.model == T2FIT_MODEL_GAUSSIAN;
+    // compact results can go straight into the caller's arrays if every one of them is page-locked
+    const bool direct = !o.dense && is_pinned(o.t2) && is_pinned(o.k) && is_pinned(o.res) && is_pinned(o.fun) &&
+                        is_pinned(o.nit) && is_pinned(o.status) && (mono || is_pinned(o.sigma));
 
     auto unpack = [&](Slot& s) {
         if (s.first < 0) return;
         const int64_t first = s.first, n = s.count;
+        s.first = -1;
+        if (s.direct) return;
+        const double tu = now_ms();
         float* outs[5] = {o.t2, o.k, o.sigma, o.res, o.fun};
+        const float* hf = reinterpret_cast<const float*>(s.h_out);
+        const int32_t* hn = reinterpret_cast<const int32_t*>(s.h_out + (size_t)5 * n * sizeof(float));
+        const uint8_t* hs = s.h_out + (size_t)5 * n * sizeof(float) + (size_t)n * sizeof(int32_t);
         c->workers->run([&](int part, int parts) {
             const int64_t lo = n * part / parts, hi = n * (part + 1) / parts;
             if (hi <= lo) return;
             for (int m = 0; m < 5; ++m) {
                 float* dst = outs[m];
                 if (!dst) continue;
-                if (m == 2 && p.model == T2FIT_MODEL_GAUSSIAN) continue;   // sigma map stays as the caller zeroed it
-                const float* src = s.h_out + (int64_t)m * kChunk;
-                if (o.dense && m < 4) {
-                    if (p.mask_idx) for (int64_t i = lo; i < hi; ++i) dst[p.mask_idx[first + i]] = src[i];
-                    else memcpy(dst + first + lo, src + lo, sizeof(float) * (hi - lo));
+                if (m == 2 && mono) continue;                     // sigma map stays as the caller zeroed it
+                const float* src = hf + (int64_t)m * n;
+                if (o.dense && m < 4 && p.mask_idx) {
+                    for (int64_t i = lo; i < hi; ++i) dst[p.mask_idx[first + i]] = src[i];   // scatter (:455-458)
                 } else {
                     memcpy(dst + first + lo, src + lo, sizeof(float) * (hi - lo));
                 }
             }
-            if (o.nit) memcpy(o.nit + first + lo, s.h_nit + lo, sizeof(int32_t) * (hi - lo));
-            if (o.status) memcpy(o.status + first + lo, s.h_st + lo, hi - lo);
+            if (o.nit) memcpy(o.nit + first + lo, hn + lo, sizeof(int32_t) * (hi - lo));
+            if (o.status) memcpy(o.status + first + lo, hs + lo, hi - lo);
         });
-        s.first = -1;
+        t_unpack += now_ms() - tu;
     };
 
     for (int64_t ch = 0; ch < n_chunks; ++ch) {
         Slot& s = c->slots[ch % kSlots];
         if (s.first >= 0) {                       // slot still holds an older chunk: drain it
+            const double tw = now_ms();
             CU_TRY(cudaEventSynchronize(s.done));
+            t_wait += now_ms() - tw;
             unpack(s);
         }
         const int64_t first = ch * kChunk, n = std::min(kChunk, M - first);
-        // pack: rows (through mask_idx) -> SoA planes of the pinned buffer
+        const double tp = now_ms();
         c->workers->run([&](int part, int parts) {
             const int64_t lo = n * part / parts, hi = n * (part + 1) / parts;
-            if (p.layout == T2FIT_LAYOUT_AOS) {
-                for (int64_t i = lo; i < hi; ++i) {
-                    const int64_t row = p.mask_idx ? p.mask_idx[first + i] : first + i;
-                    const float* src = p.echoes + row * E;
-                    for (int e = 0; e < E; ++e) s.h_in[(int64_t)e * kChunk + i] = src[e];
+            if (hi <= lo) return;
+            if (p.layout == T2FIT_LAYOUT_AOS) {   // rows -> packed rows [n, E]; runs of consecutive indices in one memcpy
+                if (!p.mask_idx) {
+                    memcpy(s.h_in + lo * E, p.echoes + (first + lo) * E, sizeof(float) * E * (hi - lo));
+                } else {
+                    const int64_t* idx = p.mask_idx + first;
+                    int64_t i = lo;
+                    while (i < hi) {
+                        int64_t j = i + 1;
+                        while (j < hi && idx[j] == idx[j - 1] + 1) ++j;
+                        memcpy(s.h_in + i * E, p.echoes + idx[i] * E, sizeof(float) * E * (j - i));
+                        i = j;
+                    }
                 }
-            } else {
+            } else {                              // SoA planes [E, ld] -> planes [E, n]
                 for (int e = 0; e < E; ++e)
-                    if (hi > lo) memcpy(s.h_in + (int64_t)e * kChunk + lo, p.echoes + (int64_t)e * p.ld + first + lo,
-                                        sizeof(float) * (hi - lo));
+                    memcpy(s.h_in + (int64_t)e * n + lo, p.echoes + (int64_t)e * p.ld + first + lo, sizeof(float) * (hi - lo));
             }
         });
-        for (int e = 0; e < E; ++e)
-            CU_TRY(cudaMemcpyAsync(s.d_in + (int64_t)e * kChunk, s.h_in + (int64_t)e * kChunk, sizeof(float) * n,
-                                   cudaMemcpyHostToDevice, s.stream));
+        t_pack += now_ms() - tp;
+        CU_TRY(cudaMemcpyAsync(s.d_in, s.h_in, sizeof(float) * E * n, cudaMemcpyHostToDevice, s.stream));
+        float* df = reinterpret_cast<float*>(s.d_out);
         KernelIO io{};
-        io.echoes = s.d_in; io.idx = nullptr; io.ld = kChunk; io.n_fit = n;
-        io.t2 = s.d_out; io.k = s.d_out + kChunk; io.sigma = s.d_out + 2 * kChunk; io.res = s.d_out + 3 * kChunk;
-        io.fun = s.d_out + 4 * kChunk; io.nit = s.d_nit; io.status = s.d_st; io.counts = c->d_counts;
-        io.dense = 0; io.vec_ok = 1;
-        rc = launch_fit(c, fc, io, p.model, E, T2FIT_LAYOUT_SOA, s.stream);
+        io.echoes = s.d_in; io.idx = nullptr; io.ld = n; io.n_fit = n;
+        io.t2 = df; io.k = df + n; io.sigma = df + 2 * n; io.res = df + 3 * n; io.fun = df + 4 * n;
+        io.nit = reinterpret_cast<int32_t*>(s.d_out + (size_t)5 * n * sizeof(float));
+        io.status = s.d_out + (size_t)5 * n * sizeof(float) + (size_t)n * sizeof(int32_t);
+        io.counts = c->d_counts; io.dense = 0; io.vec_ok = 1;
+        rc = launch_fit(c, fc, io, p.model, E, p.layout, s.stream);
         if (rc) return rc;
-        for (int m = 0; m < 5; ++m) {
-            if (m == 2 && p.model == T2FIT_MODEL_GAUSSIAN) continue;
-            CU_TRY(cudaMemcpyAsync(s.h_out + (int64_t)m * kChunk, s.d_out + (int64_t)m * kChunk, sizeof(float) * n,
+        s.direct = direct;
+        if (direct) {
+            auto d2h = [&](void* dst, const void* src, size_t bytes) {
+                return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s.stream) : cudaSuccess;
+            };
+            CU_TRY(d2h(o.t2 ? o.t2 + first : nullptr, io.t2, sizeof(float) * n));
+            CU_TRY(d2h(o.k ? o.k + first : nullptr, io.k, sizeof(float) * n));
+            if (!mono) CU_TRY(d2h(o.sigma ? o.sigma + first : nullptr, io.sigma, sizeof(float) * n));
+            CU_TRY(d2h(o.res ? o.res + first : nullptr, io.res, sizeof(float) * n));
+            CU_TRY(d2h(o.fun ? o.fun + first : nullptr, io.fun, sizeof(float) * n));
+            CU_TRY(d2h(o.nit ? o.nit + first : nullptr, io.nit, sizeof(int32_t) * n));
+            CU_TRY(d2h(o.status ? o.status + first : nullptr, io.status, n));
+        } else {
+            CU_TRY(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * (5 * sizeof(float) + sizeof(int32_t) + 1),
                                    cudaMemcpyDeviceToHost, s.stream));
         }
-        CU_TRY(cudaMemcpyAsync(s.h_nit, s.d_nit, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s.stream));
-        CU_TRY(cudaMemcpyAsync(s.h_st, s.d_st, n, cudaMemcpyDeviceToHost, s.stream));
         CU_TRY(cudaEventRecord(s.done, s.stream));
         s.first = first; s.count = n;
     }
     // drain in submission order
     for (int64_t ch = std::max<int64_t>(0, n_chunks - kSlots); ch < n_chunks; ++ch) {
         Slot& s = c->slots[ch % kSlots];
-        if (s.first >= 0) { CU_TRY(cudaEventSynchronize(s.done)); unpack(s); }
+        if (s.first >= 0) {
+            const double tw = now_ms();
+            CU_TRY(cudaEventSynchronize(s.done));
+            t_wait += now_ms() - tw;
+            unpack(s);
+        }
     }
-    CU_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(cudaStreamSynchronize(c->stream));
+    // all slot streams are idle now: read the status histogram and leave the counters zeroed for the next call
+    CU_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->slots[0].stream));
+    CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), c->slots[0].stream));
+    CU_TRY(cudaStreamSynchronize(c->slots[0].stream));
     int64_t bad = 0;
     for (int s = 1; s < 4; ++s) { o.status_count[s] = (int64_t)c->h_counts[s]; bad += o.status_count[s]; }
     o.status_count[0] = M - bad;
+    if (profile)
+        fprintf(stderr, "[t2fit host] M=%lld chunks=%lld direct=%d total %.3f ms: pack %.3f wait %.3f unpack %.3f\n", (long long)M,
+                (long long)n_chunks, (int)direct, now_ms() - t0, t_pack, t_wait, t_unpack);
     return T2FIT_OK;
 }
 
@@ -740,6 +806,7 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
         rc = launch_zero_fill(c, fa, p->model == T2FIT_MODEL_GAUSSIAN, st, &forked);
         if (rc) return rc;
     }
+    c->counts_dirty = true;
     rc = launch_fit(c, fc, io, p->model, p->n_echo, p->layout, st);
     if (forked) CU_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));           // join: results complete on `st`
     return rc;
@@ -755,6 +822,8 @@ int t2fit_status_counts(void* stream, int64_t counts[4]) {
     for (int s = 0; s < 4; ++s) counts[s] = (int64_t)c->h_counts[s];
     counts[0] = -1;  // OK count = n_fit - sum(others); the caller knows n_fit
     CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), st));   // counts are "since the last query"
+    CU_TRY(cudaStreamSynchronize(st));
+    c->counts_dirty = false;
     return T2FIT_OK;
 }
 

@@ -68,3 +68,18 @@ def test_bounds_validation_raises_like_scipy():
     g = load_golden("c1_gaussian_prior")
     with pytest.raises(ValueError, match="upper bound"):
         hostsim.fit(g["rows"][:4], g["te"], "gaussian", g["x0"], [(600, 100), (10, 600)], True)
+
+
+def test_noise_free_signals_converge_in_one_or_two_passes():
+    """At a converged point the Newton step rounds to zero (r + dr == r with fused multiply-add); the
+    solver must stop there instead of falling into its bracket/bisection path (regression)."""
+    rng = np.random.default_rng(0)
+    te = np.array([114, 132, 150, 176, 202.0])
+    n = 50000
+    t2 = np.exp(rng.uniform(np.log(11), np.log(1900), n))
+    k = rng.uniform(1, 9000, n)
+    clean = (k[:, None] * np.exp(-te[None, :] / t2[:, None])).astype(np.float32)
+    o = hostsim.fit(clean, te, "gaussian", [650, 165], [(0, 10000), (10, 2000)], True)
+    rel = np.abs(o["t2"] - t2) / t2
+    assert (o["status"] == 0).all() and o["nit"].max() <= 3
+    assert rel.max() < 2e-4 and np.median(rel) < 1e-5
