@@ -249,17 +249,18 @@ def run_gpu(args):
             step()
         torch.cuda.synchronize()
     barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # the timed region: K steps between two CUDA events on the launching stream.  No per-step events inside:
+    # an event pair around every fork/join step was measured to stretch a 68 us step to 125 us.
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_start.record(stream)
     for s in range(args.steps):
-        step(evs[s])
+        step()
     t_end.record(stream)
     barrier()
     clocks = sampler.stop() if sampler else None
     elapsed_ms = t_start.elapsed_time(t_end)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    kern_ms = elapsed_ms / args.steps
     if world > 1:
         t = torch.tensor([elapsed_ms, kern_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

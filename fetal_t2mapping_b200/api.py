@@ -177,6 +177,8 @@ def _run(lib, p, o, stream):
         msg = (lib.t2fit_last_error() or b"").decode()
         if rc == -1 and "upper bound" in msg:
             raise ValueError(msg)
+        if rc == -1 and "mask_idx out of range" in msg:
+            raise IndexError("mask_indices out of range")
         raise _abi.T2FitError(f"t2fit_run: {_abi.ERRORS.get(rc, rc)}: {msg}")
 
 
@@ -232,8 +234,6 @@ def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=
         n_vox, n_echo = y.shape
         idx = None if mask_indices is None else np.ascontiguousarray(mask_indices, dtype=np.int64)
         m = n_vox if idx is None else idx.size
-        if idx is not None and m and (idx.min() < 0 or idx.max() >= n_vox):
-            raise IndexError("mask_indices out of range")
         out = {"t2": _host_array(m, np.float32), "k": _host_array(m, np.float32), "res": _host_array(m, np.float32),
                "sigma": _host_array(m, np.float32) if fit != "gaussian" else np.zeros(m, np.float32),
                "fun": _host_array(m, np.float32) if "fun" in want else None,

@@ -567,6 +567,7 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
     }
     const int64_t n_chunks = (M + kChunk - 1) / kChunk;
     const bool mono = p.model == T2FIT_MODEL_GAUSSIAN;
+    std::atomic<bool> bad_index{false};
     // compact results can go straight into the caller's arrays if every one of them is page-locked
     const bool direct = !o.dense && is_pinned(o.t2) && is_pinned(o.k) && is_pinned(o.res) && is_pinned(o.fun) &&
                         is_pinned(o.nit) && is_pinned(o.status) && (mono || is_pinned(o.sigma));
@@ -623,6 +624,7 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
                     while (i < hi) {
                         int64_t j = i + 1;
                         while (j < hi && idx[j] == idx[j - 1] + 1) ++j;
+                        if (idx[i] < 0 || idx[j - 1] >= p.n_vox) { bad_index.store(true); return; }   // IndexError upstream
                         memcpy(s.h_in + i * E, p.echoes + idx[i] * E, sizeof(float) * E * (j - i));
                         i = j;
                     }
@@ -633,6 +635,10 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
             }
         });
         t_pack += now_ms() - tp;
+        if (bad_index.load()) {
+            for (auto& sl : c->slots) { cudaStreamSynchronize(sl.stream); sl.first = -1; }
+            return fail(T2FIT_EINVAL, "mask_idx out of range");
+        }
         CU_TRY(cudaMemcpyAsync(s.d_in, s.h_in, sizeof(float) * E * n, cudaMemcpyHostToDevice, s.stream));
         float* df = reinterpret_cast<float*>(s.d_out);
         KernelIO io{};

@@ -282,3 +282,14 @@ def test_fused_zero_fill_ragged_volumes(gpu_lib, fit, shape):
     else:
         assert np.array_equal(m[2, idx], ref.sigma.cpu().numpy())
     del keep
+
+
+def test_out_of_range_mask_indices_raise(gpu_lib):
+    y = np.ones((10, 3), np.float32)
+    _, fp = gpu_lib.preset("gaussian", True)
+    with pytest.raises(IndexError):
+        gpu_lib.fit_voxels_batch(y, np.array([0, 3, 12]), [114.0, 202.0, 299.0], "gaussian", fp)
+    with pytest.raises(IndexError):
+        gpu_lib.fit_voxels_batch(y, np.array([-1, 3]), [114.0, 202.0, 299.0], "gaussian", fp)
+    r = gpu_lib.fit_voxels_batch(y * 700, np.array([0, 3, 9]), [114.0, 202.0, 299.0], "gaussian", fp)   # still usable
+    assert r.t2.shape == (3,)

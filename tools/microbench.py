@@ -68,6 +68,15 @@ def main():
         p, o, k1 = problem(0, True, True)
         print("fill only", timeit(runner(p, o), reps=10))
         return
+    if os.environ.get("MB_ONLY") == "long":
+        p, o, k5 = problem(m, True, True)
+        f = runner(p, o)
+        print("fused, windows of 2000 reps:", [round(timeit(f, reps=2000), 1) for _ in range(8)])
+        p, o, k4 = problem(m, True, False)
+        f = runner(p, o)
+        print("fit only, windows of 2000 reps:", [round(timeit(f, reps=2000), 1) for _ in range(4)])
+        print("zero_ only, windows of 2000 reps:", [round(timeit(lambda: maps.zero_(), reps=2000), 1) for _ in range(4)])
+        return
     res["torch zero_ 4 maps"] = timeit(lambda: maps.zero_())
     p, o, k1 = problem(0, True, True); res["fill only (fused kernel, n_fit=0)"] = timeit(runner(p, o))
     p, o, k2 = problem(m, False, False); res["fit only, compact out"] = timeit(runner(p, o))
