@@ -68,6 +68,10 @@ def main():
         p, o, k1 = problem(0, True, True)
         print("fill only", timeit(runner(p, o), reps=10))
         return
+    if os.environ.get("MB_ONLY") == "fit":
+        p, o, k4 = problem(m, True, False)
+        print("fit only", timeit(runner(p, o), reps=10))
+        return
     if os.environ.get("MB_ONLY") == "long":
         p, o, k5 = problem(m, True, True)
         f = runner(p, o)
