@@ -8,12 +8,15 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_ECHO = 32
 
 MODEL_GAUSSIAN = 0
 MODEL_GAUSSIAN_RICIAN = 1
-MODELS = {"gaussian": MODEL_GAUSSIAN, "gaussian_rician": MODEL_GAUSSIAN_RICIAN}
+MODEL_RICIAN = 2
+MODELS = {"gaussian": MODEL_GAUSSIAN, "gaussian_rician": MODEL_GAUSSIAN_RICIAN, "rician": MODEL_RICIAN}
+SOLVER_FAST, SOLVER_LBFGSB = 0, 1
+SOLVERS = {"fast": SOLVER_FAST, "lbfgsb": SOLVER_LBFGSB}
 
 LAYOUT_AOS = 0
 LAYOUT_SOA = 1
@@ -50,6 +53,12 @@ class Problem(C.Structure):
         ("max_iter", C.c_int32),
         ("tol", C.c_float),
         ("init", C.c_int32),
+        ("solver", C.c_int32),
+        ("lbfgsb_ftol", C.c_double),
+        ("lbfgsb_gtol", C.c_double),
+        ("lbfgsb_maxls", C.c_int32),
+        ("lbfgsb_maxiter", C.c_int32),
+        ("lbfgsb_maxfun", C.c_int32),
     ]
 
 
@@ -65,6 +74,10 @@ class Outputs(C.Structure):
         ("fun", C.c_void_p),
         ("dense", C.c_int32),
         ("status_count", C.c_int64 * 4),
+        ("trace_f", C.c_void_p),
+        ("trace_step", C.c_void_p),
+        ("trace_len", C.c_void_p),
+        ("trace_cap", C.c_int32),
         ("zero_fill_mask", C.c_void_p),
     ]
 

@@ -98,7 +98,8 @@ class FitResult:
     ``final_errors``       f64[M]    mean squared error at the solution           (:452)
     ``res``                f32[M]    signed mean residual (compute_residuals)     (:461)
     ``status``             uint8[M]  0 ok / 1 non-finite input / 2 iteration cap / 3 bad bounds
-    ``iteration_infos``    always ``[]`` per voxel: traces exist only for sampled voxels
+    ``iteration_infos``    the callback traces (:180-234) when the call asked for them (``trace_cap``,
+                           L-BFGS-B solver), else ``[]`` per voxel
     For device calls the float fields are torch CUDA tensors (float32).
     """
     t2: object
@@ -110,6 +111,23 @@ class FitResult:
     status: object
     fit: str
     status_count: tuple = (0, 0, 0, 0)
+    solver: str = "fast"
+    trace_f: object = None       # float32[M, trace_cap]  f_val per L-BFGS-B iteration
+    trace_step: object = None    # float32[M, trace_cap]  step_size (NaN for the first iteration)
+    trace_len: object = None     # int32[M]               entries used = min(nit, trace_cap)
+
+    @property
+    def iteration_infos(self):
+        """``iteration_info`` of every voxel as the reference's callbacks build it (run_t2mapping.py:180-234):
+        a list of ``{'f_val', 'grad_norm': None, 'step_size'}`` per L-BFGS-B iteration."""
+        m = int(self.nit.shape[0]) if self.nit is not None else int(self.t2.shape[0])
+        if self.trace_len is None:
+            return [[] for _ in range(m)]
+        tn = np.asarray(self.trace_len.cpu() if _is_torch(self.trace_len) else self.trace_len)
+        tf = np.asarray(self.trace_f.cpu() if _is_torch(self.trace_f) else self.trace_f)
+        ts = np.asarray(self.trace_step.cpu() if _is_torch(self.trace_step) else self.trace_step)
+        return [[{"f_val": float(tf[i, j]), "grad_norm": None, "step_size": float(ts[i, j])} for j in range(tn[i])]
+                for i in range(m)]
 
     @property
     def results(self):
@@ -137,14 +155,35 @@ class FitResult:
         ok = np.asarray(self.convergence_flags.cpu() if _is_torch(self.status) else self.convergence_flags)
         nit = np.asarray(self.nit.cpu() if _is_torch(self.nit) else self.nit)
         fun = np.asarray(self.final_errors.cpu() if _is_torch(self.fun) else self.final_errors)
-        return [(r[i], bool(ok[i]), int(nit[i]), float(fun[i]), []) for i in range(r.shape[0])]
+        infos = self.iteration_infos
+        return [(r[i], bool(ok[i]), int(nit[i]), float(fun[i]), infos[i]) for i in range(r.shape[0])]
 
 
-def _fill_problem(p, fit, fit_params, TEeffs, prior, norm, max_iter, tol, init_mode):
-    if fit == "rician":
-        raise NotImplementedError("fit='rician' (Rician NLL, run_t2mapping.py:157-177) is not implemented on the GPU path")
+def resolve_solver(fit, solver):
+    """``auto``: the float32 Newton/LM kernels for 'gaussian' (they reach the bounded minimiser the reference's
+    ftol=1e-6 run approaches); the reference's own optimiser (L-BFGS-B restated in FP64) for 'gaussian_rician' and
+    'rician', whose presets stop at ftol=gtol=1e-2, far from any minimiser -- only the same trajectory gives the
+    same maps there."""
+    if solver == "auto":
+        return "fast" if fit == "gaussian" else "lbfgsb"
+    if solver not in _abi.SOLVERS:
+        raise ValueError(f"unknown solver {solver!r}")
+    if solver == "fast" and fit == "rician":
+        raise ValueError("fit='rician' is a negative log-likelihood, not least squares: use solver='lbfgsb'")
+    return solver
+
+
+def _fill_problem(p, fit, fit_params, TEeffs, prior, norm, max_iter, tol, init_mode, solver="fast"):
     if fit not in _abi.MODELS:
         raise ValueError(f"unknown fit {fit!r}")
+    p.solver = _abi.SOLVERS[solver]
+    if solver == "lbfgsb":                 # fit_params['options'] as handed to scipy.optimize.minimize (:260-286)
+        opt = dict(fit_params.get("options") or {})
+        p.lbfgsb_ftol = float(opt.get("ftol", 0.0))
+        p.lbfgsb_gtol = float(opt.get("gtol", 0.0))
+        p.lbfgsb_maxls = int(opt.get("maxls", 0))
+        p.lbfgsb_maxiter = int(opt.get("maxiter", 0))
+        p.lbfgsb_maxfun = int(opt.get("maxfun", 0))
     x0 = list(fit_params["initial_guess"])
     bounds = list(fit_params["param_bounds"])
     npar = 2 if fit == "gaussian" else 3
@@ -183,19 +222,24 @@ def _run(lib, p, o, stream):
 
 
 def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=True, norm=False, *,
-                     max_iter=0, tol=0.0, init_mode="loglinear", check_bounds=True, dense_out=None,
-                     want=("nit", "fun", "status")) -> FitResult:
+                     solver="auto", trace_cap=0, max_iter=0, tol=0.0, init_mode="loglinear", check_bounds=True,
+                     dense_out=None, want=("nit", "fun", "status")) -> FitResult:
     """Fit every voxel ``mask_indices[i]`` of ``reshaped_t2w`` (float32 ``[N, E]``, run_t2mapping.py:411).
 
-    Arguments as ``fit_voxel`` (run_t2mapping.py:120): ``fit`` in {'gaussian','gaussian_rician'},
-    ``fit_params`` the preset dict (``initial_guess``, ``param_bounds``), ``prior`` False =
+    Arguments as ``fit_voxel`` (run_t2mapping.py:120): ``fit`` in {'gaussian','gaussian_rician','rician'},
+    ``fit_params`` the preset dict (``initial_guess``, ``param_bounds``, ``options``), ``prior`` False =
     ``--no_prior`` per-voxel bounds (:243-245), ``norm`` row-max normalisation (:237-240).
     ``mask_indices`` None fits all rows.  Raises ``ValueError`` where scipy would (bounds with
     lb > ub, including any masked voxel with S(TE0) > 10000 under ``--no_prior``).
+    ``solver``: 'fast' | 'lbfgsb' | 'auto' (see :func:`resolve_solver`).  ``trace_cap`` > 0 (L-BFGS-B solver)
+    also returns the callback trace of every fitted voxel (``FitResult.iteration_infos``) -- meant for the
+    sampled voxels of the convergence plots (utils/t2map_utils.py:115-292), pass their indices only.
     """
     lib = init()
+    solver = resolve_solver(fit, solver)
     p, o = _abi.Problem(), _abi.Outputs()
-    keep = [_fill_problem(p, fit, fit_params, TEeffs, prior, norm, max_iter, tol, init_mode)]
+    keep = [_fill_problem(p, fit, fit_params, TEeffs, prior, norm, max_iter, tol, init_mode, solver)]
+    tracing = solver == "lbfgsb" and trace_cap > 0
     dev = _is_torch(reshaped_t2w)
     if dev:
         import torch
@@ -220,6 +264,10 @@ def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=
                "fun": alloc() if "fun" in want else None,
                "nit": alloc(torch.int32) if "nit" in want else None,
                "status": alloc(torch.uint8) if "status" in want else None}
+        if tracing:
+            out["trace_f"] = torch.full((m, trace_cap), float("nan"), dtype=torch.float32, device=y.device)
+            out["trace_step"] = torch.full((m, trace_cap), float("nan"), dtype=torch.float32, device=y.device)
+            out["trace_len"] = torch.zeros(m, dtype=torch.int32, device=y.device)
         p.echoes, p.memory = y.data_ptr(), _abi.MEM_DEVICE
         p.mask_idx = idx.data_ptr() if idx is not None else None
         ptr = lambda t: t.data_ptr() if t is not None else None
@@ -239,6 +287,10 @@ def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=
                "fun": _host_array(m, np.float32) if "fun" in want else None,
                "nit": _host_array(m, np.int32) if "nit" in want else None,
                "status": _host_array(m, np.uint8) if "status" in want else None}
+        if tracing:
+            out["trace_f"] = np.full((m, trace_cap), np.nan, np.float32)
+            out["trace_step"] = np.full((m, trace_cap), np.nan, np.float32)
+            out["trace_len"] = np.zeros(m, np.int32)
         p.echoes, p.memory = y.ctypes.data, _abi.MEM_HOST
         p.mask_idx = idx.ctypes.data if idx is not None else None
         ptr = lambda a: a.ctypes.data if a is not None else None
@@ -246,6 +298,9 @@ def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=
         keep += [y, idx]
     if n_echo != p.n_echo:
         raise ValueError(f"reshaped_t2w has {n_echo} echoes, TEeffs has {p.n_echo}")
+    if tracing:
+        o.trace_f, o.trace_step, o.trace_len = ptr(out["trace_f"]), ptr(out["trace_step"]), ptr(out["trace_len"])
+        o.trace_cap = int(trace_cap)
     p.layout, p.ld, p.n_vox, p.n_fit = _abi.LAYOUT_AOS, 0, n_vox, m
     o.t2, o.k, o.res = ptr(out["t2"]), ptr(out["k"]), ptr(out["res"])
     o.sigma = ptr(out["sigma"]) if fit != "gaussian" else None
@@ -264,7 +319,8 @@ def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=
         # scipy raises inside the first such voxel and the reference's pool.map aborts the whole map
         raise ValueError(BOUNDS_ERROR)
     return FitResult(out["t2"], out["k"], out["sigma"], out["res"], out["fun"], out["nit"], out["status"], fit,
-                     counts if counts is not None else (0, 0, 0, 0))
+                     counts if counts is not None else (0, 0, 0, 0), solver, out.get("trace_f"), out.get("trace_step"),
+                     out.get("trace_len"))
 
 
 def mask_indices_device(mask, n_masks=None):
@@ -297,8 +353,9 @@ def t2map_volume(t2w, mask, TEeffs, fit, fit_params, prior=True, norm=False, **k
     shape3 = tuple(t2w.shape[:3])
     n_echo = t2w.shape[-1]
     p, o = _abi.Problem(), _abi.Outputs()
+    solver = resolve_solver(fit, kw.get("solver", "auto"))
     keep = [_fill_problem(p, fit, fit_params, TEeffs, prior, norm, kw.get("max_iter", 0), kw.get("tol", 0.0),
-                          kw.get("init_mode", "loglinear"))]
+                          kw.get("init_mode", "loglinear"), solver)]
     fused_mask = None
     if _is_torch(t2w):
         import torch

@@ -8,6 +8,7 @@
 #include <string>
 #include "../../include/t2fit.h"
 #include "t2fit_core.cuh"
+#include "t2fit_lbfgsb.cuh"
 
 namespace t2fit {
 
@@ -17,6 +18,54 @@ constexpr float kDefaultTolMono = 2e-3f;
 constexpr float kDefaultTolFloor = 1e-5f;
 
 inline int n_params(int model) { return model == T2FIT_MODEL_GAUSSIAN ? 2 : 3; }
+
+// box in force for every voxel (lb[0] is replaced per voxel under --no_prior), run_t2mapping.py:243-245
+inline int problem_box(const t2fit_problem& p, double (&lb)[3], double (&ub)[3], std::string& err) {
+    const int np_ = n_params(p.model);
+    for (int i = 0; i < 3; ++i) { lb[i] = i < np_ ? p.lb[i] : 0.0; ub[i] = i < np_ ? p.ub[i] : 0.0; }
+    if (p.no_prior) {
+        ub[0] = p.no_prior_k_ub;
+        lb[1] = p.no_prior_t2_lb;
+        ub[1] = p.no_prior_t2_ub;
+    }
+    for (int i = 0; i < np_; ++i) {
+        if (i == 0 && p.no_prior) continue;          // lb[0] is the voxel's first echo
+        if (!(lb[i] <= ub[i])) { err = "An upper bound is less than the corresponding lower bound."; return T2FIT_EINVAL; }
+    }
+    return T2FIT_OK;
+}
+
+// constants of the reference-faithful solver (T2FIT_SOLVER_LBFGSB)
+inline int make_lb_consts(const t2fit_problem& p, lb::LbConsts& c, std::string& err) {
+    if (p.n_echo < 2 || p.n_echo > kMaxEcho) { err = "n_echo must be in [2, 32]"; return T2FIT_EINVAL; }
+    if (p.model < T2FIT_MODEL_GAUSSIAN || p.model > T2FIT_MODEL_RICIAN) { err = "unknown model"; return T2FIT_EINVAL; }
+    if (!p.te_ms) { err = "te_ms is NULL"; return T2FIT_EINVAL; }
+    if (p.n_fit < 0 || p.n_vox < 0) { err = "negative size"; return T2FIT_EINVAL; }
+    double lbv[3], ubv[3];
+    int rc = problem_box(p, lbv, ubv, err);
+    if (rc) return rc;
+    const int np_ = n_params(p.model);
+    for (int e = 0; e < kMaxEcho; ++e) {
+        const double te = e < p.n_echo ? p.te_ms[e] : 0.0;
+        if (!isfinite(te)) { err = "non-finite echo time"; return T2FIT_EINVAL; }
+        c.te[e] = te;
+    }
+    for (int i = 0; i < 3; ++i) { c.x0[i] = i < np_ ? p.x0[i] : 0.0; c.lb[i] = lbv[i]; c.ub[i] = ubv[i]; }
+    c.ftol = p.lbfgsb_ftol > 0.0 ? p.lbfgsb_ftol : 2.220446049250313e-09;
+    c.pgtol = p.lbfgsb_gtol > 0.0 ? p.lbfgsb_gtol : 1e-5;
+    c.fd_step = 1e-8;
+#ifdef T2FIT_HOSTSIM
+    if (p.tol < 0.f) c.fd_step = -1.0;              // hostsim test hook: analytic gradient
+#endif
+    c.maxls = p.lbfgsb_maxls > 0 ? p.lbfgsb_maxls : 20;
+    c.maxiter = p.lbfgsb_maxiter > 0 ? p.lbfgsb_maxiter : 15000;
+    c.maxfun = p.lbfgsb_maxfun > 0 ? p.lbfgsb_maxfun : 15000;
+    c.n_echo = p.n_echo;
+    c.no_prior = p.no_prior ? 1 : 0;
+    c.norm = p.norm ? 1 : 0;
+    c.objective = p.model;
+    return T2FIT_OK;
+}
 
 inline int make_consts(const t2fit_problem& p, FitConsts& c, std::string& err) {
     if (p.n_echo < 2 || p.n_echo > kMaxEcho) { err = "n_echo must be in [2, 32]"; return T2FIT_EINVAL; }

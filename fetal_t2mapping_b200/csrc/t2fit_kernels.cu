@@ -50,6 +50,11 @@ struct KernelIO {
     unsigned long long* counts;  // [4] per-status voxel counts of this launch (OK slot unused)
     int dense;                   // outputs indexed by idx[i] instead of i (status/nit/fun stay compact)
     int vec_ok;                  // AoS base pointer is 16-byte aligned
+    int layout;                  // T2FIT_LAYOUT_* (run-time for the L-BFGS-B kernel)
+    float* trace_f;              // L-BFGS-B solver only: callback trace, row i at i * trace_cap
+    float* trace_step;
+    int32_t* trace_len;
+    int trace_cap;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -197,6 +202,68 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
     }
     // warp-aggregated status histogram: one atomic per warp per non-OK status (normally none)
     const int st = valid ? f.status : 0;
+    const unsigned any_bad = __ballot_sync(0xffffffffu, st != 0);
+    if (any_bad && io.counts) {
+#pragma unroll
+        for (int s = 1; s < 4; ++s) {
+            const unsigned m = __ballot_sync(0xffffffffu, st == s);
+            if (m && (threadIdx.x & 31) == 0) atomicAdd(io.counts + s, (unsigned long long)__popc(m));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lbfgsb_kernel: the reference-faithful solver (t2fit_lbfgsb.cuh), one voxel per thread, FP64.
+// The optimiser state (compact L-BFGS matrices, ~10 KB) lives in per-thread local memory; the kernel
+// is bound by FP64 issue and L1/L2 traffic of that state, not by HBM.  Epilogue as
+// fit_kernel: maps store float32(x) as the reference's scatter does (:455-458), res is evaluated from
+// those stored values as compute_residuals does (utils/t2map_utils.py:62-89).
+// ------------------------------------------------------------------------------------------------
+constexpr int kLbBlock = 128;
+
+template <int OBJ>
+__global__ void __launch_bounds__(kLbBlock) lbfgsb_kernel(const __grid_constant__ lb::LbConsts c,
+                                                          const __grid_constant__ KernelIO io) {
+    const int64_t i = (int64_t)blockIdx.x * kLbBlock + threadIdx.x;
+    const bool valid = i < io.n_fit;
+    const int64_t ii = valid ? i : io.n_fit - 1;
+    const int64_t row = io.idx ? __ldg(io.idx + ii) : ii;
+    const int E = c.n_echo;
+    float y[kMaxEcho];
+    if (io.layout == T2FIT_LAYOUT_AOS) { for (int e = 0; e < E; ++e) y[e] = __ldg(io.echoes + row * E + e); }
+    else { for (int e = 0; e < E; ++e) y[e] = __ldg(io.echoes + (int64_t)e * io.ld + ii); }
+
+    int tl = 0;
+    float* tf = (valid && io.trace_f) ? io.trace_f + i * io.trace_cap : nullptr;
+    float* ts = (valid && io.trace_step) ? io.trace_step + i * io.trace_cap : nullptr;
+    const lb::LbVoxel v = lb::lbfgsb_voxel<OBJ>(y, c, valid, tf, ts, (tf || ts) ? io.trace_cap : 0, &tl);
+
+    if (valid) {
+        const float kf = (float)v.x[0], t2f = (float)v.x[1], sf = (OBJ == 0) ? 0.f : (float)v.x[2];
+        // residual epilogue on the stored float32 values (signal normalised as the fit saw it)
+        float scale = 1.f;
+        if (c.norm) {
+            float mx = y[0];
+            for (int e = 1; e < E; ++e) mx = fmaxf(mx, y[e]);
+            scale = 1.0f / mx;
+        }
+        double acc = 0.0;
+        for (int e = 0; e < E; ++e) {
+            double pred = (double)kf * exp(-c.te[e] / (double)t2f);
+            if (OBJ != 0) pred = sqrt(pred * pred + (double)sf * (double)sf);
+            acc += (double)(y[e] * scale) - (double)(float)pred;
+        }
+        const int64_t o = io.dense ? row : i;
+        if (io.t2) io.t2[o] = t2f;
+        if (io.k) io.k[o] = kf;
+        if (OBJ != 0 && io.sigma) io.sigma[o] = sf;
+        if (io.res) io.res[o] = (float)(acc / (double)E);
+        if (io.fun) io.fun[i] = (float)v.fun;
+        if (io.nit) io.nit[i] = v.nit;
+        if (io.status) io.status[i] = (uint8_t)v.status;
+        if (io.trace_len) io.trace_len[i] = tl;
+    }
+    const int st = valid ? v.status : 0;
     const unsigned any_bad = __ballot_sync(0xffffffffu, st != 0);
     if (any_bad && io.counts) {
 #pragma unroll
@@ -378,6 +445,15 @@ FitFn pick_kernel(int model, int n_echo, int layout) {
     return layout == T2FIT_LAYOUT_AOS ? pick_e<kFloor3, T2FIT_LAYOUT_AOS>(n_echo) : pick_e<kFloor3, T2FIT_LAYOUT_SOA>(n_echo);
 }
 
+using LbFn = void (*)(const lb::LbConsts, const KernelIO);
+
+LbFn pick_lb_kernel(int model, int n_echo) {
+    if (n_echo < 2 || n_echo > kMaxEcho) return nullptr;
+    if (model == T2FIT_MODEL_GAUSSIAN) return lbfgsb_kernel<0>;
+    if (model == T2FIT_MODEL_GAUSSIAN_RICIAN) return lbfgsb_kernel<1>;
+    return lbfgsb_kernel<2>;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host context
 // ------------------------------------------------------------------------------------------------
@@ -519,6 +595,17 @@ int launch_fit(Context* c, const FitConsts& fc, KernelIO io, int model, int n_ec
     return T2FIT_OK;
 }
 
+int launch_lbfgsb(Context* c, const lb::LbConsts& lc, KernelIO io, int model, int n_echo, cudaStream_t st) {
+    if (io.n_fit <= 0) return T2FIT_OK;
+    LbFn fn = pick_lb_kernel(model, n_echo);
+    if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
+    const int64_t blocks = (io.n_fit + kLbBlock - 1) / kLbBlock;
+    if (blocks > 0x7fffffffLL) return fail(T2FIT_EINVAL, "n_fit too large for one launch");
+    fn<<<(unsigned)blocks, kLbBlock, 0, st>>>(lc, io);
+    CU_TRY(cudaGetLastError());
+    return T2FIT_OK;
+}
+
 // zero-fill of the dense maps on the side stream, forked from and joined back into `st`
 int launch_zero_fill(Context* c, const FillArgs& fa, bool sigma_all, cudaStream_t st, bool* forked) {
     *forked = false;
@@ -553,9 +640,27 @@ double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitConsts& fc) {
+int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitConsts& fc, const lb::LbConsts* lc) {
     int rc = ensure_slots(c, p.n_echo);
     if (rc) return rc;
+    // callback traces (L-BFGS-B solver, sampled voxels): per-slot device scratch for this call only
+    const bool tracing = lc && p.n_fit > 0 && o.trace_cap > 0 && (o.trace_f || o.trace_step || o.trace_len);
+    struct TraceScratch { float* f = nullptr; float* s = nullptr; int32_t* n = nullptr; } tsc[kSlots];
+    auto free_trace = [&]() {
+        for (auto& t : tsc) { if (t.f) cudaFree(t.f); if (t.s) cudaFree(t.s); if (t.n) cudaFree(t.n); t = TraceScratch{}; }
+    };
+    if (tracing) {
+        const int64_t nmax = std::min<int64_t>(kChunk, p.n_fit);
+        for (auto& t : tsc) {
+            if (cudaMalloc(&t.f, sizeof(float) * nmax * o.trace_cap) != cudaSuccess ||
+                cudaMalloc(&t.s, sizeof(float) * nmax * o.trace_cap) != cudaSuccess ||
+                cudaMalloc(&t.n, sizeof(int32_t) * nmax) != cudaSuccess) {
+                cudaGetLastError();
+                free_trace();
+                return fail(T2FIT_ENOMEM, "trace scratch: ask for traces of a sampled subset of voxels");
+            }
+        }
+    }
     const int E = p.n_echo;
     const int64_t M = p.n_fit;
     static const bool profile = getenv("T2FIT_HOST_PROFILE") != nullptr;
@@ -646,9 +751,19 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
         io.t2 = df; io.k = df + n; io.sigma = df + 2 * n; io.res = df + 3 * n; io.fun = df + 4 * n;
         io.nit = reinterpret_cast<int32_t*>(s.d_out + (size_t)5 * n * sizeof(float));
         io.status = s.d_out + (size_t)5 * n * sizeof(float) + (size_t)n * sizeof(int32_t);
-        io.counts = c->d_counts; io.dense = 0; io.vec_ok = 1;
-        rc = launch_fit(c, fc, io, p.model, E, p.layout, s.stream);
-        if (rc) return rc;
+        io.counts = c->d_counts; io.dense = 0; io.vec_ok = 1; io.layout = p.layout;
+        if (tracing) {
+            TraceScratch& t = tsc[ch % kSlots];
+            io.trace_f = t.f; io.trace_step = t.s; io.trace_len = t.n; io.trace_cap = o.trace_cap;
+        }
+        rc = lc ? launch_lbfgsb(c, *lc, io, p.model, E, s.stream) : launch_fit(c, fc, io, p.model, E, p.layout, s.stream);
+        if (rc) { free_trace(); return rc; }
+        if (tracing) {
+            const size_t tb = sizeof(float) * (size_t)n * o.trace_cap;
+            if (o.trace_f) CU_TRY(cudaMemcpyAsync(o.trace_f + first * o.trace_cap, io.trace_f, tb, cudaMemcpyDeviceToHost, s.stream));
+            if (o.trace_step) CU_TRY(cudaMemcpyAsync(o.trace_step + first * o.trace_cap, io.trace_step, tb, cudaMemcpyDeviceToHost, s.stream));
+            if (o.trace_len) CU_TRY(cudaMemcpyAsync(o.trace_len + first, io.trace_len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s.stream));
+        }
         s.direct = direct;
         if (direct) {
             auto d2h = [&](void* dst, const void* src, size_t bytes) {
@@ -682,6 +797,7 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
     CU_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->slots[0].stream));
     CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), c->slots[0].stream));
     CU_TRY(cudaStreamSynchronize(c->slots[0].stream));
+    free_trace();
     int64_t bad = 0;
     for (int s = 1; s < 4; ++s) { o.status_count[s] = (int64_t)c->h_counts[s]; bad += o.status_count[s]; }
     o.status_count[0] = M - bad;
@@ -778,9 +894,15 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     if (!c) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded (no CUDA device bound; there is no CPU fit)");
     if (!p || !o) return fail(T2FIT_EINVAL, "NULL problem/outputs");
     FitConsts fc;
+    lb::LbConsts lc;
     memset(&fc, 0, sizeof(fc));
+    memset(&lc, 0, sizeof(lc));
     std::string err;
-    int rc = make_consts(*p, fc, err);
+    if (p->solver != T2FIT_SOLVER_FAST && p->solver != T2FIT_SOLVER_LBFGSB) return fail(T2FIT_EINVAL, "unknown solver");
+    const bool lbs = p->solver == T2FIT_SOLVER_LBFGSB;
+    if (!lbs && p->model == T2FIT_MODEL_RICIAN)
+        return fail(T2FIT_EINVAL, "fit 'rician' (negative log-likelihood) needs solver T2FIT_SOLVER_LBFGSB");
+    int rc = lbs ? make_lb_consts(*p, lc, err) : make_consts(*p, fc, err);
     if (rc) return fail(rc, err);
     const bool fill_only = p->n_fit == 0 && p->memory == T2FIT_MEM_DEVICE && o->dense && o->zero_fill_mask;
     if (p->n_fit == 0 && !fill_only) { memset(o->status_count, 0, sizeof(o->status_count)); return T2FIT_OK; }
@@ -790,7 +912,7 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     if (p->layout == T2FIT_LAYOUT_AOS && !p->mask_idx && p->n_fit > p->n_vox) return fail(T2FIT_EINVAL, "n_fit > n_vox");
     if (o->dense && !p->mask_idx && p->n_fit > p->n_vox) return fail(T2FIT_EINVAL, "dense output needs n_vox >= n_fit");
     CU_TRY(cudaSetDevice(c->device));
-    if (p->memory == T2FIT_MEM_HOST) return run_host(c, *p, *o, fc);
+    if (p->memory == T2FIT_MEM_HOST) return run_host(c, *p, *o, fc, lbs ? &lc : nullptr);
     if (p->memory != T2FIT_MEM_DEVICE) return fail(T2FIT_EINVAL, "bad memory kind");
 
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
@@ -799,6 +921,10 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     io.t2 = o->t2; io.k = o->k; io.sigma = o->sigma; io.res = o->res; io.fun = o->fun; io.nit = o->nit;
     io.status = o->status; io.counts = c->d_counts; io.dense = o->dense;
     io.vec_ok = (reinterpret_cast<uintptr_t>(p->echoes) % 16) == 0;
+    io.layout = p->layout;
+    if (lbs && o->trace_cap > 0) {
+        io.trace_f = o->trace_f; io.trace_step = o->trace_step; io.trace_len = o->trace_len; io.trace_cap = o->trace_cap;
+    }
     bool forked = false;
     if (o->dense && o->zero_fill_mask) {
         // np.zeros_like x4 (:415-418) on the side stream, concurrent with the fit (disjoint slots)
@@ -813,7 +939,7 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
         if (rc) return rc;
     }
     c->counts_dirty = true;
-    rc = launch_fit(c, fc, io, p->model, p->n_echo, p->layout, st);
+    rc = lbs ? launch_lbfgsb(c, lc, io, p->model, p->n_echo, st) : launch_fit(c, fc, io, p->model, p->n_echo, p->layout, st);
     if (forked) CU_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));           // join: results complete on `st`
     return rc;
 }

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define T2FIT_ABI_VERSION 1
+#define T2FIT_ABI_VERSION 2
 #define T2FIT_MAX_ECHO 32
 
 /* return codes */
@@ -40,6 +40,17 @@ extern "C" {
 /* fit model = the reference's `fit` string (run_t2mapping.py:37,48) */
 #define T2FIT_MODEL_GAUSSIAN 0        /* 'gaussian'        k exp(-te/T2)                   :129-131 */
 #define T2FIT_MODEL_GAUSSIAN_RICIAN 1 /* 'gaussian_rician' sqrt(k^2 exp(-2te/T2)+sigma^2)  :133-138 */
+#define T2FIT_MODEL_RICIAN 2          /* 'rician'  Rician negative log-likelihood (i0e)     :157-177;
+                                         T2FIT_SOLVER_LBFGSB only (it is not a least-squares problem) */
+
+/* which optimiser runs per voxel */
+#define T2FIT_SOLVER_FAST 0   /* float32 register-resident Newton / Levenberg-Marquardt: converges to the bounded
+                                 minimiser of the objective (what the reference's optimiser approaches) */
+#define T2FIT_SOLVER_LBFGSB 1 /* float64 restatement of the reference's own optimiser: scipy L-BFGS-B (m = 10) with
+                                 2-point finite-difference gradients, started from the clipped preset x0, stopped
+                                 by the preset's ftol / gtol / maxls (:260-286).  Reproduces the reference's result
+                                 -- params, success, nit, fun and the callback trace -- also where the reference
+                                 stops before convergence (ftol = gtol = 1e-2 presets). */
 
 /* echo layout */
 #define T2FIT_LAYOUT_AOS 0 /* reshaped_t2w: [n_vox, n_echo] row-major float32 (run_t2mapping.py:411) */
@@ -52,7 +63,8 @@ extern "C" {
 /* per-voxel status byte */
 #define T2FIT_ST_OK 0           /* result.success == True                                            */
 #define T2FIT_ST_NONFINITE 1    /* NaN/Inf echo: reference returns success False, x = clipped x0     */
-#define T2FIT_ST_NOTCONVERGED 2 /* iteration cap hit (reference: maxiter -> success False)           */
+#define T2FIT_ST_NOTCONVERGED 2 /* optimiser gave up on finite input: iteration cap, or (L-BFGS-B) line-search
+                                   failure / maxiter / maxfun (reference: success False)             */
 #define T2FIT_ST_BADBOUNDS 3    /* --no_prior and S(TE0) > k upper bound: scipy raises ValueError    */
 
 /* initial guess of the iteration */
@@ -81,7 +93,12 @@ typedef struct t2fit_problem {
     int32_t norm;            /* divide each row by its maximum (:237-240; utils/t2map_utils.py:74-79) */
     int32_t max_iter;        /* cap on passes over the echoes per voxel; 0 = default */
     float tol;               /* relative step tolerance; 0 = default */
-    int32_t init;            /* T2FIT_INIT_* */
+    int32_t init;            /* T2FIT_INIT_* (FAST solver only; LBFGSB always starts from the clipped x0) */
+    int32_t solver;          /* T2FIT_SOLVER_* */
+    /* fit_params['options'] of the reference's minimize() call (:40-45,:51-57,...); LBFGSB solver only.
+       0 selects scipy's default: ftol 2.220446049250313e-09, gtol 1e-5, maxls 20, maxiter = maxfun = 15000. */
+    double lbfgsb_ftol, lbfgsb_gtol;
+    int32_t lbfgsb_maxls, lbfgsb_maxiter, lbfgsb_maxfun;
 } t2fit_problem;
 
 /* Results.  Any pointer may be NULL (that output is skipped).  Parameter maps follow the reference's
@@ -90,11 +107,18 @@ typedef struct t2fit_outputs {
     float *t2, *k, *sigma, *res; /* dense != 0: [n_vox] maps, only masked slots written (caller zero-fills,
                                     as :415-418); dense == 0: [n_fit] compact */
     uint8_t *status;             /* [n_fit] T2FIT_ST_* (== 0  <=>  convergence_flags[i], :450) */
-    int32_t *nit;                /* [n_fit] passes used (num_iterations_array, :451; counts differ from L-BFGS-B) */
+    int32_t *nit;                /* [n_fit] num_iterations_array (:451): L-BFGS-B iterations (LBFGSB solver) or passes
+                                    of the FAST solver (a different count) */
     float *fun;                  /* [n_fit] mean squared error at the solution (final_errors_array, :452) */
     int32_t dense;
     int64_t status_count[4];     /* OUT (host): voxels per status; filled when the call is synchronous
                                     (T2FIT_MEM_HOST) or by t2fit_status_counts() */
+    /* iteration_info of the callback (:180-234), LBFGSB solver only, any may be NULL: per voxel up to trace_cap
+       entries of f_val and step_size (NaN for the first iteration, as the reference) and the entry count
+       (= min(nit, trace_cap)).  Row i of trace_f / trace_step starts at i * trace_cap. */
+    float *trace_f, *trace_step;
+    int32_t *trace_len;
+    int32_t trace_cap;
     const uint8_t *zero_fill_mask; /* device calls with dense != 0 only: the [n_vox] uint8 mask (1 byte per voxel,
                                     nonzero = masked, consistent with mask_idx).  When given, the call also
                                     zero-fills every unmasked slot of the four maps (np.zeros_like, :415-418)

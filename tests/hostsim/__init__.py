@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libt2fit_hostsim.so")
 SRC = os.path.join(HERE, "hostsim.cpp")
 DEPS = [SRC] + [os.path.join(HERE, "..", "..", "fetal_t2mapping_b200", "csrc", f)
-                for f in ("t2fit_core.cuh", "t2fit_consts.h")] + [os.path.join(HERE, "..", "..", "include", "t2fit.h")]
+                for f in ("t2fit_core.cuh", "t2fit_consts.h", "t2fit_lbfgsb.cuh", "t2fit_i0e_coeffs.h")] + [os.path.join(HERE, "..", "..", "include", "t2fit.h")]
 
 
 def build(force=False):
@@ -33,10 +33,13 @@ def lib():
         _lib = C.CDLL(build())
         _lib.hostsim_fit.restype = C.c_int
         _lib.hostsim_last_error.restype = C.c_char_p
+        _lib.hostsim_lbfgsb.restype = C.c_int
+        _lib.hostsim_i0e.restype = C.c_double
+        _lib.hostsim_i0e.argtypes = [C.c_double]
     return _lib
 
 
-def make_problem(rows, te, fit, x0, bounds, prior, norm, max_iter=0, tol=0.0, init=0):
+def make_problem(rows, te, fit, x0, bounds, prior, norm, max_iter=0, tol=0.0, init=0, options=None):
     rows = np.ascontiguousarray(rows, np.float32)
     te = np.ascontiguousarray(te, np.float64)
     p = _abi.Problem()
@@ -58,6 +61,13 @@ def make_problem(rows, te, fit, x0, bounds, prior, norm, max_iter=0, tol=0.0, in
     p.max_iter = max_iter
     p.tol = tol
     p.init = init
+    if options is not None:
+        p.solver = _abi.SOLVER_LBFGSB
+        p.lbfgsb_ftol = float(options.get("ftol", 0.0))
+        p.lbfgsb_gtol = float(options.get("gtol", 0.0))
+        p.lbfgsb_maxls = int(options.get("maxls", 0))
+        p.lbfgsb_maxiter = int(options.get("maxiter", 0))
+        p.lbfgsb_maxfun = int(options.get("maxfun", 0))
     return p, (rows, te)
 
 
@@ -71,4 +81,23 @@ def fit(rows, te, fit, x0, bounds, prior, norm=False, use_double=False, **kw):
                                                          ("k", "t2", "sigma", "res", "fun", "nit", "status")])
     if rc:
         raise ValueError(lib().hostsim_last_error().decode())
+    return out
+
+
+def lbfgsb(rows, te, fit, x0, bounds, prior, norm=False, options=None, trace_cap=0, tol=0.0):
+    """The reference-faithful solver (csrc/t2fit_lbfgsb.cuh) compiled for the host."""
+    p, keep = make_problem(rows, te, fit, x0, bounds, prior, norm, options=options or {}, tol=tol)
+    m = keep[0].shape[0]
+    out = {"x": np.zeros((m, 3), np.float64), "fun": np.zeros(m, np.float64), "nit": np.zeros(m, np.int32),
+           "nfev": np.zeros(m, np.int32), "status": np.zeros(m, np.uint8), "result": np.zeros(m, np.int32)}
+    tf = np.full((m, max(trace_cap, 1)), np.nan, np.float32)
+    ts = np.full((m, max(trace_cap, 1)), np.nan, np.float32)
+    tl = np.zeros(m, np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().hostsim_lbfgsb(C.byref(p), vp(out["x"]), vp(out["fun"]), vp(out["nit"]), vp(out["nfev"]), vp(out["status"]),
+                              vp(out["result"]), vp(tf) if trace_cap else None, vp(ts) if trace_cap else None, vp(tl),
+                              C.c_int(trace_cap))
+    if rc:
+        raise ValueError(lib().hostsim_last_error().decode())
+    out["trace_f"], out["trace_step"], out["trace_len"] = tf, ts, tl
     return out

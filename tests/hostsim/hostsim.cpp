@@ -56,3 +56,36 @@ extern "C" int hostsim_fit(const t2fit_problem* p, int use_double, float* k, flo
     return mono ? dispatch_e<float, kMono2>(p->n_echo, p->echoes, p->n_fit, c, k, t2, sigma, res, fun, nit, status)
                 : dispatch_e<float, kFloor3>(p->n_echo, p->echoes, p->n_fit, c, k, t2, sigma, res, fun, nit, status);
 }
+
+// ------------------------------------------------------------------------------------------------
+// reference-faithful solver (t2fit_lbfgsb.cuh) on the host: checked against scipy's L-BFGS-B itself
+// ------------------------------------------------------------------------------------------------
+template <int OBJ>
+static int dispatch_lb(int n_echo, const float* rows, int64_t m, const lb::LbConsts& c, double* x, double* fun, int32_t* nit,
+                       int32_t* nfev, uint8_t* status, int32_t* result, float* trace_f, float* trace_step, int32_t* trace_len,
+                       int trace_cap) {
+    for (int64_t i = 0; i < m; ++i) {
+        int tl = 0;
+        const lb::LbVoxel v = lb::lbfgsb_voxel<OBJ>(rows + i * n_echo, c, true, trace_f ? trace_f + i * trace_cap : nullptr,
+                                                    trace_step ? trace_step + i * trace_cap : nullptr, trace_cap, &tl);
+        x[3 * i] = v.x[0]; x[3 * i + 1] = v.x[1]; x[3 * i + 2] = v.x[2];
+        fun[i] = v.fun; nit[i] = v.nit; nfev[i] = v.nfev; status[i] = (uint8_t)v.status; result[i] = v.result;
+        if (trace_len) trace_len[i] = tl;
+    }
+    return 0;
+}
+
+extern "C" int hostsim_lbfgsb(const t2fit_problem* p, double* x, double* fun, int32_t* nit, int32_t* nfev, uint8_t* status,
+                              int32_t* result, float* trace_f, float* trace_step, int32_t* trace_len, int trace_cap) {
+    lb::LbConsts c;
+    memset(&c, 0, sizeof(c));
+    int rc = make_lb_consts(*p, c, g_err);
+    if (rc) return rc;
+    switch (p->model) {
+        case T2FIT_MODEL_GAUSSIAN: return dispatch_lb<0>(p->n_echo, p->echoes, p->n_fit, c, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+        case T2FIT_MODEL_GAUSSIAN_RICIAN: return dispatch_lb<1>(p->n_echo, p->echoes, p->n_fit, c, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+        default: return dispatch_lb<2>(p->n_echo, p->echoes, p->n_fit, c, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+    }
+}
+
+extern "C" double hostsim_i0e(double x) { return lb::i0e(x); }
