@@ -32,8 +32,10 @@
 // the optimiser core is compiled once per parameter count (not once per echo count): out-of-line on the device
 #if T2_DEVICE_BUILD
 #define T2_NI __device__ __noinline__
+#define T2_ROLLED _Pragma("unroll 1")      // keep the optimiser core compact: it must stay resident in the instruction cache
 #else
 #define T2_NI inline
+#define T2_ROLLED
 #endif
 
 namespace t2fit {
@@ -76,6 +78,11 @@ T2_HD float mulf(float a, float b) { volatile float r = a * b; return r; }
 T2_HD float addf(float a, float b) { volatile float r = a + b; return r; }
 #endif
 
+// IEEE division / square root as out-of-line calls on the device: the inline expansions (~25 instructions each)
+// would otherwise make up most of the optimiser core's code size
+T2_NI double ddiv(double a, double b) { return a / b; }
+T2_NI double dsqrt(double a) { return sqrt(a); }
+
 // np.sum over a contiguous float64 vector: numpy's pairwise_sum -- plain loop below 8 elements, else 8
 // running lanes combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential tail (n <= 128)
 T2_HD double np_sum(const double* v, int n) {
@@ -111,7 +118,7 @@ T2_HD double chebev(double y, const double (&c)[NC]) {
     return 0.5 * (b0 - b2);
 }
 
-T2_HD double i0e(double x) {
+T2_NI double i0e(double x) {
     if (x < 0) x = -x;
     if (x <= 8.0) {
         const double a[T2FIT_I0E_NA] = {T2FIT_I0E_A_LIST};
@@ -128,7 +135,7 @@ T2_HD double i0e(double x) {
 // The echo count is a run-time value here (one kernel per objective): the optimiser core, not the
 // objective, dominates the cost of this solver.
 template <int OBJ>
-T2_HD double objective(const double* p, const float* y32, const LbConsts& c) {
+T2_NI double objective(const double* p, const float* y32, const LbConsts& c) {
     const int E = c.n_echo;
     double v[kMaxEcho];
     if constexpr (OBJ == 0) {                                   // gauss_obj :141-147
@@ -206,7 +213,7 @@ struct Solver {
     // ---- projected gradient norm -------------------------------------------------------
     T2_HD void projgr() {
         double s = 0.0;
-        for (int i = 0; i < N; ++i) {
+        T2_ROLLED for (int i = 0; i < N; ++i) {
             double gi = g[i];
             if (nbd[i] != 0) {
                 if (gi < 0.0) { if (nbd[i] >= 2) gi = rmax(x[i] - u[i], gi); }
@@ -224,39 +231,39 @@ struct Solver {
     // Cholesky A = R'R of the leading nn x nn block starting at (o, o), upper triangle in place; false = not SPD
     template <int LD>
     T2_HD static bool dpofa(double (&a)[LD][LD], int o, int nn) {
-        for (int j = 0; j < nn; ++j) {
+        T2_ROLLED for (int j = 0; j < nn; ++j) {
             double s = 0.0;
-            for (int k = 0; k < j; ++k) {
+            T2_ROLLED for (int k = 0; k < j; ++k) {
                 double tt = a[o + k][o + j];
-                for (int q = 0; q < k; ++q) tt -= a[o + q][o + k] * a[o + q][o + j];
-                tt = tt / a[o + k][o + k];
+                T2_ROLLED for (int q = 0; q < k; ++q) tt -= a[o + q][o + k] * a[o + q][o + j];
+                tt = ddiv(tt, a[o + k][o + k]);
                 a[o + k][o + j] = tt;
                 s += tt * tt;
             }
             s = a[o + j][o + j] - s;
             if (!(s > 0.0)) return false;
-            a[o + j][o + j] = sqrt(s);
+            a[o + j][o + j] = dsqrt(s);
         }
         return true;
     }
     // solve T' x = b (job 11) / T x = b (job 01), T = upper triangle of the leading nn x nn block; false = zero pivot
     template <int LD>
     T2_HD static bool dtrsl_t(const double (&a)[LD][LD], int nn, double* b) {
-        for (int j = 0; j < nn; ++j) if (a[j][j] == 0.0) return false;
-        for (int j = 0; j < nn; ++j) {
+        T2_ROLLED for (int j = 0; j < nn; ++j) if (a[j][j] == 0.0) return false;
+        T2_ROLLED for (int j = 0; j < nn; ++j) {
             double s = b[j];
-            for (int q = 0; q < j; ++q) s -= a[q][j] * b[q];
-            b[j] = s / a[j][j];
+            T2_ROLLED for (int q = 0; q < j; ++q) s -= a[q][j] * b[q];
+            b[j] = ddiv(s, a[j][j]);
         }
         return true;
     }
     template <int LD>
     T2_HD static bool dtrsl_n(const double (&a)[LD][LD], int nn, double* b) {
-        for (int j = 0; j < nn; ++j) if (a[j][j] == 0.0) return false;
-        for (int j = nn - 1; j >= 0; --j) {
+        T2_ROLLED for (int j = 0; j < nn; ++j) if (a[j][j] == 0.0) return false;
+        T2_ROLLED for (int j = nn - 1; j >= 0; --j) {
             double s = b[j];
-            for (int q = j + 1; q < nn; ++q) s -= a[j][q] * b[q];
-            b[j] = s / a[j][j];
+            T2_ROLLED for (int q = j + 1; q < nn; ++q) s -= a[j][q] * b[q];
+            b[j] = ddiv(s, a[j][j]);
         }
         return true;
     }
@@ -265,18 +272,18 @@ struct Solver {
     T2_NI bool bmv(const double* v, double* p) const {
         if (col == 0) return true;
         p[col] = v[col];
-        for (int i = 1; i < col; ++i) {
+        T2_ROLLED for (int i = 1; i < col; ++i) {
             double sum = 0.0;
-            for (int k = 0; k < i; ++k) sum += sy[i][k] * v[k] / sy[k][k];
+            T2_ROLLED for (int k = 0; k < i; ++k) sum += ddiv(sy[i][k] * v[k], sy[k][k]);
             p[col + i] = v[col + i] + sum;
         }
         if (!dtrsl_t<kM>(wt, col, p + col)) return false;
-        for (int i = 0; i < col; ++i) p[i] = v[i] / sqrt(sy[i][i]);
+        T2_ROLLED for (int i = 0; i < col; ++i) p[i] = ddiv(v[i], dsqrt(sy[i][i]));
         if (!dtrsl_n<kM>(wt, col, p + col)) return false;
-        for (int i = 0; i < col; ++i) p[i] = -p[i] / sqrt(sy[i][i]);
-        for (int i = 0; i < col; ++i) {
+        T2_ROLLED for (int i = 0; i < col; ++i) p[i] = ddiv(-p[i], dsqrt(sy[i][i]));
+        T2_ROLLED for (int i = 0; i < col; ++i) {
             double sum = 0.0;
-            for (int k = i + 1; k < col; ++k) sum += sy[k][i] * p[col + k] / sy[i][i];
+            T2_ROLLED for (int k = i + 1; k < col; ++k) sum += ddiv(sy[k][i] * p[col + k], sy[i][i]);
             p[i] += sum;
         }
         return true;
@@ -284,7 +291,7 @@ struct Solver {
 
     // ---- generalized Cauchy point: z (= xcp), iwhere, c = W'(xcp - x); false = singular middle matrix ----
     T2_NI bool cauchy() {
-        for (int i = 0; i < N; ++i) z[i] = x[i];
+        T2_ROLLED for (int i = 0; i < N; ++i) z[i] = x[i];
         if (sbgnrm <= 0.0) return true;
         bool bnded = true, any_unbounded = false;
         int nbreak = 0, ibkmin = 0;
@@ -292,8 +299,8 @@ struct Solver {
         double bkmin = 0.0, f1 = 0.0;
         double dd[N], tt[N], wbp[M2], v[M2];
         int iorder[N];
-        for (int i = 0; i < col2; ++i) pc[i] = 0.0;
-        for (int i = 0; i < N; ++i) {
+        T2_ROLLED for (int i = 0; i < col2; ++i) pc[i] = 0.0;
+        T2_ROLLED for (int i = 0; i < N; ++i) {
             const double neggi = -g[i];
             double tl = 0.0, tu = 0.0;
             if (iwhere[i] != 3 && iwhere[i] != -1) {
@@ -311,17 +318,17 @@ struct Solver {
             } else {
                 dd[i] = neggi;
                 f1 -= neggi * neggi;
-                for (int j = 0; j < col; ++j) {                 // p := p - W'e_i g_i
+                T2_ROLLED for (int j = 0; j < col; ++j) {                 // p := p - W'e_i g_i
                     const int pt = (head + j) % kM;
                     pc[j] += wy[pt][i] * neggi;
                     pc[col + j] += ws[pt][i] * neggi;
                 }
                 if (nbd[i] <= 2 && nbd[i] != 0 && neggi < 0.0) {
-                    iorder[nbreak] = i; tt[nbreak] = tl / (-neggi);
+                    iorder[nbreak] = i; tt[nbreak] = ddiv(tl, -neggi);
                     if (nbreak == 0 || tt[nbreak] < bkmin) { bkmin = tt[nbreak]; ibkmin = nbreak; }
                     ++nbreak;
                 } else if (nbd[i] >= 2 && neggi > 0.0) {
-                    iorder[nbreak] = i; tt[nbreak] = tu / neggi;
+                    iorder[nbreak] = i; tt[nbreak] = ddiv(tu, neggi);
                     if (nbreak == 0 || tt[nbreak] < bkmin) { bkmin = tt[nbreak]; ibkmin = nbreak; }
                     ++nbreak;
                 } else {
@@ -330,18 +337,18 @@ struct Solver {
                 }
             }
         }
-        if (theta != 1.0) for (int j = 0; j < col; ++j) pc[col + j] *= theta;
+        if (theta != 1.0) T2_ROLLED for (int j = 0; j < col; ++j) pc[col + j] *= theta;
         if (nbreak == 0 && !any_unbounded) return true;        // d is the zero vector
-        for (int i = 0; i < col2; ++i) cc[i] = 0.0;
+        T2_ROLLED for (int i = 0; i < col2; ++i) cc[i] = 0.0;
         double f2 = -theta * f1;
         const double f2_org = f2;
         if (col > 0) {
             if (!bmv(pc, v)) return false;
             double dot = 0.0;
-            for (int i = 0; i < col2; ++i) dot += v[i] * pc[i];
+            T2_ROLLED for (int i = 0; i < col2; ++i) dot += v[i] * pc[i];
             f2 -= dot;
         }
-        double dtm = -f1 / f2, tsum = 0.0;
+        double dtm = ddiv(-f1, f2), tsum = 0.0;
         bool all_fixed = false;
         if (nbreak > 0) {
             int nleft = nbreak, it = 1;
@@ -354,7 +361,7 @@ struct Solver {
                 } else {
                     if (it == 2 && ibkmin != nbreak - 1) { tt[ibkmin] = tt[nbreak - 1]; iorder[ibkmin] = iorder[nbreak - 1]; }
                     int jm = 0;                               // least of the remaining breakpoints -> slot nleft-1
-                    for (int j = 1; j < nleft; ++j) if (tt[j] < tt[jm]) jm = j;
+                    T2_ROLLED for (int j = 1; j < nleft; ++j) if (tt[j] < tt[jm]) jm = j;
                     const double tv = tt[jm]; const int iv = iorder[jm];
                     tt[jm] = tt[nleft - 1]; iorder[jm] = iorder[nleft - 1];
                     tt[nleft - 1] = tv; iorder[nleft - 1] = iv;
@@ -373,32 +380,32 @@ struct Solver {
                 f1 = f1 + dt * f2 + dibp2 - theta * dibp * zibp;
                 f2 = f2 - theta * dibp2;
                 if (col > 0) {
-                    for (int i = 0; i < col2; ++i) cc[i] += dt * pc[i];
-                    for (int j = 0; j < col; ++j) {
+                    T2_ROLLED for (int i = 0; i < col2; ++i) cc[i] += dt * pc[i];
+                    T2_ROLLED for (int j = 0; j < col; ++j) {
                         const int pt = (head + j) % kM;
                         wbp[j] = wy[pt][ibp];
                         wbp[col + j] = theta * ws[pt][ibp];
                     }
                     if (!bmv(wbp, v)) return false;
                     double wmc = 0.0, wmp = 0.0, wmw = 0.0;
-                    for (int i = 0; i < col2; ++i) { wmc += cc[i] * v[i]; wmp += pc[i] * v[i]; wmw += wbp[i] * v[i]; }
-                    for (int i = 0; i < col2; ++i) pc[i] -= dibp * wbp[i];
+                    T2_ROLLED for (int i = 0; i < col2; ++i) { wmc += cc[i] * v[i]; wmp += pc[i] * v[i]; wmw += wbp[i] * v[i]; }
+                    T2_ROLLED for (int i = 0; i < col2; ++i) pc[i] -= dibp * wbp[i];
                     f1 += dibp * wmc;
                     f2 += 2.0 * dibp * wmp - dibp2 * wmw;
                 }
                 f2 = rmax(kEpsMch * f2_org, f2);
-                if (nleft > 0) { dtm = -f1 / f2; continue; }
+                if (nleft > 0) { dtm = ddiv(-f1, f2); continue; }
                 if (bnded) { f1 = 0.0; f2 = 0.0; dtm = 0.0; }
-                else dtm = -f1 / f2;
+                else dtm = ddiv(-f1, f2);
                 break;
             }
         }
         if (!all_fixed) {
             if (dtm <= 0.0) dtm = 0.0;
             tsum += dtm;
-            for (int i = 0; i < N; ++i) z[i] += tsum * dd[i];
+            T2_ROLLED for (int i = 0; i < N; ++i) z[i] += tsum * dd[i];
         }
-        if (col > 0) for (int i = 0; i < col2; ++i) cc[i] += dtm * pc[i];
+        if (col > 0) T2_ROLLED for (int i = 0; i < col2; ++i) cc[i] += dtm * pc[i];
         return true;
     }
 
@@ -406,13 +413,13 @@ struct Solver {
     T2_NI bool freev() {
         nenter = 0; ileave = N;
         if (iter > 0 && cnstnd) {
-            for (int i = 0; i < nfree; ++i) { const int k = index[i]; if (iwhere[k] > 0) indx2[--ileave] = k; }
-            for (int i = nfree; i < N; ++i) { const int k = index[i]; if (iwhere[k] <= 0) indx2[nenter++] = k; }
+            T2_ROLLED for (int i = 0; i < nfree; ++i) { const int k = index[i]; if (iwhere[k] > 0) indx2[--ileave] = k; }
+            T2_ROLLED for (int i = nfree; i < N; ++i) { const int k = index[i]; if (iwhere[k] <= 0) indx2[nenter++] = k; }
         }
         const bool wrk = (ileave < N) || (nenter > 0) || updatd;
         nfree = 0;
         int iact = N;
-        for (int i = 0; i < N; ++i) {
+        T2_ROLLED for (int i = 0; i < N; ++i) {
             if (iwhere[i] <= 0) index[nfree++] = i;
             else index[--iact] = i;
         }
@@ -424,23 +431,23 @@ struct Solver {
         int upcl;
         if (updatd) {
             if (iupdat > kM) {                                  // shift the old part of WN1
-                for (int jy = 0; jy < kM - 1; ++jy) {
+                T2_ROLLED for (int jy = 0; jy < kM - 1; ++jy) {
                     const int js = kM + jy;
-                    for (int q = 0; q < kM - 1 - jy; ++q) {
+                    T2_ROLLED for (int q = 0; q < kM - 1 - jy; ++q) {
                         wn1[jy + q][jy] = wn1[jy + 1 + q][jy + 1];
                         wn1[js + q][js] = wn1[js + 1 + q][js + 1];
                     }
-                    for (int q = 0; q < kM - 1; ++q) wn1[kM + q][jy] = wn1[kM + 1 + q][jy + 1];
+                    T2_ROLLED for (int q = 0; q < kM - 1; ++q) wn1[kM + q][jy] = wn1[kM + 1 + q][jy + 1];
                 }
             }
             // new rows in blocks (1,1), (2,1) and (2,2)
             const int ipntr = (head + col - 1) % kM;
             const int iy = col - 1, is = kM + col - 1;
-            for (int jy = 0; jy < col; ++jy) {
+            T2_ROLLED for (int jy = 0; jy < col; ++jy) {
                 const int js = kM + jy, jpntr = (head + jy) % kM;
                 double t1 = 0.0, t2 = 0.0, t3 = 0.0;
-                for (int k = 0; k < nfree; ++k) { const int k1 = index[k]; t1 += wy[ipntr][k1] * wy[jpntr][k1]; }
-                for (int k = nfree; k < N; ++k) {
+                T2_ROLLED for (int k = 0; k < nfree; ++k) { const int k1 = index[k]; t1 += wy[ipntr][k1] * wy[jpntr][k1]; }
+                T2_ROLLED for (int k = nfree; k < N; ++k) {
                     const int k1 = index[k];
                     t2 += ws[ipntr][k1] * ws[jpntr][k1];
                     t3 += ws[ipntr][k1] * wy[jpntr][k1];
@@ -449,10 +456,10 @@ struct Solver {
             }
             // new column in block (2,1)
             const int jy = col - 1, jpntr = (head + col - 1) % kM;
-            for (int i = 0; i < col; ++i) {
+            T2_ROLLED for (int i = 0; i < col; ++i) {
                 const int is2 = kM + i, ip = (head + i) % kM;
                 double t3 = 0.0;
-                for (int k = 0; k < nfree; ++k) { const int k1 = index[k]; t3 += ws[ip][k1] * wy[jpntr][k1]; }
+                T2_ROLLED for (int k = 0; k < nfree; ++k) { const int k1 = index[k]; t3 += ws[ip][k1] * wy[jpntr][k1]; }
                 wn1[is2][jy] = t3;
             }
             upcl = col - 1;
@@ -460,17 +467,17 @@ struct Solver {
             upcl = col;
         }
         // old parts of blocks (1,1) and (2,2): variables that entered / left the free set
-        for (int iy = 0; iy < upcl; ++iy) {
+        T2_ROLLED for (int iy = 0; iy < upcl; ++iy) {
             const int is = kM + iy, ipntr = (head + iy) % kM;
-            for (int jy = 0; jy <= iy; ++jy) {
+            T2_ROLLED for (int jy = 0; jy <= iy; ++jy) {
                 const int js = kM + jy, jpntr = (head + jy) % kM;
                 double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0;
-                for (int k = 0; k < nenter; ++k) {
+                T2_ROLLED for (int k = 0; k < nenter; ++k) {
                     const int k1 = indx2[k];
                     t1 += wy[ipntr][k1] * wy[jpntr][k1];
                     t2 += ws[ipntr][k1] * ws[jpntr][k1];
                 }
-                for (int k = ileave; k < N; ++k) {
+                T2_ROLLED for (int k = ileave; k < N; ++k) {
                     const int k1 = indx2[k];
                     t3 += wy[ipntr][k1] * wy[jpntr][k1];
                     t4 += ws[ipntr][k1] * ws[jpntr][k1];
@@ -480,43 +487,43 @@ struct Solver {
             }
         }
         // old part of block (2,1)
-        for (int is0 = 0; is0 < upcl; ++is0) {
+        T2_ROLLED for (int is0 = 0; is0 < upcl; ++is0) {
             const int is = kM + is0, ipntr = (head + is0) % kM;
-            for (int jy = 0; jy < upcl; ++jy) {
+            T2_ROLLED for (int jy = 0; jy < upcl; ++jy) {
                 const int jpntr = (head + jy) % kM;
                 double t1 = 0.0, t3 = 0.0;
-                for (int k = 0; k < nenter; ++k) { const int k1 = indx2[k]; t1 += ws[ipntr][k1] * wy[jpntr][k1]; }
-                for (int k = ileave; k < N; ++k) { const int k1 = indx2[k]; t3 += ws[ipntr][k1] * wy[jpntr][k1]; }
+                T2_ROLLED for (int k = 0; k < nenter; ++k) { const int k1 = indx2[k]; t1 += ws[ipntr][k1] * wy[jpntr][k1]; }
+                T2_ROLLED for (int k = ileave; k < N; ++k) { const int k1 = indx2[k]; t3 += ws[ipntr][k1] * wy[jpntr][k1]; }
                 if (is0 <= jy) wn1[is][jy] = wn1[is][jy] + t1 - t3;
                 else wn1[is][jy] = wn1[is][jy] - t1 + t3;
             }
         }
         // upper triangle of WN = [D + Y'ZZ'Y/theta, -L_a' + R_z'; -L_a + R_z, S'AA'S theta]
-        for (int iy = 0; iy < col; ++iy) {
+        T2_ROLLED for (int iy = 0; iy < col; ++iy) {
             const int is = col + iy, is1 = kM + iy;
-            for (int jy = 0; jy <= iy; ++jy) {
+            T2_ROLLED for (int jy = 0; jy <= iy; ++jy) {
                 const int js = col + jy, js1 = kM + jy;
-                wn[jy][iy] = wn1[iy][jy] / theta;
+                wn[jy][iy] = ddiv(wn1[iy][jy], theta);
                 wn[js][is] = wn1[is1][js1] * theta;
             }
-            for (int jy = 0; jy < iy; ++jy) wn[jy][is] = -wn1[is1][jy];
-            for (int jy = iy; jy < col; ++jy) wn[jy][is] = wn1[is1][jy];
+            T2_ROLLED for (int jy = 0; jy < iy; ++jy) wn[jy][is] = -wn1[is1][jy];
+            T2_ROLLED for (int jy = iy; jy < col; ++jy) wn[jy][is] = wn1[is1][jy];
             wn[iy][iy] += sy[iy][iy];
         }
         // Cholesky of the (1,1) block, L^-1 (-L_a' + R_z') in the (1,2) block, then the (2,2) block
         if (!dpofa<M2>(wn, 0, col)) return false;
         const int col2 = 2 * col;
-        for (int js = col; js < col2; ++js) {
-            for (int j = 0; j < col; ++j) {                   // solve L x = wn(1:col, js), L' stored in the upper triangle
+        T2_ROLLED for (int js = col; js < col2; ++js) {
+            T2_ROLLED for (int j = 0; j < col; ++j) {                   // solve L x = wn(1:col, js), L' stored in the upper triangle
                 double s = wn[j][js];
-                for (int q = 0; q < j; ++q) s -= wn[q][j] * wn[q][js];
-                wn[j][js] = s / wn[j][j];
+                T2_ROLLED for (int q = 0; q < j; ++q) s -= wn[q][j] * wn[q][js];
+                wn[j][js] = ddiv(s, wn[j][j]);
             }
         }
-        for (int is = col; is < col2; ++is)
-            for (int js = is; js < col2; ++js) {
+        T2_ROLLED for (int is = col; is < col2; ++is)
+            T2_ROLLED for (int js = is; js < col2; ++js) {
                 double dot = 0.0;
-                for (int q = 0; q < col; ++q) dot += wn[q][is] * wn[q][js];
+                T2_ROLLED for (int q = 0; q < col; ++q) dot += wn[q][is] * wn[q][js];
                 wn[is][js] += dot;
             }
         return dpofa<M2>(wn, col, col);
@@ -528,37 +535,38 @@ struct Solver {
         double rr_[N], wv[M2];
         // reduced gradient r = -Z'(B (xcp - x) + g)
         if (!cnstnd && col > 0) {
-            for (int i = 0; i < N; ++i) rr_[i] = -g[i];
+            T2_ROLLED for (int i = 0; i < N; ++i) rr_[i] = -g[i];
         } else {
-            for (int i = 0; i < nfree; ++i) { const int k = index[i]; rr_[i] = -theta * (z[k] - x[k]) - g[k]; }
+            T2_ROLLED for (int i = 0; i < nfree; ++i) { const int k = index[i]; rr_[i] = -theta * (z[k] - x[k]) - g[k]; }
             if (!bmv(cc, wv)) return false;
-            for (int j = 0; j < col; ++j) {
+            T2_ROLLED for (int j = 0; j < col; ++j) {
                 const int pt = (head + j) % kM;
                 const double a1 = wv[j], a2 = theta * wv[col + j];
-                for (int i = 0; i < nfree; ++i) { const int k = index[i]; rr_[i] += wy[pt][k] * a1 + ws[pt][k] * a2; }
+                T2_ROLLED for (int i = 0; i < nfree; ++i) { const int k = index[i]; rr_[i] += wy[pt][k] * a1 + ws[pt][k] * a2; }
             }
         }
         // wv = W'Z d, then K^-1 wv through the LEL' factors
-        for (int i = 0; i < col; ++i) {
+        T2_ROLLED for (int i = 0; i < col; ++i) {
             const int pt = (head + i) % kM;
             double t1 = 0.0, t2 = 0.0;
-            for (int j = 0; j < nfree; ++j) { const int k = index[j]; t1 += wy[pt][k] * rr_[j]; t2 += ws[pt][k] * rr_[j]; }
+            T2_ROLLED for (int j = 0; j < nfree; ++j) { const int k = index[j]; t1 += wy[pt][k] * rr_[j]; t2 += ws[pt][k] * rr_[j]; }
             wv[i] = t1; wv[col + i] = theta * t2;
         }
         if (!dtrsl_t<M2>(wn, col2, wv)) return false;
-        for (int i = 0; i < col; ++i) wv[i] = -wv[i];
+        T2_ROLLED for (int i = 0; i < col; ++i) wv[i] = -wv[i];
         if (!dtrsl_n<M2>(wn, col2, wv)) return false;
         // d = (1/theta) r + (1/theta^2) Z'W wv
-        for (int jy = 0; jy < col; ++jy) {
+        const double inv_theta = ddiv(1.0, theta);
+        T2_ROLLED for (int jy = 0; jy < col; ++jy) {
             const int js = col + jy, pt = (head + jy) % kM;
-            for (int i = 0; i < nfree; ++i) { const int k = index[i]; rr_[i] += wy[pt][k] * wv[jy] / theta + ws[pt][k] * wv[js]; }
+            T2_ROLLED for (int i = 0; i < nfree; ++i) { const int k = index[i]; rr_[i] += ddiv(wy[pt][k] * wv[jy], theta) + ws[pt][k] * wv[js]; }
         }
-        for (int i = 0; i < nfree; ++i) rr_[i] *= 1.0 / theta;
+        T2_ROLLED for (int i = 0; i < nfree; ++i) rr_[i] *= inv_theta;
         // projection of the Newton point onto the box (v3.0), else backtrack along the Newton direction
         double xp[N];
-        for (int i = 0; i < N; ++i) xp[i] = z[i];
+        T2_ROLLED for (int i = 0; i < N; ++i) xp[i] = z[i];
         bool iword = false;
-        for (int a = 0; a < nfree; ++a) {
+        T2_ROLLED for (int a = 0; a < nfree; ++a) {
             const int k = index[a];
             const double dk = rr_[a], xk = z[k];
             if (nbd[k] == 0) z[k] = xk + dk;
@@ -568,23 +576,23 @@ struct Solver {
         }
         if (!iword) return true;
         double dd_p = 0.0;
-        for (int i = 0; i < N; ++i) dd_p += (z[i] - x[i]) * g[i];
+        T2_ROLLED for (int i = 0; i < N; ++i) dd_p += (z[i] - x[i]) * g[i];
         if (dd_p > 0.0) {
-            for (int i = 0; i < N; ++i) z[i] = xp[i];
+            T2_ROLLED for (int i = 0; i < N; ++i) z[i] = xp[i];
             double alpha = 1.0, temp1 = 1.0;
             int ibd = -1;
-            for (int a = 0; a < nfree; ++a) {
+            T2_ROLLED for (int a = 0; a < nfree; ++a) {
                 const int k = index[a];
                 const double dk = rr_[a];
                 if (nbd[k] != 0) {
                     if (dk < 0.0 && nbd[k] <= 2) {
                         const double temp2 = l[k] - z[k];
                         if (temp2 >= 0.0) temp1 = 0.0;
-                        else if (dk * alpha < temp2) temp1 = temp2 / dk;
+                        else if (dk * alpha < temp2) temp1 = ddiv(temp2, dk);
                     } else if (dk > 0.0 && nbd[k] >= 2) {
                         const double temp2 = u[k] - z[k];
                         if (temp2 <= 0.0) temp1 = 0.0;
-                        else if (dk * alpha > temp2) temp1 = temp2 / dk;
+                        else if (dk * alpha > temp2) temp1 = ddiv(temp2, dk);
                     }
                     if (temp1 < alpha) { alpha = temp1; ibd = a; }
                 }
@@ -595,7 +603,7 @@ struct Solver {
                 if (dk > 0.0) { z[k] = u[k]; rr_[ibd] = 0.0; }
                 else if (dk < 0.0) { z[k] = l[k]; rr_[ibd] = 0.0; }
             }
-            for (int a = 0; a < nfree; ++a) z[index[a]] += alpha * rr_[a];
+            T2_ROLLED for (int a = 0; a < nfree; ++a) z[index[a]] += alpha * rr_[a];
         }
         return true;
     }
@@ -606,30 +614,30 @@ struct Solver {
         ++iupdat;
         if (iupdat <= kM) { col = iupdat; itail = (head + iupdat - 1) % kM; }
         else { itail = (itail + 1) % kM; head = (head + 1) % kM; }
-        for (int i = 0; i < N; ++i) { ws[itail][i] = d[i]; wy[itail][i] = r[i]; }
-        theta = rr / dr;
+        T2_ROLLED for (int i = 0; i < N; ++i) { ws[itail][i] = d[i]; wy[itail][i] = r[i]; }
+        theta = ddiv(rr, dr);
         if (iupdat > kM) {                                      // move the old information up and left
-            for (int j = 0; j < col - 1; ++j) {
-                for (int q = 0; q <= j; ++q) ss[q][j] = ss[q + 1][j + 1];
-                for (int q = 0; q < col - 1 - j; ++q) sy[j + q][j] = sy[j + 1 + q][j + 1];
+            T2_ROLLED for (int j = 0; j < col - 1; ++j) {
+                T2_ROLLED for (int q = 0; q <= j; ++q) ss[q][j] = ss[q + 1][j + 1];
+                T2_ROLLED for (int q = 0; q < col - 1 - j; ++q) sy[j + q][j] = sy[j + 1 + q][j + 1];
             }
         }
-        for (int j = 0; j < col - 1; ++j) {                     // last row of S'Y, last column of S'S
+        T2_ROLLED for (int j = 0; j < col - 1; ++j) {                     // last row of S'Y, last column of S'S
             const int pt = (head + j) % kM;
             double a = 0.0, b = 0.0;
-            for (int i = 0; i < N; ++i) { a += d[i] * wy[pt][i]; b += ws[pt][i] * d[i]; }
+            T2_ROLLED for (int i = 0; i < N; ++i) { a += d[i] * wy[pt][i]; b += ws[pt][i] * d[i]; }
             sy[col - 1][j] = a;
             ss[j][col - 1] = b;
         }
         ss[col - 1][col - 1] = (stp == 1.0) ? dtd : stp * stp * dtd;
         sy[col - 1][col - 1] = dr;
         // T = theta S'S + L D^-1 L' (upper triangle), then its Cholesky factor
-        for (int j = 0; j < col; ++j) wt[0][j] = theta * ss[0][j];
-        for (int i = 1; i < col; ++i)
-            for (int j = i; j < col; ++j) {
+        T2_ROLLED for (int j = 0; j < col; ++j) wt[0][j] = theta * ss[0][j];
+        T2_ROLLED for (int i = 1; i < col; ++i)
+            T2_ROLLED for (int j = i; j < col; ++j) {
                 const int k1 = (i < j ? i : j);
                 double ddum = 0.0;
-                for (int k = 0; k < k1; ++k) ddum += sy[i][k] * sy[j][k] / sy[k][k];
+                T2_ROLLED for (int k = 0; k < k1; ++k) ddum += ddiv(sy[i][k] * sy[j][k], sy[k][k]);
                 wt[i][j] = ddum + theta * ss[i][j];
             }
         return dpofa<kM>(wt, 0, col);
@@ -638,39 +646,42 @@ struct Solver {
     // ---- More'-Thuente safeguarded step (MINPACK-2 dcstep) -------------------------------
     T2_NI static void dcstep(double& stx_, double& fx_, double& dx_, double& sty_, double& fy_, double& dy_, double& stp_,
                              double fp, double dp, bool& brackt_, double stpmin, double stpmax) {
-        const double sgnd = dp * (dx_ / fabs(dx_));
+        const double sgnd = dp * ddiv(dx_, fabs(dx_));
         double stpf;
         if (fp > fx_) {
-            const double th = 3.0 * (fx_ - fp) / (stp_ - stx_) + dx_ + dp;
+            const double th = ddiv(3.0 * (fx_ - fp), stp_ - stx_) + dx_ + dp;
             const double s = rmax(fabs(th), rmax(fabs(dx_), fabs(dp)));
-            double gamma = s * sqrt((th / s) * (th / s) - (dx_ / s) * (dp / s));
+            const double ths = ddiv(th, s);
+            double gamma = s * dsqrt(ths * ths - ddiv(dx_, s) * ddiv(dp, s));
             if (stp_ < stx_) gamma = -gamma;
-            const double p = (gamma - dx_) + th, q = ((gamma - dx_) + gamma) + dp, rr = p / q;
+            const double p = (gamma - dx_) + th, q = ((gamma - dx_) + gamma) + dp, rr = ddiv(p, q);
             const double stpc = stx_ + rr * (stp_ - stx_);
-            const double stpq = stx_ + ((dx_ / ((fx_ - fp) / (stp_ - stx_) + dx_)) / 2.0) * (stp_ - stx_);
-            stpf = (fabs(stpc - stx_) < fabs(stpq - stx_)) ? stpc : stpc + (stpq - stpc) / 2.0;
+            const double stpq = stx_ + (ddiv(dx_, ddiv(fx_ - fp, stp_ - stx_) + dx_) * 0.5) * (stp_ - stx_);
+            stpf = (fabs(stpc - stx_) < fabs(stpq - stx_)) ? stpc : stpc + (stpq - stpc) * 0.5;
             brackt_ = true;
         } else if (sgnd < 0.0) {
-            const double th = 3.0 * (fx_ - fp) / (stp_ - stx_) + dx_ + dp;
+            const double th = ddiv(3.0 * (fx_ - fp), stp_ - stx_) + dx_ + dp;
             const double s = rmax(fabs(th), rmax(fabs(dx_), fabs(dp)));
-            double gamma = s * sqrt((th / s) * (th / s) - (dx_ / s) * (dp / s));
+            const double ths = ddiv(th, s);
+            double gamma = s * dsqrt(ths * ths - ddiv(dx_, s) * ddiv(dp, s));
             if (stp_ > stx_) gamma = -gamma;
-            const double p = (gamma - dp) + th, q = ((gamma - dp) + gamma) + dx_, rr = p / q;
+            const double p = (gamma - dp) + th, q = ((gamma - dp) + gamma) + dx_, rr = ddiv(p, q);
             const double stpc = stp_ + rr * (stx_ - stp_);
-            const double stpq = stp_ + (dp / (dp - dx_)) * (stx_ - stp_);
+            const double stpq = stp_ + ddiv(dp, dp - dx_) * (stx_ - stp_);
             stpf = (fabs(stpc - stp_) > fabs(stpq - stp_)) ? stpc : stpq;
             brackt_ = true;
         } else if (fabs(dp) < fabs(dx_)) {
-            const double th = 3.0 * (fx_ - fp) / (stp_ - stx_) + dx_ + dp;
+            const double th = ddiv(3.0 * (fx_ - fp), stp_ - stx_) + dx_ + dp;
             const double s = rmax(fabs(th), rmax(fabs(dx_), fabs(dp)));
-            double gamma = s * sqrt(rmax(0.0, (th / s) * (th / s) - (dx_ / s) * (dp / s)));
+            const double ths = ddiv(th, s);
+            double gamma = s * dsqrt(rmax(0.0, ths * ths - ddiv(dx_, s) * ddiv(dp, s)));
             if (stp_ > stx_) gamma = -gamma;
-            const double p = (gamma - dp) + th, q = (gamma + (dx_ - dp)) + gamma, rr = p / q;
+            const double p = (gamma - dp) + th, q = (gamma + (dx_ - dp)) + gamma, rr = ddiv(p, q);
             double stpc;
             if (rr < 0.0 && gamma != 0.0) stpc = stp_ + rr * (stx_ - stp_);
             else if (stp_ > stx_) stpc = stpmax;
             else stpc = stpmin;
-            const double stpq = stp_ + (dp / (dp - dx_)) * (stx_ - stp_);
+            const double stpq = stp_ + ddiv(dp, dp - dx_) * (stx_ - stp_);
             if (brackt_) {
                 stpf = (fabs(stpc - stp_) < fabs(stpq - stp_)) ? stpc : stpq;
                 if (stp_ > stx_) stpf = rmin(stp_ + 0.66 * (sty_ - stp_), stpf);
@@ -682,11 +693,12 @@ struct Solver {
             }
         } else {
             if (brackt_) {
-                const double th = 3.0 * (fp - fy_) / (sty_ - stp_) + dy_ + dp;
+                const double th = ddiv(3.0 * (fp - fy_), sty_ - stp_) + dy_ + dp;
                 const double s = rmax(fabs(th), rmax(fabs(dy_), fabs(dp)));
-                double gamma = s * sqrt((th / s) * (th / s) - (dy_ / s) * (dp / s));
+                const double ths = ddiv(th, s);
+                double gamma = s * dsqrt(ths * ths - ddiv(dy_, s) * ddiv(dp, s));
                 if (stp_ > sty_) gamma = -gamma;
-                const double p = (gamma - dp) + th, q = ((gamma - dp) + gamma) + dy_, rr = p / q;
+                const double p = (gamma - dp) + th, q = ((gamma - dp) + gamma) + dy_, rr = ddiv(p, q);
                 stpf = stp_ + rr * (sty_ - stp_);
             } else if (stp_ > stx_) stpf = stpmax;
             else stpf = stpmin;
@@ -741,7 +753,7 @@ struct Solver {
     T2_NI void setup(const double* x0, const double* lo, const double* hi, double ftol_, double pgtol_, int maxls_) {
         ftol = ftol_; pgtol = pgtol_; maxls = maxls_;
         cnstnd = false; boxed = true;
-        for (int i = 0; i < N; ++i) {
+        T2_ROLLED for (int i = 0; i < N; ++i) {
             const bool hl = lo[i] > -INFINITY, hu = hi[i] < INFINITY;
             nbd[i] = hl ? (hu ? 2 : 1) : (hu ? 3 : 0);
             l[i] = hl ? lo[i] : 0.0; u[i] = hu ? hi[i] : 0.0;
@@ -755,7 +767,7 @@ struct Solver {
         }
         reset_memory();
         itail = 0; nfree = N; nenter = 0; ileave = N;
-        for (int i = 0; i < N; ++i) { index[i] = i; indx2[i] = i; }
+        T2_ROLLED for (int i = 0; i < N; ++i) { index[i] = i; indx2[i] = i; }
         fold = dnorm = dtd = gd = gdold = stp = stpmx = sbgnrm = 0.0;
         iter = ifun = iback = nfgv = 0;
         result = kRunning;
@@ -764,7 +776,7 @@ struct Solver {
     // f, g at the start point have been evaluated
     T2_NI void begin(double f0, const double* g0) {
         f = f0;
-        for (int i = 0; i < N; ++i) g[i] = g0[i];
+        T2_ROLLED for (int i = 0; i < N; ++i) g[i] = g0[i];
         nfgv = 1;
         projgr();
         if (sbgnrm <= pgtol) { result = kConvPg; return; }
@@ -776,7 +788,7 @@ struct Solver {
         for (;;) {
             bool wrk;
             if (!cnstnd && col > 0) {
-                for (int i = 0; i < N; ++i) z[i] = x[i];
+                T2_ROLLED for (int i = 0; i < N; ++i) z[i] = x[i];
                 wrk = updatd;
             } else {
                 if (!cauchy()) { reset_memory(); continue; }
@@ -786,36 +798,36 @@ struct Solver {
                 if (wrk && !formk()) { reset_memory(); continue; }
                 if (!subsm()) { reset_memory(); continue; }
             }
-            for (int i = 0; i < N; ++i) d[i] = z[i] - x[i];
+            T2_ROLLED for (int i = 0; i < N; ++i) d[i] = z[i] - x[i];
             // lnsrlb, first entry
             dtd = 0.0;
-            for (int i = 0; i < N; ++i) dtd += d[i] * d[i];
-            dnorm = sqrt(dtd);
+            T2_ROLLED for (int i = 0; i < N; ++i) dtd += d[i] * d[i];
+            dnorm = dsqrt(dtd);
             stpmx = 1e10;
             if (cnstnd) {
                 if (iter == 0) stpmx = 1.0;
                 else {
-                    for (int i = 0; i < N; ++i) {
+                    T2_ROLLED for (int i = 0; i < N; ++i) {
                         const double a1 = d[i];
                         if (nbd[i] != 0) {
                             if (a1 < 0.0 && nbd[i] <= 2) {
                                 const double a2 = l[i] - x[i];
                                 if (a2 >= 0.0) stpmx = 0.0;
-                                else if (a1 * stpmx < a2) stpmx = a2 / a1;
+                                else if (a1 * stpmx < a2) stpmx = ddiv(a2, a1);
                             } else if (a1 > 0.0 && nbd[i] >= 2) {
                                 const double a2 = u[i] - x[i];
                                 if (a2 <= 0.0) stpmx = 0.0;
-                                else if (a1 * stpmx > a2) stpmx = a2 / a1;
+                                else if (a1 * stpmx > a2) stpmx = ddiv(a2, a1);
                             }
                         }
                     }
                 }
             }
-            stp = (iter == 0 && !boxed) ? rmin(1.0 / dnorm, stpmx) : 1.0;
-            for (int i = 0; i < N; ++i) { t[i] = x[i]; r[i] = g[i]; }
+            stp = (iter == 0 && !boxed) ? rmin(ddiv(1.0, dnorm), stpmx) : 1.0;
+            T2_ROLLED for (int i = 0; i < N; ++i) { t[i] = x[i]; r[i] = g[i]; }
             fold = f; ifun = 0; iback = 0;
             gd = 0.0;
-            for (int i = 0; i < N; ++i) gd += g[i] * d[i];
+            T2_ROLLED for (int i = 0; i < N; ++i) gd += g[i] * d[i];
             gdold = gd;
             if (gd >= 0.0) {                                  // not a descent direction
                 if (col == 0) { result = kAbnormal; return; }
@@ -824,7 +836,7 @@ struct Solver {
             }
             // dcsrch 'START'
             brackt = false; stage = 1; finit = f; ginit = gd; gtest = 1e-3 * ginit;
-            width = stpmx - 0.0; width1 = width / 0.5;
+            width = stpmx - 0.0; width1 = width * 2.0;
             stx = 0.0; fx = finit; gx = ginit; sty = 0.0; fy = finit; gy = ginit;
             stmin = 0.0; stmax = stp + 4.0 * stp;
             ifun = 1; ++nfgv; iback = 0;
@@ -834,24 +846,24 @@ struct Solver {
     }
 
     T2_HD void trial_point() {
-        if (stp == 1.0) { for (int i = 0; i < N; ++i) x[i] = z[i]; }
-        else { for (int i = 0; i < N; ++i) x[i] = stp * d[i] + t[i]; }
+        if (stp == 1.0) { T2_ROLLED for (int i = 0; i < N; ++i) x[i] = z[i]; }
+        else { T2_ROLLED for (int i = 0; i < N; ++i) x[i] = stp * d[i] + t[i]; }
     }
 
     // f, g at the trial point x have been evaluated.  Returns true when a NEW ITERATE was accepted
     // (scipy's callback / nit point); `result` != kRunning means the run has ended.
     T2_NI bool advance(double fv, const double* gv) {
         f = fv;
-        for (int i = 0; i < N; ++i) g[i] = gv[i];
+        T2_ROLLED for (int i = 0; i < N; ++i) g[i] = gv[i];
         gd = 0.0;
-        for (int i = 0; i < N; ++i) gd += g[i] * d[i];
+        T2_ROLLED for (int i = 0; i < N; ++i) gd += g[i] * d[i];
 #ifdef T2FIT_LB_TRACE
         printf("  ls: iter %d ifun %d stp %.10g f %.10g gd %.6g (finit %.10g ginit %.6g) x %.8f %.8f\n", iter, ifun, stp, f, gd, finit, ginit, x[0], x[1]);
 #endif
         if (dcsrch_next(f, gd) == 0) {
             ++ifun; ++nfgv; iback = ifun - 1;
             if (iback >= maxls) {                             // line search gave up: back to the start of it
-                for (int i = 0; i < N; ++i) { x[i] = t[i]; g[i] = r[i]; }
+                T2_ROLLED for (int i = 0; i < N; ++i) { x[i] = t[i]; g[i] = r[i]; }
                 f = fold;
                 if (col == 0) { result = kAbnormal; return false; }
                 reset_memory();
@@ -872,12 +884,12 @@ struct Solver {
         const double ddum0 = rmax(fabs(fold), rmax(fabs(f), 1.0));
         if ((fold - f) <= ftol * ddum0) { result = kConvF; return; }
         double rr = 0.0;
-        for (int i = 0; i < N; ++i) { r[i] = g[i] - r[i]; rr += r[i] * r[i]; }
+        T2_ROLLED for (int i = 0; i < N; ++i) { r[i] = g[i] - r[i]; rr += r[i] * r[i]; }
         double dr, ddum;
         if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; }
         else {
             dr = (gd - gdold) * stp;
-            for (int i = 0; i < N; ++i) d[i] *= stp;
+            T2_ROLLED for (int i = 0; i < N; ++i) d[i] *= stp;
             ddum = -gdold * stp;
         }
         if (dr <= kEpsMch * ddum) {
@@ -971,8 +983,7 @@ T2_HD LbVoxel lbfgsb_voxel(const float* yraw, const LbConsts& c, bool lane_valid
         {
             fv = objective<OBJ>(s.x, y, c);
             double xt[N];
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
+            T2_ROLLED for (int i = 0; i < N; ++i) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) xt[j] = s.x[j];
                 const double h = fd_step<N>(s.x, lo, hi, i, c.fd_step);

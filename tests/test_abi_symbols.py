@@ -31,10 +31,25 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     assert lib.t2fit_abi_version() == _abi.ABI_VERSION
 
 
-def test_struct_layout_matches_header():
-    # sizes computed from the C declaration (LP64): guards against drift between t2fit.h and _abi.py
-    assert C.sizeof(_abi.Problem) == 8 + 4 + 4 + 8 + 8 + 8 + 8 + 4 + 4 + 8 + 3 * 8 * 3 + 4 + 4 + 3 * 8 + 4 + 4 + 4 + 4
-    assert C.sizeof(_abi.Outputs) == 7 * 8 + 8 + 4 * 8 + 8
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof of every field, computed by gcc from include/t2fit.h, equal the ctypes mirror."""
+    import subprocess
+    fields = {"t2fit_problem": [f for f, _ in _abi.Problem._fields_], "t2fit_outputs": [f for f, _ in _abi.Outputs._fields_]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "t2fit.h"', 'int main(void) {']
+    for st, fs in fields.items():
+        lines.append(f'  printf("{st} %zu\\n", sizeof({st}));')
+        for f in fs:
+            lines.append(f'  printf("{st}.{f} %zu\\n", offsetof({st}, {f}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for st, cls in (("t2fit_problem", _abi.Problem), ("t2fit_outputs", _abi.Outputs)):
+        assert int(got[st]) == C.sizeof(cls), st
+        for f, _ in cls._fields_:
+            assert int(got[f"{st}.{f}"]) == getattr(cls, f).offset, f"{st}.{f}"
 
 
 def test_library_contains_sm100a_sass_only():
