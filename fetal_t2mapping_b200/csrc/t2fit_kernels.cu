@@ -222,54 +222,74 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
 constexpr int kLbBlock = 128;
 
 template <int OBJ>
-__global__ void __launch_bounds__(kLbBlock) lbfgsb_kernel(const __grid_constant__ lb::LbConsts c,
-                                                          const __grid_constant__ KernelIO io) {
-    const int64_t i = (int64_t)blockIdx.x * kLbBlock + threadIdx.x;
-    const bool valid = i < io.n_fit;
-    const int64_t ii = valid ? i : io.n_fit - 1;
-    const int64_t row = io.idx ? __ldg(io.idx + ii) : ii;
+__device__ __noinline__ void lb_store(const lb::LbConsts& c, const KernelIO& io, const lb::VoxelRun<OBJ>& run, int64_t i, int64_t row) {
+    const lb::LbVoxel v = run.finish();
     const int E = c.n_echo;
-    float y[kMaxEcho];
-    if (io.layout == T2FIT_LAYOUT_AOS) { for (int e = 0; e < E; ++e) y[e] = __ldg(io.echoes + row * E + e); }
-    else { for (int e = 0; e < E; ++e) y[e] = __ldg(io.echoes + (int64_t)e * io.ld + ii); }
-
-    int tl = 0;
-    float* tf = (valid && io.trace_f) ? io.trace_f + i * io.trace_cap : nullptr;
-    float* ts = (valid && io.trace_step) ? io.trace_step + i * io.trace_cap : nullptr;
-    const lb::LbVoxel v = lb::lbfgsb_voxel<OBJ>(y, c, valid, tf, ts, (tf || ts) ? io.trace_cap : 0, &tl);
-
-    if (valid) {
-        const float kf = (float)v.x[0], t2f = (float)v.x[1], sf = (OBJ == 0) ? 0.f : (float)v.x[2];
-        // residual epilogue on the stored float32 values (signal normalised as the fit saw it)
-        float scale = 1.f;
-        if (c.norm) {
-            float mx = y[0];
-            for (int e = 1; e < E; ++e) mx = fmaxf(mx, y[e]);
-            scale = 1.0f / mx;
-        }
-        double acc = 0.0;
-        for (int e = 0; e < E; ++e) {
-            double pred = (double)kf * exp(-c.te[e] / (double)t2f);
-            if (OBJ != 0) pred = sqrt(pred * pred + (double)sf * (double)sf);
-            acc += (double)(y[e] * scale) - (double)(float)pred;
-        }
-        const int64_t o = io.dense ? row : i;
-        if (io.t2) io.t2[o] = t2f;
-        if (io.k) io.k[o] = kf;
-        if (OBJ != 0 && io.sigma) io.sigma[o] = sf;
-        if (io.res) io.res[o] = (float)(acc / (double)E);
-        if (io.fun) io.fun[i] = (float)v.fun;
-        if (io.nit) io.nit[i] = v.nit;
-        if (io.status) io.status[i] = (uint8_t)v.status;
-        if (io.trace_len) io.trace_len[i] = tl;
+    const float kf = (float)v.x[0], t2f = (float)v.x[1], sf = (OBJ == 0) ? 0.f : (float)v.x[2];
+    // residual epilogue on the stored float32 values; run.y is the signal as the fit saw it (normalised if norm)
+    double acc = 0.0;
+    for (int e = 0; e < E; ++e) {
+        double pred = (double)kf * exp(-c.te[e] / (double)t2f);
+        if (OBJ != 0) pred = sqrt(pred * pred + (double)sf * (double)sf);
+        acc += (double)run.y[e] - (double)(float)pred;
     }
-    const int st = valid ? v.status : 0;
-    const unsigned any_bad = __ballot_sync(0xffffffffu, st != 0);
-    if (any_bad && io.counts) {
-#pragma unroll
-        for (int s = 1; s < 4; ++s) {
-            const unsigned m = __ballot_sync(0xffffffffu, st == s);
-            if (m && (threadIdx.x & 31) == 0) atomicAdd(io.counts + s, (unsigned long long)__popc(m));
+    const int64_t o = io.dense ? row : i;
+    if (io.t2) io.t2[o] = t2f;
+    if (io.k) io.k[o] = kf;
+    if (OBJ != 0 && io.sigma) io.sigma[o] = sf;
+    if (io.res) io.res[o] = (float)(acc / (double)E);
+    if (io.fun) io.fun[i] = (float)v.fun;
+    if (io.nit) io.nit[i] = v.nit;
+    if (io.status) io.status[i] = (uint8_t)v.status;
+    if (io.trace_len) io.trace_len[i] = v.trace_len;
+    if (v.status != 0 && io.counts) atomicAdd(io.counts + v.status, 1ull);
+}
+
+// Persistent grid; every LANE pulls its next voxel from a global queue as soon as its current one has
+// terminated (warp-aggregated atomicAdd), so lanes whose optimiser stopped early do not idle until the
+// slowest voxel of the warp is done (iteration counts vary 3..40 between neighbouring voxels).
+template <int OBJ>
+__global__ void __launch_bounds__(kLbBlock) lbfgsb_kernel(const __grid_constant__ lb::LbConsts c,
+                                                          const __grid_constant__ KernelIO io,
+                                                          unsigned long long* __restrict__ queue) {
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
+    const int E = c.n_echo;
+    lb::VoxelRun<OBJ> run;
+    run.active = false;
+    int64_t cur = -1, row = 0;
+    bool exhausted = false;
+    for (;;) {
+        const bool need = !run.active && !exhausted;
+        const unsigned m = __ballot_sync(full, need);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(m));
+            base = __shfl_sync(full, base, leader);
+            if (need) {
+                const int64_t i = (int64_t)base + __popc(m & ((1u << lane) - 1u));
+                if (i < io.n_fit) {
+                    cur = i;
+                    row = io.idx ? __ldg(io.idx + i) : i;
+                    float yraw[kMaxEcho];
+                    if (io.layout == T2FIT_LAYOUT_AOS) { for (int e = 0; e < E; ++e) yraw[e] = __ldg(io.echoes + row * E + e); }
+                    else { for (int e = 0; e < E; ++e) yraw[e] = __ldg(io.echoes + (int64_t)e * io.ld + i); }
+                    const bool tr = io.trace_cap > 0;
+                    run.start(yraw, c, (tr && io.trace_f) ? io.trace_f + i * io.trace_cap : nullptr,
+                              (tr && io.trace_step) ? io.trace_step + i * io.trace_cap : nullptr, tr ? io.trace_cap : 0);
+                    if (!run.active) lb_store<OBJ>(c, io, run, cur, row);      // non-finite input / bad bounds: no optimiser run
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (!__any_sync(full, run.active)) {
+            if (__all_sync(full, exhausted)) break;
+            continue;
+        }
+        if (run.active) {
+            run.pass(c);
+            if (!run.active) lb_store<OBJ>(c, io, run, cur, row);
         }
     }
 }
@@ -445,7 +465,7 @@ FitFn pick_kernel(int model, int n_echo, int layout) {
     return layout == T2FIT_LAYOUT_AOS ? pick_e<kFloor3, T2FIT_LAYOUT_AOS>(n_echo) : pick_e<kFloor3, T2FIT_LAYOUT_SOA>(n_echo);
 }
 
-using LbFn = void (*)(const lb::LbConsts, const KernelIO);
+using LbFn = void (*)(const lb::LbConsts, const KernelIO, unsigned long long*);
 
 LbFn pick_lb_kernel(int model, int n_echo) {
     if (n_echo < 2 || n_echo > kMaxEcho) return nullptr;
@@ -534,6 +554,8 @@ struct Slot {
 };
 constexpr size_t kOutBytes = (size_t)kChunk * (5 * sizeof(float) + sizeof(int32_t) + 1);
 
+constexpr int kQueues = 16;
+
 struct Context {
     int device = -1;
     cudaDeviceProp prop{};
@@ -549,6 +571,8 @@ struct Context {
     int64_t* d_total = nullptr;
     int64_t* h_total = nullptr;
     int64_t tiles_cap = 0;
+    unsigned long long* d_queue = nullptr;   // [kQueues] voxel queue counters of the L-BFGS-B launches (round robin)
+    unsigned queue_next = 0;
     bool counts_dirty = false;               // device-memory launches may have bumped d_counts
     cudaStream_t fill_stream = nullptr;      // side stream of the zero-fill kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -599,9 +623,18 @@ int launch_lbfgsb(Context* c, const lb::LbConsts& lc, KernelIO io, int model, in
     if (io.n_fit <= 0) return T2FIT_OK;
     LbFn fn = pick_lb_kernel(model, n_echo);
     if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
-    const int64_t blocks = (io.n_fit + kLbBlock - 1) / kLbBlock;
-    if (blocks > 0x7fffffffLL) return fail(T2FIT_EINVAL, "n_fit too large for one launch");
-    fn<<<(unsigned)blocks, kLbBlock, 0, st>>>(lc, io);
+    // persistent grid sized to what is resident at once; voxels are handed out through a queue counter
+    static const int env_per_sm = [] { const char* e = getenv("T2FIT_LB_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
+    int per_sm = env_per_sm;
+    if (per_sm <= 0) {
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kLbBlock, 0));
+        if (per_sm <= 0) per_sm = 1;
+    }
+    const int64_t want = (io.n_fit + kLbBlock - 1) / kLbBlock;
+    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)per_sm * c->prop.multiProcessorCount);
+    unsigned long long* q = c->d_queue + (c->queue_next++ % kQueues);
+    CU_TRY(cudaMemsetAsync(q, 0, sizeof(unsigned long long), st));
+    fn<<<grid, kLbBlock, 0, st>>>(lc, io, q);
     CU_TRY(cudaGetLastError());
     return T2FIT_OK;
 }
@@ -844,6 +877,7 @@ int t2fit_init(int device) {
     CU_TRY(cudaMalloc(&c->d_counts, 4 * sizeof(unsigned long long)));
     CU_TRY(cudaMemset(c->d_counts, 0, 4 * sizeof(unsigned long long)));
     CU_TRY(cudaMallocHost(&c->h_counts, 4 * sizeof(unsigned long long)));
+    CU_TRY(cudaMalloc(&c->d_queue, kQueues * sizeof(unsigned long long)));
     CU_TRY(cudaMalloc(&c->d_total, sizeof(int64_t)));
     CU_TRY(cudaMallocHost(&c->h_total, sizeof(int64_t)));
     unsigned hw = std::thread::hardware_concurrency();
@@ -869,6 +903,7 @@ void t2fit_shutdown(void) {
     if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->d_tile_counts) cudaFree(c->d_tile_counts);
     if (c->d_tile_offsets) cudaFree(c->d_tile_offsets);
+    if (c->d_queue) cudaFree(c->d_queue);
     if (c->d_total) cudaFree(c->d_total);
     if (c->h_total) cudaFreeHost(c->h_total);
     if (c->stream) cudaStreamDestroy(c->stream);

@@ -499,6 +499,20 @@ struct Solver {
             }
         }
         // upper triangle of WN = [D + Y'ZZ'Y/theta, -L_a' + R_z'; -L_a + R_z, S'AA'S theta]
+#ifdef T2FIT_LB_DIRECT_WN
+        T2_ROLLED for (int iy = 0; iy < col; ++iy) {
+            const int is = col + iy, ip = (head + iy) % kM;
+            T2_ROLLED for (int jy = 0; jy < col; ++jy) {
+                const int js = col + jy, jp = (head + jy) % kM;
+                double yzy = 0.0, sas = 0.0, say = 0.0, szy = 0.0;
+                T2_ROLLED for (int k = 0; k < nfree; ++k) { const int k1 = index[k]; yzy += wy[ip][k1] * wy[jp][k1]; szy += ws[ip][k1] * wy[jp][k1]; }
+                T2_ROLLED for (int k = nfree; k < N; ++k) { const int k1 = index[k]; sas += ws[ip][k1] * ws[jp][k1]; say += ws[ip][k1] * wy[jp][k1]; }
+                if (jy <= iy) { wn[jy][iy] = ddiv(yzy, theta); wn[js][is] = sas * theta; }
+                wn[jy][is] = (jy < iy) ? -say : szy;
+            }
+            wn[iy][iy] += sy[iy][iy];
+        }
+#else
         T2_ROLLED for (int iy = 0; iy < col; ++iy) {
             const int is = col + iy, is1 = kM + iy;
             T2_ROLLED for (int jy = 0; jy <= iy; ++jy) {
@@ -510,6 +524,7 @@ struct Solver {
             T2_ROLLED for (int jy = iy; jy < col; ++jy) wn[jy][is] = wn1[is1][jy];
             wn[iy][iy] += sy[iy][iy];
         }
+#endif
         // Cholesky of the (1,1) block, L^-1 (-L_a' + R_z') in the (1,2) block, then the (2,2) block
         if (!dpofa<M2>(wn, 0, col)) return false;
         const int col2 = 2 * col;
@@ -922,48 +937,58 @@ T2_HD double fd_step(const double* x, const double* lo, const double* hi, int i,
 struct LbVoxel {
     double x[3];
     double fun;
-    int nit, nfev, status, result;
+    int nit, nfev, status, result, trace_len;
 };
 
+// One voxel as a resumable run: start() = fit_voxel's preamble (:237-245), pass() = one fun_and_grad(x) of scipy's
+// ScalarFunction (f plus N forward differences) followed by the optimiser's reaction to it, finish() = what
+// fit_voxel returns.  The device kernel drives many runs per thread from a work queue; the host simulation one.
 template <int OBJ>
-T2_HD LbVoxel lbfgsb_voxel(const float* yraw, const LbConsts& c, bool lane_valid, float* trace_f, float* trace_step,
-                           int trace_cap, int* trace_len) {
-    constexpr int N = (OBJ == 0) ? 2 : 3;
-    LbVoxel out;
-    const int E = c.n_echo;
-    float y[kMaxEcho];
-    bool finite = true;
-    float ymax = yraw[0];
-    for (int e = 0; e < E; ++e) {
-        y[e] = yraw[e];
-        finite = finite && ((yraw[e] - yraw[e]) == 0.0f);
-        ymax = yraw[e] > ymax ? yraw[e] : ymax;
-    }
-    if (c.norm) {                                             // float32 / float32 (:237-238)
-        for (int e = 0; e < E; ++e) { y[e] = yraw[e] / ymax; finite = finite && ((y[e] - y[e]) == 0.0f); }
-    }
-    double lo[3] = {c.lb[0], c.lb[1], c.lb[2]}, hi[3] = {c.ub[0], c.ub[1], c.ub[2]};
-    if (c.no_prior) lo[0] = (double)yraw[0];                  // :243-245 (upper bound and T2 box are in c)
-    int status = kOk;
-    if (c.no_prior && (yraw[0] > (float)hi[0])) status = kBadBounds;   // scipy: "An upper bound is less than ..."
-    else if (!finite) status = kNonFinite;
-    if (OBJ == 2 && status == kOk) {                  // rician: log(signal) needs signal > 0
-        for (int e = 0; e < E; ++e) if (!(y[e] > 0.0f)) status = kNonFinite;
-    }
+struct VoxelRun {
+    static constexpr int N = (OBJ == 0) ? 2 : 3;
     Solver<N> s;
-    s.setup(c.x0, lo, hi, c.ftol, c.pgtol, c.maxls);
-    int nit = 0, nfev = 0, tl = 0;
+    float y[kMaxEcho];
+    double lo[3], hi[3];
     double xprev[N];
-    bool have_prev = false;
-    bool active = lane_valid && status == kOk;
-    bool started = false;
-    // every pass of this loop is one fun_and_grad(x): f plus N forward differences
-    for (;;) {
-        if (!warp_any(active)) break;
+    float* trace_f;
+    float* trace_step;
+    int trace_cap, tl;
+    int nit, nfev, status;
+    bool have_prev, started, active;
+
+    T2_NI void start(const float* yraw, const LbConsts& c, float* tf, float* ts, int tcap) {
+        const int E = c.n_echo;
+        bool finite = true;
+        float ymax = yraw[0];
+        T2_ROLLED for (int e = 0; e < E; ++e) {
+            y[e] = yraw[e];
+            finite = finite && ((yraw[e] - yraw[e]) == 0.0f);
+            ymax = yraw[e] > ymax ? yraw[e] : ymax;
+        }
+        if (c.norm) {                                         // float32 / float32 (:237-238)
+            T2_ROLLED for (int e = 0; e < E; ++e) { y[e] = yraw[e] / ymax; finite = finite && ((y[e] - y[e]) == 0.0f); }
+        }
+        for (int i = 0; i < 3; ++i) { lo[i] = c.lb[i]; hi[i] = c.ub[i]; }
+        if (c.no_prior) lo[0] = (double)yraw[0];              // :243-245 (upper bound and T2 box are in c)
+        status = kOk;
+        if (c.no_prior && (yraw[0] > (float)hi[0])) status = kBadBounds;   // scipy: "An upper bound is less than ..."
+        else if (!finite) status = kNonFinite;
+        if (OBJ == 2 && status == kOk) {                      // rician: log(signal) needs signal > 0
+            T2_ROLLED for (int e = 0; e < E; ++e) if (!(y[e] > 0.0f)) status = kNonFinite;
+        }
+        s.setup(c.x0, lo, hi, c.ftol, c.pgtol, c.maxls);
+        nit = 0; nfev = 0; tl = 0;
+        have_prev = false; started = false;
+        trace_f = tf; trace_step = ts; trace_cap = tcap;
+        active = status == kOk;
+    }
+
+    T2_NI void pass(const LbConsts& c) {
+        const int E = c.n_echo;
         double fv = 0.0, gv[N];
 #ifdef T2FIT_HOSTSIM
         if (c.fd_step < 0.0) {                                // test hook: analytic gradient (validates the optimiser core
-            fv = objective<OBJ>(s.x, y, c);                // against scipy with jac=True, free of finite-difference noise)
+            fv = objective<OBJ>(s.x, y, c);                   // against scipy with jac=True, free of finite-difference noise)
             for (int i = 0; i < N; ++i) gv[i] = 0.0;
             for (int e = 0; e < E; ++e) {
                 if (OBJ == 0) {
@@ -981,6 +1006,7 @@ T2_HD LbVoxel lbfgsb_voxel(const float* yraw, const LbConsts& c, bool lane_valid
         } else
 #endif
         {
+            (void)E;
             fv = objective<OBJ>(s.x, y, c);
             double xt[N];
             T2_ROLLED for (int i = 0; i < N; ++i) {
@@ -989,13 +1015,13 @@ T2_HD LbVoxel lbfgsb_voxel(const float* yraw, const LbConsts& c, bool lane_valid
                 const double h = fd_step<N>(s.x, lo, hi, i, c.fd_step);
                 xt[i] = s.x[i] + h;
                 const double dx = xt[i] - s.x[i];
-                gv[i] = (objective<OBJ>(xt, y, c) - fv) / dx;
+                gv[i] = ddiv(objective<OBJ>(xt, y, c) - fv, dx);
             }
         }
-        if (!active) continue;
         nfev += N + 1;
-        if (!(fv - fv == 0.0)) {                              // objective not finite: scipy ends ABNORMAL at the start point
-            if (!started) { s.f = fv; s.result = kAbnormal; active = false; continue; }
+        if (!started && !(fv - fv == 0.0)) {                  // objective not finite at the start point: scipy ends ABNORMAL there
+            s.f = fv; s.result = kAbnormal; active = false;
+            return;
         }
         if (!started) {
             started = true;
@@ -1021,23 +1047,28 @@ T2_HD LbVoxel lbfgsb_voxel(const float* yraw, const LbConsts& c, bool lane_valid
         }
         if (s.result != kRunning) active = false;
     }
-    if (trace_len) *trace_len = tl < trace_cap ? tl : trace_cap;
-    for (int i = 0; i < N; ++i) out.x[i] = s.x[i];
-    if (N < 3) out.x[2] = 0.0;
-    out.fun = s.f;
-    out.nit = nit;
-    out.nfev = nfev;
-    out.result = s.result;
-    if (status == kOk) {
-        // success False: ABNORMAL (x = start of the failed line search), maxiter or maxfun
-        if (s.result == kAbnormal || s.result == kMaxIter || s.result == kMaxFun) status = kNotConverged;
-    } else {
-        out.fun = NAN; out.nit = 0;
-        if (status == kBadBounds) { out.x[0] = out.x[1] = out.x[2] = NAN; }
+
+    T2_HD LbVoxel finish() const {
+        LbVoxel out;
+        for (int i = 0; i < N; ++i) out.x[i] = s.x[i];
+        if (N < 3) out.x[2] = 0.0;
+        out.fun = s.f;
+        out.nit = nit;
+        out.nfev = nfev;
+        out.result = s.result;
+        out.trace_len = tl < trace_cap ? tl : trace_cap;
+        int st = status;
+        if (st == kOk) {
+            // success False: ABNORMAL (x = start of the failed line search), maxiter or maxfun
+            if (s.result == kAbnormal || s.result == kMaxIter || s.result == kMaxFun) st = kNotConverged;
+        } else {
+            out.fun = NAN; out.nit = 0;
+            if (st == kBadBounds) { out.x[0] = out.x[1] = out.x[2] = NAN; }
+        }
+        out.status = st;
+        return out;
     }
-    out.status = status;
-    return out;
-}
+};
 
 }  // namespace lb
 }  // namespace t2fit

@@ -65,12 +65,14 @@ static int dispatch_lb(int n_echo, const float* rows, int64_t m, const lb::LbCon
                        int32_t* nfev, uint8_t* status, int32_t* result, float* trace_f, float* trace_step, int32_t* trace_len,
                        int trace_cap) {
     for (int64_t i = 0; i < m; ++i) {
-        int tl = 0;
-        const lb::LbVoxel v = lb::lbfgsb_voxel<OBJ>(rows + i * n_echo, c, true, trace_f ? trace_f + i * trace_cap : nullptr,
-                                                    trace_step ? trace_step + i * trace_cap : nullptr, trace_cap, &tl);
+        lb::VoxelRun<OBJ> run;
+        run.start(rows + i * n_echo, c, trace_f ? trace_f + i * trace_cap : nullptr,
+                  trace_step ? trace_step + i * trace_cap : nullptr, (trace_f || trace_step) ? trace_cap : 0);
+        while (run.active) run.pass(c);
+        const lb::LbVoxel v = run.finish();
         x[3 * i] = v.x[0]; x[3 * i + 1] = v.x[1]; x[3 * i + 2] = v.x[2];
         fun[i] = v.fun; nit[i] = v.nit; nfev[i] = v.nfev; status[i] = (uint8_t)v.status; result[i] = v.result;
-        if (trace_len) trace_len[i] = tl;
+        if (trace_len) trace_len[i] = v.trace_len;
     }
     return 0;
 }
