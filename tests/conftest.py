@@ -28,9 +28,36 @@ def load_golden(name):
 
 
 def fit_params_of(g):
+    """The fit_params dict the fixture was generated with: its x0 / bounds and the preset's scipy options
+    (run_t2mapping.py:36-106; every fixture uses the options of its (fit, field) preset)."""
+    from fetal_t2mapping_b200 import presets
+    opts = presets.preset(g["fit"], g.get("field", "lf") == "lf")[1]["options"]
     return {"initial_guess": [float(v) for v in g["x0"]],
             "param_bounds": [(float(a), float(b)) for a, b in g["bounds"]],
-            "solver": "L-BFGS-B", "options": {}}
+            "solver": "L-BFGS-B", "options": opts}
+
+
+def lbfgsb_parity_report(t2, nit, success, g):
+    """Parity of a reference-faithful (L-BFGS-B) result with a fixture, judged against the reference's own
+    reproducibility floor (tests/golden/make_jitter.py): returns a dict of rates."""
+    ref, rp = g["ref_params"], g["reproducible"]
+    with np.errstate(all="ignore"):
+        rel = np.abs(np.asarray(t2, np.float64) - ref[:, 1]) / np.abs(ref[:, 1])
+        relj = np.abs(g["jit_params"][:, 1] - ref[:, 1]) / np.abs(ref[:, 1])
+    return dict(all=float(np.mean(rel <= 1e-3)), jitter_all=float(np.mean(relj <= 1e-3)),
+                reproducible=float(np.mean(rel[rp] <= 1e-3)), n_reproducible=int(rp.sum()),
+                nit_eq=float(np.mean(np.asarray(nit) == g["ref_nit"])), jitter_nit_eq=float(np.mean(g["jit_nit"] == g["ref_nit"])),
+                success_eq=bool(np.array_equal(np.asarray(success, bool), g["ref_success"])))
+
+
+def assert_lbfgsb_parity(rep, name):
+    """Tolerances: identical success sets; relative |dT2| <= 1e-3 on >= 99 % of the voxels whose reference
+    result is reproducible under a 1-ulp change of exp (the rest differ between two runs of the reference
+    itself); over ALL voxels no worse than the reference's own jittered rerun by more than 1.5 points."""
+    assert rep["success_eq"], name
+    assert rep["reproducible"] >= 0.99, (name, rep)
+    assert rep["all"] >= rep["jitter_all"] - 0.015, (name, rep)
+    assert rep["nit_eq"] >= rep["jitter_nit_eq"] - 0.03, (name, rep)
 
 
 @pytest.fixture(scope="session")

@@ -1,0 +1,134 @@
+"""Augment the golden fixtures with the reference's own reproducibility floor and callback traces.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_jitter.py
+
+Why: fit_voxel differentiates its objective by forward differences with an absolute step of 1e-8
+(scipy ``jac=False``), so a one-ulp difference in ``np.exp`` changes the gradient by up to
+ulp(f)/1e-8 -- about 1e-6 relative far from the optimum -- and the L-BFGS-B trajectory with it.
+numpy ships several exp kernels (AVX512F / libm) that differ in the last ulp, so the reference does
+not reproduce its own maps bit for bit across hosts; with the loose ftol=gtol=1e-2 presets a few
+percent of the voxels land on visibly different points.  To state parity against an optimiser with
+that property, every fixture gets a second run of the UNMODIFIED reference in which ``np.exp``
+is replaced (module global ``np`` of run_t2mapping) by a proxy that returns the neighbouring
+double for a deterministic ~14 % of its results:
+
+    jit_params / jit_success / jit_nit      the reference's outputs under that 1-ulp jitter
+    reproducible                            success equal and |dT2|/T2 <= 1e-4 between the two runs
+
+and, for the first 24 voxels, the callback traces of the plain run (iteration_info, :180-234):
+
+    trace_f [24, 64], trace_step [24, 64], trace_len [24]
+"""
+import argparse
+import contextlib
+import copy
+import io
+import os
+import sys
+import warnings
+from functools import partial
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from oracle.ref_loader import load_reference             # noqa: E402
+from make_golden import ref_preset                        # noqa: E402
+
+TRACE_VOX, TRACE_CAP = 24, 64
+
+
+class JitterNumpy:
+    """numpy, except that exp() returns the next double up for results whose bit pattern is 0 mod 7."""
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+    @staticmethod
+    def exp(a):
+        e = np.exp(a)
+        bits = np.asarray(e, dtype=np.float64).view(np.int64)
+        return np.where(bits % 7 == 0, np.nextafter(e, np.inf), e)
+
+
+def _one(i, ref_fit_voxel, fit, fit_params, te, rows, prior, norm, want_trace):
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        try:
+            p, ok, nit, fun, info = ref_fit_voxel(i, fit, copy.deepcopy(fit_params), te, rows, prior, norm)
+            tr = [(d["f_val"], d["step_size"]) for d in info] if want_trace else []
+            return np.asarray(p, float), bool(ok), int(nit), float(fun), tr
+        except ValueError:
+            return np.full(len(fit_params["initial_guess"]), np.nan), False, -1, np.nan, []
+
+
+def run_rows(ref, rows, te, fit, fp, prior, norm, procs, want_trace=False):
+    import multiprocessing as mp
+    fn = partial(_one, ref_fit_voxel=ref.fit_voxel, fit=fit, fit_params=fp, te=te, rows=rows, prior=prior, norm=norm,
+                 want_trace=want_trace)
+    if procs > 1 and rows.shape[0] >= 64:
+        with mp.get_context("fork").Pool(procs) as pool:
+            return pool.map(fn, range(rows.shape[0]), chunksize=32)
+    return [fn(i) for i in range(rows.shape[0])]
+
+
+def augment(ref, path, procs):
+    d = dict(np.load(path, allow_pickle=True))
+    fit, field = str(d["fit"]), str(d.get("field", "lf"))
+    prior, norm = bool(d["prior"]), bool(d["norm"])
+    rows, te = d["rows"], d["te"]
+    _, fp = ref_preset(ref, fit, field)
+    fp["initial_guess"] = [float(v) for v in d["x0"]]
+    fp["param_bounds"] = [tuple(float(v) for v in b) for b in d["bounds"]]
+    # traces of the plain reference for the first voxels
+    nt = min(TRACE_VOX, rows.shape[0])
+    out = run_rows(ref, rows[:nt], te, fit, fp, prior, norm, 1, want_trace=True)
+    tf = np.full((nt, TRACE_CAP), np.nan, np.float64)
+    ts = np.full((nt, TRACE_CAP), np.nan, np.float64)
+    tl = np.zeros(nt, np.int32)
+    for i, o in enumerate(out):
+        n = min(len(o[4]), TRACE_CAP)
+        tl[i] = n
+        for j in range(n):
+            tf[i, j], ts[i, j] = o[4][j]
+        assert np.allclose(o[0], d["ref_params"][i], equal_nan=True), "plain rerun differs from the stored fixture"
+    # the same reference with a 1-ulp jitter in np.exp
+    real_np = ref.np
+    ref.np = JitterNumpy()
+    try:
+        out = run_rows(ref, rows, te, fit, fp, prior, norm, procs)
+    finally:
+        ref.np = real_np
+    jp = np.array([o[0] for o in out]); jok = np.array([o[1] for o in out]); jn = np.array([o[2] for o in out], np.int32)
+    with np.errstate(all="ignore"):
+        rel = np.abs(jp[:, 1] - d["ref_params"][:, 1]) / np.abs(d["ref_params"][:, 1])
+    repro = (jok == d["ref_success"]) & (rel <= 1e-4)
+    d.update(jit_params=jp, jit_success=jok, jit_nit=jn, reproducible=repro, trace_f=tf, trace_step=ts, trace_len=tl)
+    np.savez_compressed(path, **d)
+    print(f"{os.path.basename(path)}: M={rows.shape[0]} reproducible={int(repro.sum())} ({repro.mean():.4f}); "
+          f"jitter run within 1e-3 of plain run: {np.mean(rel <= 1e-3):.4f}; nit equal {np.mean(jn == d['ref_nit']):.4f}", flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--procs", type=int, default=os.cpu_count())
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    ref = load_reference()
+    names = ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior", "c2_gaussian_hf_prior", "c3_floor_noprior",
+             "c3_floor_prior", "c5_floor_noprior", "c3_rician_prior", "norm_gaussian"]
+    for n in names:
+        if a.only and a.only not in n:
+            continue
+        augment(ref, os.path.join(HERE, n + ".npz"), a.procs)
+
+
+if __name__ == "__main__":
+    main()

@@ -8,7 +8,7 @@ classification is stored in the golden fixtures (tests/golden/make_golden.py).
 import numpy as np
 import pytest
 
-from tests.conftest import fit_params_of, load_golden
+from tests.conftest import assert_lbfgsb_parity, fit_params_of, lbfgsb_parity_report, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -29,6 +29,80 @@ def run_rows(t2, g, device, **kw):
         return dict(t2=conv(r.t2), k=conv(r.k), sigma=conv(r.sigma), res=conv(r.res), fun=conv(r.fun),
                     nit=conv(r.nit), status=conv(r.status))
     return dict(t2=r.t2, k=r.k, sigma=r.sigma, res=r.res, fun=r.fun, nit=r.nit, status=r.status)
+
+
+LB_CASES = ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior", "c2_gaussian_hf_prior", "c3_floor_noprior",
+            "c3_floor_prior", "c5_floor_noprior", "c3_rician_prior", "norm_gaussian"]
+
+
+@pytest.mark.parametrize("name", LB_CASES)
+def test_lbfgsb_solver_reproduces_the_reference(gpu_lib, name):
+    """T2FIT_SOLVER_LBFGSB (the reference's own optimiser restated in FP64) against the reference's outputs for
+    all three fit types, including the presets that stop before convergence (ftol = gtol = 1e-2)."""
+    g = load_golden(name)
+    o = run_rows(gpu_lib, g, True, solver="lbfgsb")
+    rep = lbfgsb_parity_report(o["t2"], o["nit"], o["status"] == 0, g)
+    assert_lbfgsb_parity(rep, name)
+    # k, sigma and the final objective value on the voxels whose iteration count agrees (same trajectory)
+    same = (o["nit"] == g["ref_nit"]) & g["reproducible"]
+    ref = g["ref_params"]
+    assert np.quantile(np.abs(o["k"][same] - ref[same, 0]) / np.maximum(np.abs(ref[same, 0]), 1.0), 0.99) <= 2e-3
+    assert np.quantile(np.abs(o["fun"][same] - g["ref_fun"][same]) / np.maximum(np.abs(g["ref_fun"][same]), 1e-6), 0.99) <= 2e-3
+    if g["fit"] != "gaussian":
+        # sigma is the loosest direction of these presets (ftol = gtol = 1e-2): 90 % within 1e-2, 99 % within 0.1
+        rs = np.abs(o["sigma"][same] - ref[same, 2]) / np.maximum(np.abs(ref[same, 2]), 1.0)
+        assert np.quantile(rs, 0.90) <= 1e-2 and np.quantile(rs, 0.99) <= 1e-1
+
+
+@pytest.mark.parametrize("name", ["c2_gaussian_noprior", "c3_floor_noprior", "c3_rician_prior"])
+def test_lbfgsb_callback_traces(gpu_lib, name):
+    """iteration_info of the reference's callbacks (run_t2mapping.py:180-234): f_val and step_size per iteration,
+    NaN step on the first one; host and device memory paths."""
+    import torch
+    g = load_golden(name)
+    nt = g["trace_len"].shape[0]
+    fp = fit_params_of(g)
+    for dev in (False, True):
+        rows = g["rows"][:nt]
+        rows = torch.from_numpy(np.ascontiguousarray(rows)).cuda() if dev else rows
+        r = gpu_lib.fit_voxels_batch(rows, None, g["te"], g["fit"], fp, prior=g["prior"], norm=g["norm"], solver="lbfgsb",
+                                     trace_cap=64)
+        infos = r.iteration_infos
+        nit = np.asarray(r.nit.cpu() if dev else r.nit)
+        assert len(infos) == nt
+        checked = 0
+        for i in range(nt):
+            assert len(infos[i]) == min(nit[i], 64)
+            if nit[i] != g["ref_nit"][i] or not g["reproducible"][i]:
+                continue
+            n = int(g["trace_len"][i])
+            assert np.isnan(infos[i][0]["step_size"]) and infos[i][0]["grad_norm"] is None
+            f = np.array([d["f_val"] for d in infos[i]])
+            st = np.array([d["step_size"] for d in infos[i]])
+            # first iterations and the final point agree closely; in between finite-difference noise lets the two
+            # trajectories drift by a few percent before they contract to the same answer
+            assert np.allclose(f[:min(n, 3)], g["trace_f"][i, :min(n, 3)], rtol=5e-3), (name, i)
+            assert np.allclose(f[n - 1], g["trace_f"][i, n - 1], rtol=1e-2), (name, i)
+            if n > 1:
+                assert np.allclose(st[1], g["trace_step"][i, 1], rtol=2e-2, atol=1e-3), (name, i)
+            checked += 1
+        assert checked >= nt // 2
+        ar = r.as_all_results()
+        assert len(ar) == nt and len(ar[0]) == 5 and len(ar[0][4]) == len(infos[0]) and ar[0][2] == nit[0]
+
+
+def test_rician_failed_set(gpu_lib):
+    """rician_obj takes log(signal): any echo <= 0 makes the objective NaN and scipy gives up at the clipped x0
+    with success False (SURVEY 8(a) probe)."""
+    _, fp = gpu_lib.preset("rician", True)
+    te = np.array([114.0, 202.0, 299.0])
+    rows = np.array([[700, 390, 150], [700, 0, 150], [700, -5, 150], [np.nan, 390, 150]], np.float32)
+    r = gpu_lib.fit_voxels_batch(rows, None, te, "rician", fp, prior=True)
+    assert r.solver == "lbfgsb"
+    assert list(r.status == 0) == [True, False, False, False]
+    assert np.allclose(r.k[1:], 650) and np.allclose(r.t2[1:], 110) and np.allclose(r.sigma[1:], 40)
+    with pytest.raises(ValueError):
+        gpu_lib.fit_voxels_batch(rows, None, te, "rician", fp, prior=True, solver="fast")
 
 
 @pytest.mark.parametrize("device", [False, True], ids=["host", "device"])
@@ -77,7 +151,7 @@ def test_floor_model_reaches_a_bounded_minimum(gpu_lib, name):
     point in the reference's own objective, (iii) it agrees with the exact bounded LSQ minimiser on the
     voxels where that minimiser is well determined (signal present, same basin)."""
     g = load_golden(name)
-    o = run_rows(gpu_lib, g, True)
+    o = run_rows(gpu_lib, g, True, solver="fast")
     assert np.array_equal(o["status"] == 0, g["ref_success"]) or (o["status"] != 0).mean() < 0.01
     te = g["te"][None, :]
     y = g["rows"].astype(np.float64)
@@ -97,9 +171,10 @@ def test_floor_model_reaches_a_bounded_minimum(gpu_lib, name):
     assert (rel[sel] <= T2_RTOL).mean() >= 0.97
 
 
+@pytest.mark.parametrize("solver", ["fast", "lbfgsb"])
 @pytest.mark.parametrize("fit", ["gaussian", "gaussian_rician"])
 @pytest.mark.parametrize("prior", [True, False], ids=["prior", "noprior"])
-def test_edge_cases_failed_sets(gpu_lib, fit, prior):
+def test_edge_cases_failed_sets(gpu_lib, fit, prior, solver):
     g = load_golden(f"edge_{fit}_{'prior' if prior else 'noprior'}")
     fp = fit_params_of(g)
     raises = np.array([len(str(e)) > 0 for e in g["ref_error"]])
@@ -107,10 +182,10 @@ def test_edge_cases_failed_sets(gpu_lib, fit, prior):
     if raises.any():
         # scipy raised ValueError inside those voxels -> the reference's whole pool.map aborts
         with pytest.raises(ValueError):
-            gpu_lib.fit_voxels_batch(rows, None, g["te"], fit, fp, prior=prior, norm=False)
+            gpu_lib.fit_voxels_batch(rows, None, g["te"], fit, fp, prior=prior, norm=False, solver=solver)
         rows = rows[~raises]
     keep = ~raises
-    r = gpu_lib.fit_voxels_batch(rows, None, g["te"], fit, fp, prior=prior, norm=False)
+    r = gpu_lib.fit_voxels_batch(rows, None, g["te"], fit, fp, prior=prior, norm=False, solver=solver)
     # identical failed-fit set
     assert np.array_equal(r.status == 0, g["ref_success"][keep])
     failed = ~g["ref_success"][keep]
@@ -118,10 +193,15 @@ def test_edge_cases_failed_sets(gpu_lib, fit, prior):
     # failed voxels keep the clipped x0, finite numbers, never NaN
     assert np.allclose(r.t2[failed], ref[failed, 1]) and np.allclose(r.k[failed], ref[failed, 0])
     assert np.isfinite(r.t2).all() and np.isfinite(r.k).all()
-    if fit == "gaussian":
+    if fit == "gaussian" or solver == "lbfgsb":
         ok = g["converged"][keep] & (ref[:, 1] > 10.0)     # T2 on its lower bound: k not identifiable
         rel = np.abs(r.t2[ok] - ref[ok, 1]) / ref[ok, 1]
-        assert rel.max() <= T2_RTOL
+        if solver == "fast":
+            assert rel.max() <= T2_RTOL
+        else:       # pathological rows: one ulp of exp can move the reference's own stopping point by percents
+            assert np.mean(rel <= T2_RTOL) >= 0.75 and rel.max() <= 5e-2
+    if solver == "lbfgsb":                                 # same optimiser: same iteration counts on these rows
+        assert np.mean(r.nit == g["ref_nit"][keep]) >= 0.8
 
 
 def test_norm_path(gpu_lib):
@@ -130,7 +210,7 @@ def test_norm_path(gpu_lib):
     LSQ minimiser of the same normalised objective instead, and loosely with the reference."""
     from oracle import fit_oracle as fo
     g = load_golden("norm_gaussian")
-    o = run_rows(gpu_lib, g, True)
+    o = run_rows(gpu_lib, g, True, solver="fast")
     assert (o["status"] == 0).all()
     fp = fit_params_of(g)
     ex = np.array([fo.fit_voxel_exact(i, "gaussian", fp, g["te"], g["rows"], True, True)[0] for i in range(120)])
@@ -168,12 +248,16 @@ def test_volume_block_matches_reference_block(gpu_lib, fit):
         for m in maps:
             assert (m[~mask] == 0).all()                   # zeros off-mask, never NaN
         assert np.array_equal(np.flatnonzero(t2m.reshape(-1)), g["mask_indices"])
+        rel = np.abs(t2m[mask] - g["t2"][mask]) / g["t2"][mask]
+        close = (rel <= 1e-4) & (np.abs(km[mask] - g["k"][mask]) <= 1e-4 * np.abs(g["k"][mask])) & \
+                (np.abs(sm[mask] - g["sigma"][mask]) <= 1e-3 * np.maximum(g["sigma"][mask], 1.0))
+        assert np.abs(rm[mask][close] - g["res"][mask][close]).max() < 0.05
         if fit == "gaussian":
-            rel = np.abs(t2m[mask] - g["t2"][mask]) / g["t2"][mask]
             assert (rel <= T2_RTOL).mean() >= 0.98
-            close = rel <= 1e-4
-            assert np.abs(rm[mask][close] - g["res"][mask][close]).max() < 0.05
             assert (sm == 0).all()
+        else:                                              # default solver for this fit: the reference's optimiser
+            assert (rel <= T2_RTOL).mean() >= 0.90 and close.mean() >= 0.3
+            assert np.abs(sm[mask][close] - g["sigma"][mask][close]).max() < 0.5
 
 
 def test_host_and_device_paths_bit_identical(gpu_lib):
@@ -240,9 +324,9 @@ def test_full_size_c2_properties(gpu_lib):
     assert ok.all() and (rel <= T2_RTOL).mean() >= 0.995
 
 
-@pytest.mark.parametrize("fit", ["gaussian", "gaussian_rician"])
+@pytest.mark.parametrize("fit,solver", [("gaussian", "fast"), ("gaussian_rician", "fast"), ("gaussian_rician", "lbfgsb")])
 @pytest.mark.parametrize("shape", [(13, 11, 7), (40, 37, 29), (64, 64, 5)])
-def test_fused_zero_fill_ragged_volumes(gpu_lib, fit, shape):
+def test_fused_zero_fill_ragged_volumes(gpu_lib, fit, solver, shape):
     """The fill-role blocks of the fit launch must zero every unmasked slot (and all of sigma for the
     2-parameter model) whatever the volume size, starting from NaN-poisoned maps, and must never touch a
     masked slot; mask bytes other than 1 count as masked."""
@@ -260,7 +344,7 @@ def test_fused_zero_fill_ragged_volumes(gpu_lib, fit, shape):
     _, fp = gpu_lib.preset(fit, True)
     lib = gpu_lib.init()
     p, o = _abi.Problem(), _abi.Outputs()
-    keep = _fill_problem(p, fit, fp, te, False, False, 0, 0.0, "loglinear")
+    keep = _fill_problem(p, fit, fp, te, False, False, 0, 0.0, "loglinear", solver)
     yd, idxd, md = torch.from_numpy(y).cuda(), torch.from_numpy(idx).cuda(), torch.from_numpy(mask).cuda()
     maps = torch.full((4, n), float("nan"), device="cuda")
     p.echoes, p.memory, p.layout, p.mask_idx, p.n_vox, p.n_fit = yd.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_AOS, idxd.data_ptr(), n, idx.size
@@ -273,7 +357,7 @@ def test_fused_zero_fill_ragged_volumes(gpu_lib, fit, shape):
     assert not np.isnan(m).any()
     off = mask == 0
     assert (m[:, off] == 0).all()
-    ref = gpu_lib.fit_voxels_batch(yd, idxd, te, fit, fp, prior=False)
+    ref = gpu_lib.fit_voxels_batch(yd, idxd, te, fit, fp, prior=False, solver=solver)
     torch.cuda.synchronize()
     assert np.array_equal(m[0, idx], ref.t2.cpu().numpy()) and np.array_equal(m[1, idx], ref.k.cpu().numpy())
     assert np.array_equal(m[3, idx], ref.res.cpu().numpy())
