@@ -10,4 +10,7 @@ from .presets import preset, set_fit_params                                     
 from .api import (FitResult, compute_residuals, device_info, fit_voxels_batch, init,   # noqa: F401
                   mask_indices_device, shutdown, t2map_volume, work_model)
 
-__version__ = "0.1.0"
+from .roi import phantom_roi_table, roi_stats, save_phantom_csv, set_phantom_gt        # noqa: F401
+from .loader import VolumeMaps, t2map_series                                          # noqa: F401
+
+__version__ = "0.2.0"

@@ -20,6 +20,8 @@ SOLVERS = {"fast": SOLVER_FAST, "lbfgsb": SOLVER_LBFGSB}
 
 LAYOUT_AOS = 0
 LAYOUT_SOA = 1
+LAYOUT_PLANES = 2
+DTYPES = {"uint8": 0, "int16": 1, "uint16": 2, "int32": 3, "float32": 4, "float64": 5, "bool": 0}
 MEM_HOST = 0
 MEM_DEVICE = 1
 
@@ -92,6 +94,10 @@ SYMBOLS = [
     ("t2fit_run", C.c_int, [C.POINTER(Problem), C.POINTER(Outputs), C.c_void_p]),
     ("t2fit_status_counts", C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     ("t2fit_mask_indices", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    ("t2fit_mask_union", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
+                                   C.c_void_p]),
+    ("t2fit_roi_stats", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_double),
+                                  C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_void_p]),
     ("t2fit_pack_soa", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                  C.c_void_p]),
     ("t2fit_scatter", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int64,

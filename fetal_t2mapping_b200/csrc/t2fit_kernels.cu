@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
     const int64_t row = io.idx ? __ldg(io.idx + ii) : ii;
     float y[E];
     if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row, io.vec_ok != 0, y);
-    else load_soa<E>(io.echoes, io.ld, ii, y);
+    else if (LAYOUT == T2FIT_LAYOUT_SOA) load_soa<E>(io.echoes, io.ld, ii, y);
+    else load_soa<E>(io.echoes, io.ld, row, y);          // PLANES: per-TE volumes, voxel `row` of every plane
 
     const VoxelFit f = fit_voxel<float, MODEL, E>(y, c, valid);
 
@@ -273,7 +274,10 @@ __global__ void __launch_bounds__(kLbBlock) lbfgsb_kernel(const __grid_constant_
                     row = io.idx ? __ldg(io.idx + i) : i;
                     float yraw[kMaxEcho];
                     if (io.layout == T2FIT_LAYOUT_AOS) { for (int e = 0; e < E; ++e) yraw[e] = __ldg(io.echoes + row * E + e); }
-                    else { for (int e = 0; e < E; ++e) yraw[e] = __ldg(io.echoes + (int64_t)e * io.ld + i); }
+                    else {
+                        const int64_t col = io.layout == T2FIT_LAYOUT_SOA ? i : row;
+                        for (int e = 0; e < E; ++e) yraw[e] = __ldg(io.echoes + (int64_t)e * io.ld + col);
+                    }
                     const bool tr = io.trace_cap > 0;
                     run.start(yraw, c, (tr && io.trace_f) ? io.trace_f + i * io.trace_cap : nullptr,
                               (tr && io.trace_step) ? io.trace_step + i * io.trace_cap : nullptr, tr ? io.trace_cap : 0);
@@ -388,6 +392,78 @@ __global__ void __launch_bounds__(256) mask_write_kernel(const uint8_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// mask union from per-TE mask volumes + --in_vitro_fast label masking (run_t2mapping.py:383-384,393-400)
+// ------------------------------------------------------------------------------------------------
+struct UnionArgs {
+    const void* planes[kMaxEcho];
+    const void* label;
+    int n_planes, dtype, label_dtype;
+    int64_t n_vox;
+};
+
+__device__ __forceinline__ double load_as_double(const void* p, int dtype, int64_t v) {
+    switch (dtype) {
+        case T2FIT_DT_U8: return (double)static_cast<const uint8_t*>(p)[v];
+        case T2FIT_DT_I16: return (double)static_cast<const int16_t*>(p)[v];
+        case T2FIT_DT_U16: return (double)static_cast<const uint16_t*>(p)[v];
+        case T2FIT_DT_I32: return (double)static_cast<const int32_t*>(p)[v];
+        case T2FIT_DT_F32: return (double)static_cast<const float*>(p)[v];
+        default: return static_cast<const double*>(p)[v];
+    }
+}
+
+__global__ void __launch_bounds__(256) mask_union_kernel(const __grid_constant__ UnionArgs a, uint8_t* __restrict__ out) {
+    const int64_t nt = (int64_t)gridDim.x * 256;
+    for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < a.n_vox; v += nt) {
+        double sum = 0.0;
+        for (int p = 0; p < a.n_planes; ++p) sum += load_as_double(a.planes[p], a.dtype, v);   // np.sum(mask, axis=3)
+        bool m = sum > 0.0;
+        if (a.label && load_as_double(a.label, a.label_dtype, v) == 0.0) m = false;            // mask[label == 0] = 0
+        out[v] = m ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phantom ROI statistics (save_phantom_csv): NaN-skipping mean / population std per label, two passes
+// (mean first, then squared deviations, as np.nanstd does).  Per-block shared accumulators (float64),
+// one atomicAdd per (map, roi) per block into the global accumulators.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxRoi = 64;
+constexpr int kMaxStatMaps = 4;
+
+struct RoiArgs {
+    const float* maps[kMaxStatMaps];
+    const int32_t* label;
+    int64_t n_vox;
+    int n_maps, n_roi, pass;       // pass 0: count + sum, pass 1: sum of squared deviations from mean[]
+};
+
+__global__ void __launch_bounds__(256) roi_stats_kernel(const __grid_constant__ RoiArgs a, double* __restrict__ sum,
+                                                        unsigned long long* __restrict__ cnt, const double* __restrict__ mean) {
+    __shared__ double s_sum[kMaxStatMaps * kMaxRoi];
+    __shared__ unsigned long long s_cnt[kMaxStatMaps * kMaxRoi];
+    const int slots = a.n_maps * a.n_roi;
+    for (int i = threadIdx.x; i < slots; i += 256) { s_sum[i] = 0.0; s_cnt[i] = 0ull; }
+    __syncthreads();
+    const int64_t nt = (int64_t)gridDim.x * 256;
+    for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < a.n_vox; v += nt) {
+        const int lab = __ldg(a.label + v);
+        if (lab < 1 || lab > a.n_roi) continue;
+        for (int m = 0; m < a.n_maps; ++m) {
+            const float x = __ldg(a.maps[m] + v);
+            if (x != x) continue;                                   // nanmean / nanstd skip NaN
+            const int slot = m * a.n_roi + lab - 1;
+            if (a.pass == 0) { atomicAdd(&s_sum[slot], (double)x); atomicAdd(&s_cnt[slot], 1ull); }
+            else { const double d = (double)x - mean[slot]; atomicAdd(&s_sum[slot], d * d); }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < slots; i += 256) {
+        if (s_sum[i] != 0.0 || s_cnt[i]) { atomicAdd(sum + i, s_sum[i]); if (a.pass == 0) atomicAdd(cnt + i, s_cnt[i]); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // pack / scatter
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_soa_kernel(const float* __restrict__ aos, int n_echo, const int64_t* __restrict__ idx,
@@ -461,8 +537,10 @@ FitFn pick_e(int n_echo) {
 
 FitFn pick_kernel(int model, int n_echo, int layout) {
     if (model == T2FIT_MODEL_GAUSSIAN)
-        return layout == T2FIT_LAYOUT_AOS ? pick_e<kMono2, T2FIT_LAYOUT_AOS>(n_echo) : pick_e<kMono2, T2FIT_LAYOUT_SOA>(n_echo);
-    return layout == T2FIT_LAYOUT_AOS ? pick_e<kFloor3, T2FIT_LAYOUT_AOS>(n_echo) : pick_e<kFloor3, T2FIT_LAYOUT_SOA>(n_echo);
+        return layout == T2FIT_LAYOUT_AOS ? pick_e<kMono2, T2FIT_LAYOUT_AOS>(n_echo)
+               : layout == T2FIT_LAYOUT_SOA ? pick_e<kMono2, T2FIT_LAYOUT_SOA>(n_echo) : pick_e<kMono2, T2FIT_LAYOUT_PLANES>(n_echo);
+    return layout == T2FIT_LAYOUT_AOS ? pick_e<kFloor3, T2FIT_LAYOUT_AOS>(n_echo)
+           : layout == T2FIT_LAYOUT_SOA ? pick_e<kFloor3, T2FIT_LAYOUT_SOA>(n_echo) : pick_e<kFloor3, T2FIT_LAYOUT_PLANES>(n_echo);
 }
 
 using LbFn = void (*)(const lb::LbConsts, const KernelIO, unsigned long long*);
@@ -767,9 +845,21 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
                         i = j;
                     }
                 }
-            } else {                              // SoA planes [E, ld] -> planes [E, n]
+            } else if (p.layout == T2FIT_LAYOUT_SOA) {   // SoA planes [E, ld] -> planes [E, n]
                 for (int e = 0; e < E; ++e)
                     memcpy(s.h_in + (int64_t)e * n + lo, p.echoes + (int64_t)e * p.ld + first + lo, sizeof(float) * (hi - lo));
+            } else {                              // per-TE volumes [E, ld >= n_vox] -> planes [E, n] of the masked voxels
+                const int64_t* idx = p.mask_idx ? p.mask_idx + first : nullptr;
+                for (int64_t i = lo; i < hi; ++i) {
+                    const int64_t v = idx ? idx[i] : first + i;
+                    if (v < 0 || v >= p.n_vox) { bad_index.store(true); return; }
+                }
+                for (int e = 0; e < E; ++e) {
+                    const float* src = p.echoes + (int64_t)e * p.ld;
+                    float* dst = s.h_in + (int64_t)e * n;
+                    if (idx) for (int64_t i = lo; i < hi; ++i) dst[i] = src[idx[i]];
+                    else memcpy(dst + lo, src + first + lo, sizeof(float) * (hi - lo));
+                }
             }
         });
         t_pack += now_ms() - tp;
@@ -784,12 +874,13 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
         io.t2 = df; io.k = df + n; io.sigma = df + 2 * n; io.res = df + 3 * n; io.fun = df + 4 * n;
         io.nit = reinterpret_cast<int32_t*>(s.d_out + (size_t)5 * n * sizeof(float));
         io.status = s.d_out + (size_t)5 * n * sizeof(float) + (size_t)n * sizeof(int32_t);
-        io.counts = c->d_counts; io.dense = 0; io.vec_ok = 1; io.layout = p.layout;
+        io.counts = c->d_counts; io.dense = 0; io.vec_ok = 1;
+        io.layout = p.layout == T2FIT_LAYOUT_AOS ? T2FIT_LAYOUT_AOS : T2FIT_LAYOUT_SOA;     // staged chunks are packed
         if (tracing) {
             TraceScratch& t = tsc[ch % kSlots];
             io.trace_f = t.f; io.trace_step = t.s; io.trace_len = t.n; io.trace_cap = o.trace_cap;
         }
-        rc = lc ? launch_lbfgsb(c, *lc, io, p.model, E, s.stream) : launch_fit(c, fc, io, p.model, E, p.layout, s.stream);
+        rc = lc ? launch_lbfgsb(c, *lc, io, p.model, E, s.stream) : launch_fit(c, fc, io, p.model, E, io.layout, s.stream);
         if (rc) { free_trace(); return rc; }
         if (tracing) {
             const size_t tb = sizeof(float) * (size_t)n * o.trace_cap;
@@ -942,9 +1033,11 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     const bool fill_only = p->n_fit == 0 && p->memory == T2FIT_MEM_DEVICE && o->dense && o->zero_fill_mask;
     if (p->n_fit == 0 && !fill_only) { memset(o->status_count, 0, sizeof(o->status_count)); return T2FIT_OK; }
     if (!p->echoes && !fill_only) return fail(T2FIT_EINVAL, "echoes is NULL");
-    if (p->layout != T2FIT_LAYOUT_AOS && p->layout != T2FIT_LAYOUT_SOA) return fail(T2FIT_EINVAL, "bad layout");
+    if (p->layout != T2FIT_LAYOUT_AOS && p->layout != T2FIT_LAYOUT_SOA && p->layout != T2FIT_LAYOUT_PLANES)
+        return fail(T2FIT_EINVAL, "bad layout");
     if (p->layout == T2FIT_LAYOUT_SOA && p->ld < p->n_fit) return fail(T2FIT_EINVAL, "ld < n_fit");
-    if (p->layout == T2FIT_LAYOUT_AOS && !p->mask_idx && p->n_fit > p->n_vox) return fail(T2FIT_EINVAL, "n_fit > n_vox");
+    if (p->layout == T2FIT_LAYOUT_PLANES && p->ld < p->n_vox) return fail(T2FIT_EINVAL, "ld < n_vox");
+    if (p->layout != T2FIT_LAYOUT_SOA && !p->mask_idx && p->n_fit > p->n_vox) return fail(T2FIT_EINVAL, "n_fit > n_vox");
     if (o->dense && !p->mask_idx && p->n_fit > p->n_vox) return fail(T2FIT_EINVAL, "dense output needs n_vox >= n_fit");
     CU_TRY(cudaSetDevice(c->device));
     if (p->memory == T2FIT_MEM_HOST) return run_host(c, *p, *o, fc, lbs ? &lc : nullptr);
@@ -1019,6 +1112,72 @@ int t2fit_mask_indices(const uint8_t* masks, int64_t n_vox, int32_t n_masks, int
     CU_TRY(cudaMemcpyAsync(c->h_total, c->d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     *n_out = *c->h_total;
+    return T2FIT_OK;
+}
+
+int t2fit_mask_union(const void* const* planes, int32_t n_planes, int32_t dtype, const void* label, int32_t label_dtype,
+                     int64_t n_vox, uint8_t* mask_out, void* stream) {
+    Context* c = g_ctx;
+    if (!c) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
+    if (!planes || n_planes < 1 || n_planes > kMaxEcho || !mask_out || n_vox < 0) return fail(T2FIT_EINVAL, "bad mask_union arguments");
+    if (dtype < T2FIT_DT_U8 || dtype > T2FIT_DT_F64 || (label && (label_dtype < T2FIT_DT_U8 || label_dtype > T2FIT_DT_F64)))
+        return fail(T2FIT_EINVAL, "bad dtype code");
+    if (n_vox == 0) return T2FIT_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    UnionArgs a{};
+    for (int p = 0; p < n_planes; ++p) { if (!planes[p]) return fail(T2FIT_EINVAL, "NULL mask plane"); a.planes[p] = planes[p]; }
+    a.label = label; a.n_planes = n_planes; a.dtype = dtype; a.label_dtype = label_dtype; a.n_vox = n_vox;
+    const int64_t want = (n_vox + 255) / 256;
+    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)c->prop.multiProcessorCount * 16);
+    mask_union_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, mask_out);
+    CU_TRY(cudaGetLastError());
+    return T2FIT_OK;
+}
+
+int t2fit_roi_stats(const float* const* maps, int32_t n_maps, const int32_t* label, int64_t n_vox, int32_t n_roi, double* mean_out,
+                    double* std_out, int64_t* count_out, void* stream) {
+    Context* c = g_ctx;
+    if (!c) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
+    if (!maps || !label || n_maps < 1 || n_maps > kMaxStatMaps || n_roi < 1 || n_roi > kMaxRoi || n_vox < 0 || !mean_out || !std_out)
+        return fail(T2FIT_EINVAL, "bad roi_stats arguments (n_maps <= 4, n_roi <= 64)");
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int slots = n_maps * n_roi;
+    double *d_sum = nullptr, *d_mean = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    CU_TRY(cudaMalloc(&d_sum, sizeof(double) * slots * 2));
+    d_mean = d_sum + slots;
+    if (cudaMalloc(&d_cnt, sizeof(unsigned long long) * slots) != cudaSuccess) { cudaFree(d_sum); return fail(T2FIT_ENOMEM, "roi_stats scratch"); }
+    std::vector<double> h_sum(slots), h_mean(slots), h_sq(slots);
+    std::vector<unsigned long long> h_cnt(slots);
+    RoiArgs a{};
+    for (int m = 0; m < n_maps; ++m) a.maps[m] = maps[m];
+    a.label = label; a.n_vox = n_vox; a.n_maps = n_maps; a.n_roi = n_roi;
+    const int64_t want = (n_vox + 255) / 256;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)c->prop.multiProcessorCount * 8));
+    auto cleanup = [&]() { cudaFree(d_sum); cudaFree(d_cnt); };
+    cudaError_t e = cudaMemsetAsync(d_sum, 0, sizeof(double) * slots * 2, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * slots, st);
+    a.pass = 0;
+    if (e == cudaSuccess) { roi_stats_kernel<<<grid, 256, 0, st>>>(a, d_sum, d_cnt, d_mean); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_sum.data(), d_sum, sizeof(double) * slots, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt.data(), d_cnt, sizeof(unsigned long long) * slots, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cleanup(); return fail(T2FIT_ECUDA, std::string("roi_stats pass 0: ") + cudaGetErrorString(e)); }
+    for (int i = 0; i < slots; ++i) h_mean[i] = h_cnt[i] ? h_sum[i] / (double)h_cnt[i] : NAN;
+    e = cudaMemcpyAsync(d_mean, h_mean.data(), sizeof(double) * slots, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_sum, 0, sizeof(double) * slots, st);
+    a.pass = 1;
+    if (e == cudaSuccess) { roi_stats_kernel<<<grid, 256, 0, st>>>(a, d_sum, d_cnt, d_mean); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_sq.data(), d_sum, sizeof(double) * slots, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) return fail(T2FIT_ECUDA, std::string("roi_stats pass 1: ") + cudaGetErrorString(e));
+    for (int i = 0; i < slots; ++i) {
+        mean_out[i] = h_mean[i];
+        std_out[i] = h_cnt[i] ? sqrt(h_sq[i] / (double)h_cnt[i]) : NAN;
+        if (count_out) count_out[i] = (int64_t)h_cnt[i];
+    }
     return T2FIT_OK;
 }
 

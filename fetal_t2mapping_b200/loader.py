@@ -1,0 +1,175 @@
+"""Batched, overlapped loader for the T2 fit: the block of ``process_t2maps`` that feeds the hot path.
+
+Reference (run_t2mapping.py:365-400): per subject/session, read one recon volume and one mask volume per
+echo time, ``np.stack`` them, union the masks (``np.sum(mask, axis=3) > 0``), optionally mask by the
+phantom label (``--in_vitro_fast``: ``mask[label == 0] = 0``), flatten and cast to float32 (:411-412).
+
+Here the per-TE volumes go to the GPU *as they come off disk* -- plane e of an ``[E, N]`` device buffer
+(``T2FIT_LAYOUT_PLANES``), no interleaving ``np.stack`` on the host -- through page-locked staging
+buffers on a copy stream, while the previous volume is being fitted on the compute stream:
+
+    host cast into pinned planes -> H2D (copy stream) -> mask union + label masking -> ordered mask
+    indices -> fit + residuals + zero-filled dense maps (one t2fit_run) -> D2H of the four maps
+
+``depth`` staging slots are in flight.  Everything on the device runs through the C ABI
+(``t2fit_mask_union``, ``t2fit_mask_indices``, ``t2fit_run``); torch provides pinned memory, streams
+and events only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi
+from .api import BOUNDS_ERROR, _fill_problem, _run, _state, init, resolve_solver
+
+__all__ = ["t2map_series", "VolumeMaps"]
+
+
+@dataclass
+class VolumeMaps:
+    """What ``process_t2maps`` holds for one subject/session after the fit (:471-474): the four float32 maps
+    ``[z,y,x]`` (zeros off-mask), plus the union mask and the number of fitted voxels."""
+    t2: np.ndarray
+    k: np.ndarray
+    sigma: np.ndarray
+    res: np.ndarray
+    mask: np.ndarray
+    n_fit: int
+    failed: int
+
+
+class _Slot:
+    def __init__(self, torch, dev, n_echo, n_vox, mask_dtype, label_dtype):
+        self.n_echo, self.n_vox = n_echo, n_vox
+        self.h_planes = torch.empty((n_echo, n_vox), dtype=torch.float32, pin_memory=True)
+        self.d_planes = torch.empty((n_echo, n_vox), dtype=torch.float32, device=dev)
+        self.h_masks = torch.empty((n_echo, n_vox), dtype=mask_dtype, pin_memory=True)
+        self.d_masks = torch.empty((n_echo, n_vox), dtype=mask_dtype, device=dev)
+        self.h_label = torch.empty(n_vox, dtype=label_dtype, pin_memory=True) if label_dtype is not None else None
+        self.d_label = torch.empty(n_vox, dtype=label_dtype, device=dev) if label_dtype is not None else None
+        self.d_mask = torch.empty(n_vox, dtype=torch.uint8, device=dev)
+        self.d_idx = torch.empty(n_vox, dtype=torch.int64, device=dev)
+        self.d_maps = torch.empty((4, n_vox), dtype=torch.float32, device=dev)
+        self.h_maps = torch.empty((4, n_vox), dtype=torch.float32, pin_memory=True)
+        self.h_mask = torch.empty(n_vox, dtype=torch.uint8, pin_memory=True)
+        self.d_status = torch.empty(n_vox, dtype=torch.uint8, device=dev)
+        self.h_cnt = torch.zeros(3, dtype=torch.int64, pin_memory=True)
+        self.copied = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+        self.shape3 = None
+        self.has_label = False
+        self.n_fit = 0
+        self.busy = False
+
+
+def _torch_dtype(torch, np_dtype):
+    name = np.dtype(np_dtype).name
+    if name == "bool":
+        return torch.uint8
+    if name in ("uint8", "int16", "int32", "float32", "float64"):
+        return getattr(torch, name)
+    if name == "uint16":
+        return torch.int32        # widened on the host (torch has no pinned uint16 everywhere)
+    return torch.float32
+
+
+def t2map_series(volumes, TEeffs, fit, fit_params, prior=True, norm=False, *, fast=False, solver="auto", depth=2):
+    """Fit a series of subjects/sessions, overlapping each volume's staging with the previous volume's fit.
+
+    ``volumes``: iterable of ``(t2w_list, mask_list)`` or ``(t2w_list, mask_list, label)`` -- per-TE recon and
+    mask arrays ``[z,y,x]`` in ascending echo-time order as ``process_t2maps`` reads them (:365-381), all of one
+    shape per volume; ``label`` the phantom label image or None.  ``fast`` = ``--in_vitro_fast`` (mask by label,
+    :393-400).  Yields one :class:`VolumeMaps` per volume, in order.  Raises ``ValueError`` where the reference's
+    map would abort (scipy bounds error under ``--no_prior``)."""
+    import torch
+    lib = init()
+    dev = torch.device("cuda", _state["device"])
+    solver = resolve_solver(fit, solver)
+    te = np.asarray(TEeffs, np.float64).reshape(-1)
+    n_echo = te.size
+    copy_stream = torch.cuda.Stream(dev)
+    compute = torch.cuda.Stream(dev)
+    slots = {}
+    pending = []                   # slots whose results have not been yielded yet, in order
+
+    def finish(s):
+        s.done.synchronize()
+        s.busy = False
+        nonfinite, gave_up, bad_bounds = (int(v) for v in s.h_cnt)
+        if bad_bounds > 0:
+            raise ValueError(BOUNDS_ERROR)
+        maps = s.h_maps.numpy()
+        return VolumeMaps(*(maps[i].reshape(s.shape3).copy() for i in range(4)),
+                          mask=s.h_mask.numpy().reshape(s.shape3).astype(bool), n_fit=s.n_fit, failed=nonfinite + gave_up)
+
+    for item in volumes:
+        t2w_list, mask_list = item[0], item[1]
+        label = item[2] if len(item) > 2 else None
+        if len(t2w_list) != n_echo or len(mask_list) != n_echo:
+            raise ValueError(f"{n_echo} echo times but {len(t2w_list)} volumes / {len(mask_list)} masks")
+        shape3 = tuple(np.shape(t2w_list[0]))
+        n_vox = int(np.prod(shape3))
+        m_dt = _torch_dtype(torch, np.asarray(mask_list[0]).dtype)
+        l_dt = _torch_dtype(torch, np.asarray(label).dtype) if (label is not None and fast) else None
+        key = (n_vox, m_dt, l_dt)
+        ring = slots.setdefault(key, [])
+        s = next((x for x in ring if not x.busy), None)
+        if s is None and len(ring) < depth:
+            s = _Slot(torch, dev, n_echo, n_vox, m_dt, l_dt)
+            ring.append(s)
+        while s is None:                                   # all slots of this shape in flight: drain the oldest
+            yield finish(pending.pop(0))
+            s = next((x for x in ring if not x.busy), None)
+        s.busy, s.shape3 = True, shape3
+        # ---- host: cast into page-locked planes (the .astype(np.float32) of :411), enqueue H2D on the copy stream
+        hp, hm = s.h_planes.numpy(), s.h_masks.numpy()
+        for e in range(n_echo):
+            a = np.asarray(t2w_list[e])
+            if a.shape != shape3 or np.shape(mask_list[e]) != shape3:
+                raise ValueError("all per-TE volumes and masks of one subject must have the same shape")
+            np.copyto(hp[e], a.reshape(-1), casting="unsafe")
+            np.copyto(hm[e], np.asarray(mask_list[e]).reshape(-1), casting="unsafe")
+        s.has_label = l_dt is not None
+        if s.has_label:
+            np.copyto(s.h_label.numpy(), np.asarray(label).reshape(-1), casting="unsafe")
+        with torch.cuda.stream(copy_stream):
+            s.d_planes.copy_(s.h_planes, non_blocking=True)
+            s.d_masks.copy_(s.h_masks, non_blocking=True)
+            if s.has_label:
+                s.d_label.copy_(s.h_label, non_blocking=True)
+            s.copied.record(copy_stream)
+        # ---- device: mask union (+ label), ordered indices, fit into zero-filled dense maps, D2H
+        compute.wait_event(s.copied)
+        cs = compute.cuda_stream
+        planes = (C.c_void_p * n_echo)(*[s.d_masks[e].data_ptr() for e in range(n_echo)])
+        dt_code = _abi.DTYPES[str(m_dt).replace("torch.", "")]
+        l_code = _abi.DTYPES[str(l_dt).replace("torch.", "")] if s.has_label else 0
+        _abi.check(lib, lib.t2fit_mask_union(planes, n_echo, dt_code, s.d_label.data_ptr() if s.has_label else None, l_code,
+                                             n_vox, s.d_mask.data_ptr(), cs), "t2fit_mask_union")
+        n = C.c_int64()
+        _abi.check(lib, lib.t2fit_mask_indices(s.d_mask.data_ptr(), n_vox, 1, s.d_idx.data_ptr(), C.byref(n), cs),
+                   "t2fit_mask_indices")
+        s.n_fit = int(n.value)
+        p, o = _abi.Problem(), _abi.Outputs()
+        keep = _fill_problem(p, fit, fit_params, te, prior, norm, 0, 0.0, "loglinear", solver)
+        p.echoes, p.memory, p.layout, p.ld = s.d_planes.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_PLANES, n_vox
+        p.mask_idx, p.n_vox, p.n_fit = s.d_idx.data_ptr(), n_vox, s.n_fit
+        o.t2, o.k, o.sigma, o.res = (s.d_maps[i].data_ptr() for i in range(4))
+        o.dense, o.zero_fill_mask = 1, s.d_mask.data_ptr()
+        o.status = s.d_status.data_ptr()
+        _run(lib, p, o, cs)
+        del keep
+        with torch.cuda.stream(compute):
+            st = s.d_status[:s.n_fit]
+            s.h_cnt.copy_(torch.stack([(st == 1).sum(), (st == 2).sum(), (st == 3).sum()]), non_blocking=True)
+            s.h_maps.copy_(s.d_maps, non_blocking=True)
+            s.h_mask.copy_(s.d_mask, non_blocking=True)
+            s.done.record(compute)
+        pending.append(s)
+        while len(pending) >= depth:
+            yield finish(pending.pop(0))
+    while pending:
+        yield finish(pending.pop(0))

@@ -55,6 +55,9 @@ extern "C" {
 /* echo layout */
 #define T2FIT_LAYOUT_AOS 0 /* reshaped_t2w: [n_vox, n_echo] row-major float32 (run_t2mapping.py:411) */
 #define T2FIT_LAYOUT_SOA 1 /* packed: [n_echo, ld] float32, column i = i-th fitted voxel            */
+#define T2FIT_LAYOUT_PLANES 2 /* per-TE volumes as they come off disk: [n_echo, ld] float32, ld >= n_vox, plane e =
+                                 the flattened recon volume of echo e (the list `t2w` BEFORE np.stack, :377-385);
+                                 voxel mask_idx[i] of every plane is read -- no interleaving pass is needed */
 
 /* where the data pointers of a call live */
 #define T2FIT_MEM_HOST 0   /* library stages through pinned buffers, copies results back */
@@ -76,9 +79,9 @@ typedef struct t2fit_problem {
     const float *echoes;     /* see layout */
     int32_t layout;          /* T2FIT_LAYOUT_* */
     int32_t memory;          /* T2FIT_MEM_* (applies to echoes, mask_idx and every output pointer) */
-    int64_t ld;              /* SOA only: elements between consecutive echo planes (>= n_fit) */
+    int64_t ld;              /* SOA / PLANES: elements between consecutive echo planes (SOA >= n_fit, PLANES >= n_vox) */
     const int64_t *mask_idx; /* [n_fit] ascending flat voxel indices = mask_indices (:421); NULL = rows 0..n_fit-1.
-                                AOS: row to read (and dense output slot).  SOA: dense output slot only. */
+                                AOS / PLANES: voxel to read (and dense output slot).  SOA: dense output slot only. */
     int64_t n_vox;           /* rows of the AOS array = length of dense maps */
     int64_t n_fit;           /* voxels to fit (M) */
     int32_t n_echo;          /* E, 2..T2FIT_MAX_ECHO */
@@ -152,6 +155,27 @@ int t2fit_status_counts(void *stream, int64_t counts[4]);
  * idx_out (capacity n_vox) and the count to *n_out (host).  Device pointers; synchronises stream. */
 int t2fit_mask_indices(const uint8_t *masks, int64_t n_vox, int32_t n_masks, int64_t *idx_out, int64_t *n_out,
                        void *stream);
+
+/* Mask union straight from the per-TE mask volumes (:383-384) with the optional --in_vitro_fast label masking
+ * (mask[label == 0] = 0, :393-400): mask_out[v] = (sum_p planes[p][v] > 0) && (label == NULL || label[v] != 0).
+ * planes: HOST array of n_planes DEVICE pointers to [n_vox] arrays of element type `dtype`; label: DEVICE pointer
+ * of type `label_dtype` or NULL.  dtype codes: T2FIT_DT_*.  mask_out: device uint8 [n_vox] (0/1). */
+#define T2FIT_DT_U8 0
+#define T2FIT_DT_I16 1
+#define T2FIT_DT_U16 2
+#define T2FIT_DT_I32 3
+#define T2FIT_DT_F32 4
+#define T2FIT_DT_F64 5
+int t2fit_mask_union(const void *const *planes, int32_t n_planes, int32_t dtype, const void *label, int32_t label_dtype,
+                     int64_t n_vox, uint8_t *mask_out, void *stream);
+
+/* Phantom ROI statistics (save_phantom_csv, utils/t2map_utils.py:30-59): for every label value 1..n_roi the
+ * NaN-skipping mean and population standard deviation (np.nanmean / np.nanstd) of each of n_maps float32 maps
+ * over the voxels with label == value.  maps: HOST array of n_maps DEVICE pointers to [n_vox] float32; label:
+ * DEVICE int32 [n_vox].  Outputs are HOST arrays [n_maps, n_roi] (mean, std: float64; count: int64 non-NaN voxels);
+ * an empty ROI gives NaN as numpy does.  Synchronises `stream`. */
+int t2fit_roi_stats(const float *const *maps, int32_t n_maps, const int32_t *label, int64_t n_vox, int32_t n_roi,
+                    double *mean_out, double *std_out, int64_t *count_out, void *stream);
 
 /* pack_masked_soa: gather rows mask_idx[i] of the AOS array into the echo-contiguous SOA buffer
  * soa[e*ld + i] (device pointers).  The host-memory path of t2fit_run does this on the CPU side
