@@ -88,6 +88,22 @@ def _host_array(n, dtype, zero=False):
         return np.zeros(n, dtype) if zero else np.empty(n, dtype)
 
 
+def _host_block(m, fields):
+    """All result arrays of one call as views into ONE page-locked block (one pinned allocation / DMA mapping instead
+    of one per field).  ``fields``: list of (name, dtype).  Falls back to plain numpy without torch."""
+    offs, total = {}, 0
+    for name, dt in fields:
+        total = (total + 255) // 256 * 256                       # 256-byte aligned views (vector stores, cache lines)
+        offs[name] = total
+        total += m * np.dtype(dt).itemsize
+    try:
+        import torch
+        base = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True).numpy()
+    except Exception:
+        base = np.empty(max(total, 1), np.uint8)
+    return {name: base[offs[name]:offs[name] + m * np.dtype(dt).itemsize].view(dt) for name, dt in fields}
+
+
 @dataclass
 class FitResult:
     """Everything ``pool.map(fit_voxel)`` + ``compute_residuals`` produce, for all masked voxels.
@@ -104,7 +120,7 @@ class FitResult:
     """
     t2: object
     k: object
-    sigma: object
+    _sigma: object
     res: object
     fun: object
     nit: object
@@ -115,6 +131,13 @@ class FitResult:
     trace_f: object = None       # float32[M, trace_cap]  f_val per L-BFGS-B iteration
     trace_step: object = None    # float32[M, trace_cap]  step_size (NaN for the first iteration)
     trace_len: object = None     # int32[M]               entries used = min(nit, trace_cap)
+
+    @property
+    def sigma(self):
+        """sigma_map values; all zeros for the 2-parameter fit (run_t2mapping.py:417,457-458), created on first use."""
+        if self._sigma is None:
+            self._sigma = np.zeros(self.t2.shape[0], np.float32)
+        return self._sigma
 
     @property
     def iteration_infos(self):
@@ -282,11 +305,11 @@ def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=
         n_vox, n_echo = y.shape
         idx = None if mask_indices is None else np.ascontiguousarray(mask_indices, dtype=np.int64)
         m = n_vox if idx is None else idx.size
-        out = {"t2": _host_array(m, np.float32), "k": _host_array(m, np.float32), "res": _host_array(m, np.float32),
-               "sigma": _host_array(m, np.float32) if fit != "gaussian" else np.zeros(m, np.float32),
-               "fun": _host_array(m, np.float32) if "fun" in want else None,
-               "nit": _host_array(m, np.int32) if "nit" in want else None,
-               "status": _host_array(m, np.uint8) if "status" in want else None}
+        fields = [("t2", np.float32), ("k", np.float32), ("res", np.float32)]
+        fields += [("sigma", np.float32)] if fit != "gaussian" else []                  # 2-parameter fit: zeros, made on first access
+        fields += [(n, dt) for n, dt in (("fun", np.float32), ("nit", np.int32), ("status", np.uint8)) if n in want]
+        out = {"sigma": None, "fun": None, "nit": None, "status": None}
+        out.update(_host_block(m, fields))
         if tracing:
             out["trace_f"] = np.full((m, trace_cap), np.nan, np.float32)
             out["trace_step"] = np.full((m, trace_cap), np.nan, np.float32)

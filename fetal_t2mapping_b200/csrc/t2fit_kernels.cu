@@ -616,7 +616,18 @@ class Workers {
 };
 
 constexpr int kSlots = 3;
-constexpr int64_t kChunk = 1 << 18;  // voxels per staging chunk
+// voxels per staging chunk (T2FIT_HOST_CHUNK overrides, for tuning)
+// Sized by BYTES, not voxels: measured on the B200 boxes (profiles/r01_notes.md), per-chunk transfers of ~2.6 MB pipeline
+// cleanly (c2: 1.2-1.4 ms per volume) while >= 3.9 MB per chunk stalls the PCIe side 3x; ~2.6 MB of input per chunk.
+constexpr int64_t kChunkInBytes = 2621440;
+constexpr int64_t kChunkMax = 1 << 18;
+static const int64_t kChunkEnv = [] { const char* e = getenv("T2FIT_HOST_CHUNK"); const long long v = e ? atoll(e) : 0; return v >= 1024 ? (int64_t)v : (int64_t)0; }();
+inline int64_t chunk_for(int n_echo) {
+    if (kChunkEnv) return kChunkEnv;
+    const int64_t n = (kChunkInBytes / (4 * (int64_t)n_echo)) & ~(int64_t)4095;
+    return std::min(kChunkMax, std::max<int64_t>(4096, n));
+}
+constexpr size_t kOutPerVoxel = 5 * sizeof(float) + sizeof(int32_t) + 1;
 
 struct Slot {
     float* h_in = nullptr;     // pinned, E_cap * kChunk floats: gathered rows [n, E] (AoS) or planes [E, n] (SoA)
@@ -630,7 +641,6 @@ struct Slot {
     int64_t first = -1, count = 0;  // chunk in flight
     bool direct = false;            // results were copied straight into the caller's (pinned) arrays
 };
-constexpr size_t kOutBytes = (size_t)kChunk * (5 * sizeof(float) + sizeof(int32_t) + 1);
 
 constexpr int kQueues = 16;
 
@@ -641,7 +651,8 @@ struct Context {
     unsigned long long* d_counts = nullptr;  // [4]
     unsigned long long* h_counts = nullptr;  // pinned [4]
     Slot slots[kSlots];
-    int e_cap = 0;
+    int e_cap = 0;                           // slots hold chunk_for(E) voxels of E echoes for every E <= e_cap seen so far
+    size_t in_cap = 0, out_cap = 0;
     Workers* workers = nullptr;
     // scratch of t2fit_mask_indices
     int* d_tile_counts = nullptr;
@@ -668,20 +679,24 @@ void free_slots(Context* c) {
         s.h_in = s.d_in = nullptr;
         s.h_out = s.d_out = nullptr;
     }
-    c->e_cap = 0;
+    c->e_cap = 0; c->in_cap = 0; c->out_cap = 0;
 }
 
 int ensure_slots(Context* c, int n_echo) {
-    if (c->e_cap >= n_echo) return T2FIT_OK;
+    const size_t need_in = sizeof(float) * (size_t)n_echo * (size_t)chunk_for(n_echo);
+    const size_t need_out = kOutPerVoxel * (size_t)chunk_for(n_echo);
+    if (c->in_cap >= need_in && c->out_cap >= need_out) return T2FIT_OK;
+    const size_t in_b = std::max(need_in, c->in_cap), out_b = std::max(need_out, c->out_cap);
     free_slots(c);
     for (auto& s : c->slots) {
-        CU_TRY(cudaMallocHost(&s.h_in, sizeof(float) * n_echo * kChunk));
-        CU_TRY(cudaMalloc(&s.d_in, sizeof(float) * n_echo * kChunk));
-        CU_TRY(cudaMallocHost(&s.h_out, kOutBytes));
-        CU_TRY(cudaMalloc(&s.d_out, kOutBytes));
+        CU_TRY(cudaMallocHost(&s.h_in, in_b));
+        CU_TRY(cudaMalloc(&s.d_in, in_b));
+        CU_TRY(cudaMallocHost(&s.h_out, out_b));
+        CU_TRY(cudaMalloc(&s.d_out, out_b));
         if (!s.stream) CU_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         if (!s.done) CU_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
+    c->in_cap = in_b; c->out_cap = out_b;
     c->e_cap = n_echo;
     return T2FIT_OK;
 }
@@ -761,7 +776,7 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
         for (auto& t : tsc) { if (t.f) cudaFree(t.f); if (t.s) cudaFree(t.s); if (t.n) cudaFree(t.n); t = TraceScratch{}; }
     };
     if (tracing) {
-        const int64_t nmax = std::min<int64_t>(kChunk, p.n_fit);
+        const int64_t nmax = std::min<int64_t>(chunk_for(p.n_echo), p.n_fit);
         for (auto& t : tsc) {
             if (cudaMalloc(&t.f, sizeof(float) * nmax * o.trace_cap) != cudaSuccess ||
                 cudaMalloc(&t.s, sizeof(float) * nmax * o.trace_cap) != cudaSuccess ||
@@ -781,12 +796,32 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
         CU_TRY(cudaStreamSynchronize(c->slots[0].stream));
         c->counts_dirty = false;
     }
+    const int64_t kChunk = chunk_for(E);
     const int64_t n_chunks = (M + kChunk - 1) / kChunk;
     const bool mono = p.model == T2FIT_MODEL_GAUSSIAN;
     std::atomic<bool> bad_index{false};
     // compact results can go straight into the caller's arrays if every one of them is page-locked
-    const bool direct = !o.dense && is_pinned(o.t2) && is_pinned(o.k) && is_pinned(o.res) && is_pinned(o.fun) &&
-                        is_pinned(o.nit) && is_pinned(o.status) && (mono || is_pinned(o.sigma));
+    // How compact results reach the caller's arrays (T2FIT_HOST_OUT overrides, for measurements):
+    //   zerocopy  every result array is page-locked: the kernel stores straight into host memory through its device
+    //             mapping (coalesced 128-byte writes over PCIe while it runs; no D2H copy, no unpack)      [default if pinned]
+    //   direct    page-locked arrays, per-chunk cudaMemcpyAsync per field (measured erratic: 2-4.5 ms per c2 volume)
+    //   staged    one D2H per chunk into pinned staging + threaded unpack / scatter                      [default otherwise]
+    static const int out_mode_env = [] {
+        const char* e = getenv("T2FIT_HOST_OUT");
+        return !e ? 0 : !strcmp(e, "zerocopy") ? 0 : !strcmp(e, "direct") ? 1 : 2;
+    }();
+    const bool all_pinned = !o.dense && is_pinned(o.t2) && is_pinned(o.k) && is_pinned(o.res) && is_pinned(o.fun) &&
+                            is_pinned(o.nit) && is_pinned(o.status) && (mono || is_pinned(o.sigma));
+    bool zerocopy = all_pinned && out_mode_env == 0;
+    struct DevView { float *t2 = nullptr, *k = nullptr, *sigma = nullptr, *res = nullptr, *fun = nullptr; int32_t* nit = nullptr; uint8_t* status = nullptr; } dv;
+    if (zerocopy) {
+        auto map = [&](void* h, void** d) { *d = nullptr; return !h || cudaHostGetDevicePointer(d, h, 0) == cudaSuccess; };
+        zerocopy = map(o.t2, (void**)&dv.t2) && map(o.k, (void**)&dv.k) && map(mono ? nullptr : o.sigma, (void**)&dv.sigma) &&
+                   map(o.res, (void**)&dv.res) && map(o.fun, (void**)&dv.fun) && map(o.nit, (void**)&dv.nit) &&
+                   map(o.status, (void**)&dv.status);
+        if (!zerocopy) cudaGetLastError();
+    }
+    const bool direct = zerocopy || (all_pinned && out_mode_env == 1);
 
     auto unpack = [&](Slot& s) {
         if (s.first < 0) return;
@@ -874,6 +909,12 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
         io.t2 = df; io.k = df + n; io.sigma = df + 2 * n; io.res = df + 3 * n; io.fun = df + 4 * n;
         io.nit = reinterpret_cast<int32_t*>(s.d_out + (size_t)5 * n * sizeof(float));
         io.status = s.d_out + (size_t)5 * n * sizeof(float) + (size_t)n * sizeof(int32_t);
+        if (zerocopy) {                               // results go straight to the caller's page-locked arrays
+            io.t2 = dv.t2 ? dv.t2 + first : nullptr; io.k = dv.k ? dv.k + first : nullptr;
+            io.sigma = dv.sigma ? dv.sigma + first : nullptr; io.res = dv.res ? dv.res + first : nullptr;
+            io.fun = dv.fun ? dv.fun + first : nullptr; io.nit = dv.nit ? dv.nit + first : nullptr;
+            io.status = dv.status ? dv.status + first : nullptr;
+        }
         io.counts = c->d_counts; io.dense = 0; io.vec_ok = 1;
         io.layout = p.layout == T2FIT_LAYOUT_AOS ? T2FIT_LAYOUT_AOS : T2FIT_LAYOUT_SOA;     // staged chunks are packed
         if (tracing) {
@@ -889,7 +930,9 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
             if (o.trace_len) CU_TRY(cudaMemcpyAsync(o.trace_len + first, io.trace_len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s.stream));
         }
         s.direct = direct;
-        if (direct) {
+        if (zerocopy) {
+            // nothing to copy
+        } else if (direct) {
             auto d2h = [&](void* dst, const void* src, size_t bytes) {
                 return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s.stream) : cudaSuccess;
             };
@@ -901,7 +944,7 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
             CU_TRY(d2h(o.nit ? o.nit + first : nullptr, io.nit, sizeof(int32_t) * n));
             CU_TRY(d2h(o.status ? o.status + first : nullptr, io.status, n));
         } else {
-            CU_TRY(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * (5 * sizeof(float) + sizeof(int32_t) + 1),
+            CU_TRY(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n * kOutPerVoxel,
                                    cudaMemcpyDeviceToHost, s.stream));
         }
         CU_TRY(cudaEventRecord(s.done, s.stream));
@@ -927,7 +970,7 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
     o.status_count[0] = M - bad;
     if (profile)
         fprintf(stderr, "[t2fit host] M=%lld chunks=%lld direct=%d total %.3f ms: pack %.3f wait %.3f unpack %.3f\n", (long long)M,
-                (long long)n_chunks, (int)direct, now_ms() - t0, t_pack, t_wait, t_unpack);
+                (long long)n_chunks, zerocopy ? 2 : (int)direct, now_ms() - t0, t_pack, t_wait, t_unpack);
     return T2FIT_OK;
 }
 
