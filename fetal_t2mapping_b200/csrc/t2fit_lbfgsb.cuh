@@ -196,6 +196,7 @@ struct Solver {
     double ws[kM][N], wy[kM][N];
     double sy[kM][kM], ss[kM][kM], wt[kM][kM];
     double wn[M2][M2], wn1[M2][M2];
+    double rd[kM], rsd[kM];     // 1 / D_kk and 1 / sqrt(D_kk), D = diag(S'Y): the divisions of bmv / formt as multiplications
     double pc[M2], cc[M2];      // p and c of the Cauchy search (c = W'(xcp - x) feeds the reduced gradient)
     double theta;
     int col, head, itail, iupdat;
@@ -274,17 +275,17 @@ struct Solver {
         p[col] = v[col];
         T2_ROLLED for (int i = 1; i < col; ++i) {
             double sum = 0.0;
-            T2_ROLLED for (int k = 0; k < i; ++k) sum += ddiv(sy[i][k] * v[k], sy[k][k]);
+            T2_ROLLED for (int k = 0; k < i; ++k) sum += sy[i][k] * v[k] * rd[k];
             p[col + i] = v[col + i] + sum;
         }
         if (!dtrsl_t<kM>(wt, col, p + col)) return false;
-        T2_ROLLED for (int i = 0; i < col; ++i) p[i] = ddiv(v[i], dsqrt(sy[i][i]));
+        T2_ROLLED for (int i = 0; i < col; ++i) p[i] = v[i] * rsd[i];
         if (!dtrsl_n<kM>(wt, col, p + col)) return false;
-        T2_ROLLED for (int i = 0; i < col; ++i) p[i] = ddiv(-p[i], dsqrt(sy[i][i]));
+        T2_ROLLED for (int i = 0; i < col; ++i) p[i] = -p[i] * rsd[i];
         T2_ROLLED for (int i = 0; i < col; ++i) {
             double sum = 0.0;
-            T2_ROLLED for (int k = i + 1; k < col; ++k) sum += ddiv(sy[k][i] * p[col + k], sy[i][i]);
-            p[i] += sum;
+            T2_ROLLED for (int k = i + 1; k < col; ++k) sum += sy[k][i] * p[col + k];
+            p[i] += sum * rd[i];
         }
         return true;
     }
@@ -646,13 +647,14 @@ struct Solver {
         }
         ss[col - 1][col - 1] = (stp == 1.0) ? dtd : stp * stp * dtd;
         sy[col - 1][col - 1] = dr;
+        T2_ROLLED for (int k = 0; k < col; ++k) { rd[k] = ddiv(1.0, sy[k][k]); rsd[k] = ddiv(1.0, dsqrt(sy[k][k])); }
         // T = theta S'S + L D^-1 L' (upper triangle), then its Cholesky factor
         T2_ROLLED for (int j = 0; j < col; ++j) wt[0][j] = theta * ss[0][j];
         T2_ROLLED for (int i = 1; i < col; ++i)
             T2_ROLLED for (int j = i; j < col; ++j) {
                 const int k1 = (i < j ? i : j);
                 double ddum = 0.0;
-                T2_ROLLED for (int k = 0; k < k1; ++k) ddum += ddiv(sy[i][k] * sy[j][k], sy[k][k]);
+                T2_ROLLED for (int k = 0; k < k1; ++k) ddum += sy[i][k] * sy[j][k] * rd[k];
                 wt[i][j] = ddum + theta * ss[i][j];
             }
         return dpofa<kM>(wt, 0, col);
