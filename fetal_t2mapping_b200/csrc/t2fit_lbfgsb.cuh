@@ -33,9 +33,11 @@
 #if T2_DEVICE_BUILD
 #define T2_NI __device__ __noinline__
 #define T2_ROLLED _Pragma("unroll 1")      // keep the optimiser core compact: it must stay resident in the instruction cache
+#define T2_INNER _Pragma("unroll 4")       // innermost dot products: a few independent loads in flight (the kernel is latency-bound)
 #else
 #define T2_NI inline
 #define T2_ROLLED
+#define T2_INNER
 #endif
 
 namespace t2fit {
@@ -236,7 +238,7 @@ struct Solver {
             double s = 0.0;
             T2_ROLLED for (int k = 0; k < j; ++k) {
                 double tt = a[o + k][o + j];
-                T2_ROLLED for (int q = 0; q < k; ++q) tt -= a[o + q][o + k] * a[o + q][o + j];
+                T2_INNER for (int q = 0; q < k; ++q) tt -= a[o + q][o + k] * a[o + q][o + j];
                 tt = ddiv(tt, a[o + k][o + k]);
                 a[o + k][o + j] = tt;
                 s += tt * tt;
@@ -253,7 +255,7 @@ struct Solver {
         T2_ROLLED for (int j = 0; j < nn; ++j) if (a[j][j] == 0.0) return false;
         T2_ROLLED for (int j = 0; j < nn; ++j) {
             double s = b[j];
-            T2_ROLLED for (int q = 0; q < j; ++q) s -= a[q][j] * b[q];
+            T2_INNER for (int q = 0; q < j; ++q) s -= a[q][j] * b[q];
             b[j] = ddiv(s, a[j][j]);
         }
         return true;
@@ -263,7 +265,7 @@ struct Solver {
         T2_ROLLED for (int j = 0; j < nn; ++j) if (a[j][j] == 0.0) return false;
         T2_ROLLED for (int j = nn - 1; j >= 0; --j) {
             double s = b[j];
-            T2_ROLLED for (int q = j + 1; q < nn; ++q) s -= a[j][q] * b[q];
+            T2_INNER for (int q = j + 1; q < nn; ++q) s -= a[j][q] * b[q];
             b[j] = ddiv(s, a[j][j]);
         }
         return true;
@@ -275,7 +277,7 @@ struct Solver {
         p[col] = v[col];
         T2_ROLLED for (int i = 1; i < col; ++i) {
             double sum = 0.0;
-            T2_ROLLED for (int k = 0; k < i; ++k) sum += sy[i][k] * v[k] * rd[k];
+            T2_INNER for (int k = 0; k < i; ++k) sum += sy[i][k] * v[k] * rd[k];
             p[col + i] = v[col + i] + sum;
         }
         if (!dtrsl_t<kM>(wt, col, p + col)) return false;
@@ -284,7 +286,7 @@ struct Solver {
         T2_ROLLED for (int i = 0; i < col; ++i) p[i] = -p[i] * rsd[i];
         T2_ROLLED for (int i = 0; i < col; ++i) {
             double sum = 0.0;
-            T2_ROLLED for (int k = i + 1; k < col; ++k) sum += sy[k][i] * p[col + k];
+            T2_INNER for (int k = i + 1; k < col; ++k) sum += sy[k][i] * p[col + k];
             p[i] += sum * rd[i];
         }
         return true;
@@ -532,14 +534,14 @@ struct Solver {
         T2_ROLLED for (int js = col; js < col2; ++js) {
             T2_ROLLED for (int j = 0; j < col; ++j) {                   // solve L x = wn(1:col, js), L' stored in the upper triangle
                 double s = wn[j][js];
-                T2_ROLLED for (int q = 0; q < j; ++q) s -= wn[q][j] * wn[q][js];
+                T2_INNER for (int q = 0; q < j; ++q) s -= wn[q][j] * wn[q][js];
                 wn[j][js] = ddiv(s, wn[j][j]);
             }
         }
         T2_ROLLED for (int is = col; is < col2; ++is)
             T2_ROLLED for (int js = is; js < col2; ++js) {
                 double dot = 0.0;
-                T2_ROLLED for (int q = 0; q < col; ++q) dot += wn[q][is] * wn[q][js];
+                T2_INNER for (int q = 0; q < col; ++q) dot += wn[q][is] * wn[q][js];
                 wn[is][js] += dot;
             }
         return dpofa<M2>(wn, col, col);
@@ -654,7 +656,7 @@ struct Solver {
             T2_ROLLED for (int j = i; j < col; ++j) {
                 const int k1 = (i < j ? i : j);
                 double ddum = 0.0;
-                T2_ROLLED for (int k = 0; k < k1; ++k) ddum += sy[i][k] * sy[j][k] * rd[k];
+                T2_INNER for (int k = 0; k < k1; ++k) ddum += sy[i][k] * sy[j][k] * rd[k];
                 wt[i][j] = ddum + theta * ss[i][j];
             }
         return dpofa<kM>(wt, 0, col);
