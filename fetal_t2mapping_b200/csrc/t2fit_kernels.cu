@@ -130,7 +130,7 @@ template <bool SIGMA_ALL>
 __global__ void __launch_bounds__(256) zero_fill_kernel(const __grid_constant__ FillArgs a) {
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int lane = threadIdx.x & 31;
-    const int64_t gw = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * 256) >> 5;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t full_chunks = a.n_vox / kFillChunk;
     const bool fast = a.vec && a.t2 && a.k && a.res && a.sigma;
     if (fast) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) zero_fill_kernel(const __grid_constant__ 
     }
     // per-voxel path: everything if not `fast`, else only the ragged tail after the last full chunk
     const int64_t v0 = fast ? full_chunks * kFillChunk : 0;
-    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x, nt = (int64_t)gridDim.x * 256;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
 #pragma unroll 1
     for (int64_t v = v0 + t; v < a.n_vox; v += nt) fill_voxel<SIGMA_ALL>(a, v, a.mask[v] == 0);
 }
@@ -739,11 +739,12 @@ int launch_zero_fill(Context* c, const FillArgs& fa, bool sigma_all, cudaStream_
     CU_TRY(cudaEventRecord(c->ev_fork, st));
     CU_TRY(cudaStreamWaitEvent(c->fill_stream, c->ev_fork, 0));
     const int64_t chunks = (fa.n_vox + kFillChunk - 1) / kFillChunk;
-    const int64_t want = (chunks + 7) / 8;                                  // 8 warps per block
+    static const int threads = [] { const char* e = getenv("T2FIT_FILL_THREADS"); const int v = e ? atoi(e) : 256; return (v >= 32 && v <= 256 && v % 32 == 0) ? v : 256; }();
+    const int64_t want = (chunks + threads / 32 - 1) / (threads / 32);      // one chunk per warp per round
     static const int per_sm = [] { const char* e = getenv("T2FIT_FILL_BLOCKS_PER_SM"); return e ? std::max(1, atoi(e)) : 1; }();
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)per_sm * c->prop.multiProcessorCount));
-    if (sigma_all) zero_fill_kernel<true><<<grid, 256, 0, c->fill_stream>>>(fa);
-    else zero_fill_kernel<false><<<grid, 256, 0, c->fill_stream>>>(fa);
+    if (sigma_all) zero_fill_kernel<true><<<grid, threads, 0, c->fill_stream>>>(fa);
+    else zero_fill_kernel<false><<<grid, threads, 0, c->fill_stream>>>(fa);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(c->ev_join, c->fill_stream));
     *forked = true;
