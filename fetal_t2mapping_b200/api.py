@@ -42,6 +42,11 @@ def init(device: int | None = None):
         device = int(os.environ.get("LOCAL_RANK", "0"))
     if _state["device"] == device:
         return lib
+    # one process per GPU: share the host cores between the ranks of this node for the staging threads of the host path
+    lws = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    if lws > 1 and "T2FIT_HOST_THREADS" not in os.environ:
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        os.environ["T2FIT_HOST_THREADS"] = str(max(2, min(16, ncpu // lws)))
     _abi.check(lib, lib.t2fit_init(int(device)), "t2fit_init")
     _state["device"] = int(device)
     return lib
