@@ -53,8 +53,8 @@ class _Slot:
         self.d_mask = torch.empty(n_vox, dtype=torch.uint8, device=dev)
         self.d_idx = torch.empty(n_vox, dtype=torch.int64, device=dev)
         self.d_maps = torch.empty((4, n_vox), dtype=torch.float32, device=dev)
-        self.h_maps = torch.empty((4, n_vox), dtype=torch.float32, pin_memory=True)
-        self.h_mask = torch.empty(n_vox, dtype=torch.uint8, pin_memory=True)
+        self.h_maps = None         # page-locked result block of the volume in flight; handed to the caller, not reused
+        self.h_mask = None
         self.d_status = torch.empty(n_vox, dtype=torch.uint8, device=dev)
         self.h_cnt = torch.zeros(3, dtype=torch.int64, pin_memory=True)
         self.copied = torch.cuda.Event()
@@ -63,6 +63,17 @@ class _Slot:
         self.has_label = False
         self.n_fit = 0
         self.busy = False
+
+
+def _stage(torch, dst, a):
+    """Cast / copy one volume into its page-locked plane (torch's copy is multi-threaded for large arrays)."""
+    a = np.ascontiguousarray(a).reshape(-1)
+    if a.dtype == np.bool_:
+        a = a.view(np.uint8)
+    try:
+        dst.copy_(torch.from_numpy(a))
+    except (TypeError, RuntimeError):                      # dtypes torch cannot wrap (uint16, ...)
+        np.copyto(dst.numpy(), a, casting="unsafe")
 
 
 def _torch_dtype(torch, np_dtype):
@@ -101,9 +112,10 @@ def t2map_series(volumes, TEeffs, fit, fit_params, prior=True, norm=False, *, fa
         nonfinite, gave_up, bad_bounds = (int(v) for v in s.h_cnt)
         if bad_bounds > 0:
             raise ValueError(BOUNDS_ERROR)
-        maps = s.h_maps.numpy()
-        return VolumeMaps(*(maps[i].reshape(s.shape3).copy() for i in range(4)),
-                          mask=s.h_mask.numpy().reshape(s.shape3).astype(bool), n_fit=s.n_fit, failed=nonfinite + gave_up)
+        maps, mk = s.h_maps.numpy(), s.h_mask.numpy()          # views of the page-locked blocks: no copy; the blocks go
+        s.h_maps = s.h_mask = None                               # back to torch's pinned pool when the caller drops them
+        return VolumeMaps(*(maps[i].reshape(s.shape3) for i in range(4)),
+                          mask=mk.reshape(s.shape3).view(np.bool_), n_fit=s.n_fit, failed=nonfinite + gave_up)
 
     for item in volumes:
         t2w_list, mask_list = item[0], item[1]
@@ -125,16 +137,17 @@ def t2map_series(volumes, TEeffs, fit, fit_params, prior=True, norm=False, *, fa
             s = next((x for x in ring if not x.busy), None)
         s.busy, s.shape3 = True, shape3
         # ---- host: cast into page-locked planes (the .astype(np.float32) of :411), enqueue H2D on the copy stream
-        hp, hm = s.h_planes.numpy(), s.h_masks.numpy()
         for e in range(n_echo):
             a = np.asarray(t2w_list[e])
             if a.shape != shape3 or np.shape(mask_list[e]) != shape3:
                 raise ValueError("all per-TE volumes and masks of one subject must have the same shape")
-            np.copyto(hp[e], a.reshape(-1), casting="unsafe")
-            np.copyto(hm[e], np.asarray(mask_list[e]).reshape(-1), casting="unsafe")
+            _stage(torch, s.h_planes[e], a)
+            _stage(torch, s.h_masks[e], np.asarray(mask_list[e]))
         s.has_label = l_dt is not None
         if s.has_label:
-            np.copyto(s.h_label.numpy(), np.asarray(label).reshape(-1), casting="unsafe")
+            _stage(torch, s.h_label, np.asarray(label))
+        s.h_maps = torch.empty((4, n_vox), dtype=torch.float32, pin_memory=True)
+        s.h_mask = torch.empty(n_vox, dtype=torch.uint8, pin_memory=True)
         with torch.cuda.stream(copy_stream):
             s.d_planes.copy_(s.h_planes, non_blocking=True)
             s.d_masks.copy_(s.h_masks, non_blocking=True)
