@@ -79,20 +79,6 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
-def _host_array(n, dtype, zero=False):
-    """Result array in page-locked host memory when torch is importable (the library then copies D2H
-    straight into it, no staging copy); plain numpy otherwise."""
-    try:
-        import torch
-        t = torch.empty(n, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
-        a = t.numpy()
-        if zero:
-            a[:] = 0
-        return a
-    except Exception:
-        return np.zeros(n, dtype) if zero else np.empty(n, dtype)
-
-
 def _host_block(m, fields):
     """All result arrays of one call as views into ONE page-locked block (one pinned allocation / DMA mapping instead
     of one per field).  ``fields``: list of (name, dtype).  Falls back to plain numpy without torch."""

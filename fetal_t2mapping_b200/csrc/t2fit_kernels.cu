@@ -1263,12 +1263,14 @@ int t2fit_residuals(const t2fit_problem* p, const float* k_map, const float* t2_
     FitConsts fc;
     memset(&fc, 0, sizeof(fc));
     std::string err;
-    int rc = make_consts(*p, fc, err);
+    t2fit_problem q = *p;                     // 'rician' maps are evaluated with the noise-floor model, as the reference
+    if (q.model == T2FIT_MODEL_RICIAN) q.model = T2FIT_MODEL_GAUSSIAN_RICIAN;   // does (utils/t2map_utils.py:68-71)
+    int rc = make_consts(q, fc, err);
     if (rc) return fail(rc, err);
     if (p->n_fit == 0) return T2FIT_OK;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
-    residual_kernel<<<(unsigned)((p->n_fit + 255) / 256), 256, 0, st>>>(fc, p->echoes, p->mask_idx, p->n_fit, p->model, k_map,
+    residual_kernel<<<(unsigned)((p->n_fit + 255) / 256), 256, 0, st>>>(fc, p->echoes, p->mask_idx, p->n_fit, q.model, k_map,
                                                                        t2_map, sigma_map, res_map);
     CU_TRY(cudaGetLastError());
     return T2FIT_OK;

@@ -377,3 +377,25 @@ def test_out_of_range_mask_indices_raise(gpu_lib):
         gpu_lib.fit_voxels_batch(y, np.array([-1, 3]), [114.0, 202.0, 299.0], "gaussian", fp)
     r = gpu_lib.fit_voxels_batch(y * 700, np.array([0, 3, 9]), [114.0, 202.0, 299.0], "gaussian", fp)   # still usable
     assert r.t2.shape == (3,)
+
+
+@pytest.mark.parametrize("fit", ["gaussian", "gaussian_rician", "rician"])
+def test_compute_residuals_mirror(gpu_lib, fit):
+    """compute_residuals(reshaped_t2w, TEeffs, fit, norm, k_map, t2_map, sigma_map, res_map, mask_indices, mask) as the
+    reference calls it (run_t2mapping.py:461), against the oracle's restatement of utils/t2map_utils.py:62-89; 'rician'
+    maps are evaluated with the noise-floor model, as the reference does."""
+    from oracle import fit_oracle as fo
+    rng = np.random.default_rng(1)
+    shape = (6, 7, 8)
+    n = int(np.prod(shape))
+    te = np.array([114.0, 150.0, 202.0, 299.0])
+    y = rng.uniform(50, 900, (n, 4)).astype(np.float32)
+    mask = rng.random(shape) < 0.4
+    idx = np.flatnonzero(mask.reshape(-1))
+    k = np.zeros(n, np.float32); t2v = np.zeros(n, np.float32); sg = np.zeros(n, np.float32)
+    k[idx] = rng.uniform(300, 900, idx.size); t2v[idx] = rng.uniform(40, 400, idx.size); sg[idx] = rng.uniform(2, 60, idx.size)
+    for norm in (False, True):
+        got = gpu_lib.compute_residuals(y, te, fit, norm, k, t2v, sg, np.zeros(n, np.float32), idx, mask)
+        want = fo.residual_map(y, te, fit, norm, k, t2v, sg, np.zeros(n, np.float32), idx, mask)
+        assert got.shape == shape and (got[~mask] == 0).all()
+        assert np.allclose(got, want, rtol=2e-4, atol=2e-3)
