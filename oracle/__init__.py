@@ -19,11 +19,11 @@ Contents
 ``ref_loader.py``   imports the UNMODIFIED reference from ``/root/reference``
                     (only exists in the build container) to pin the oracle and
                     to generate ``tests/golden/*.npz``.
-``lbfgsb_c/``       plain-C restatement of the L-BFGS-B 3.0 algorithm as driven
-                    by ``fit_voxel`` (fast oracle for full-size checks).
 
 Pinning status: the reference ships no tests or golden vectors for this path
 (SURVEY.md §4), so the oracle is pinned against outputs of the reference itself
 run in the build container (``tests/golden/make_golden.py`` → committed
-fixtures; ``tests/test_oracle_pinned.py``).
+fixtures; ``tests/test_oracle_pinned.py``), including a second run of the
+unmodified reference under a one-ulp jitter of ``np.exp`` that measures how well the
+reference reproduces itself (``tests/golden/make_jitter.py``).
 """

@@ -17,8 +17,11 @@ hands the objective to ``scipy.optimize.minimize(method="L-BFGS-B", jac=False)``
 2-point finite-difference gradient (``scipy/optimize/_lbfgsb_py.py``,
 ``_numdiff.py``).  Reference pin: scipy 1.11.3 / numpy 1.26.0
 (requirements_frozen.txt:103,144); this image: scipy 1.18.1 / numpy 2.3.  The
-oracle calls that dependency with exactly the reference's arguments; a plain-C
-restatement of the published algorithm lives in ``oracle/lbfgsb_c``.
+oracle calls that dependency with exactly the reference's arguments, so it IS the
+reference's arithmetic on this host.  (The product's FP64 solver restates the
+published L-BFGS-B algorithm in ``fetal_t2mapping_b200/csrc/t2fit_lbfgsb.cuh``; it is
+checked against this oracle and against scipy itself in ``tests/``, never the other
+way round.)
 
 Oracle modes:
   ``verbatim``  the reference's own options (ftol/gtol/maxls from the preset).
