@@ -46,6 +46,22 @@ def test_series_loader_matches_single_volume_path(gpu_lib, fit):
             assert (a[~union] == 0).all()
 
 
+def test_series_loader_default_solver_is_the_faithful_one_for_three_parameter_fits(gpu_lib):
+    """gaussian_rician / rician through the loader (PLANES layout) with the default solver = L-BFGS-B: identical to the
+    one-volume path on the stacked arrays (AoS layout), both fits."""
+    te = np.array([114.0, 150.0, 202.0, 299.0])
+    vols = [_volume((10, 9, 8), te, 70 + i) for i in range(2)]
+    vols = [([np.abs(a) + 1.0 for a in v[0]], v[1], v[2]) for v in vols]      # magnitude data: the Rician NLL takes log(signal)
+    for fit in ("gaussian_rician", "rician"):
+        _, fp = gpu_lib.preset(fit, True)
+        out = list(gpu_lib.t2map_series(((v[0], v[1]) for v in vols), te, fit, fp, prior=True))
+        for (t2w, masks, _), r in zip(vols, out):
+            ref = gpu_lib.t2map_volume(np.stack(t2w, axis=-1), np.stack(masks, axis=-1), te, fit, fp, prior=True)
+            for a, b in zip((r.t2, r.k, r.sigma, r.res), ref):
+                assert np.array_equal(a, b)
+            assert (r.sigma[r.mask] >= 2.0).all()          # the 3-parameter fits fill the sigma map
+
+
 def test_series_loader_in_vitro_fast_label_masking(gpu_lib):
     te = np.array([114.0, 202.0, 299.0])
     _, fp = gpu_lib.preset("gaussian", True)
