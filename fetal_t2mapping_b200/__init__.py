@@ -8,7 +8,7 @@ reference.  There is no CPU implementation of the fit in this package.
 """
 from .presets import preset, set_fit_params                                           # noqa: F401
 from .api import (FitResult, compute_residuals, device_info, fit_voxels_batch, init,   # noqa: F401
-                  mask_indices_device, shutdown, t2map_volume, work_model)
+                  mask_indices_device, pinned_array, shutdown, t2map_volume, work_model)
 
 from .roi import phantom_roi_table, roi_stats, save_phantom_csv, set_phantom_gt        # noqa: F401
 from .loader import VolumeMaps, t2map_series                                          # noqa: F401

@@ -26,7 +26,7 @@ from . import _abi
 from .presets import NO_PRIOR_K_UB, NO_PRIOR_T2_BOUNDS
 
 __all__ = ["fit_voxels_batch", "t2map_volume", "compute_residuals", "FitResult", "init", "shutdown", "device_info",
-           "mask_indices_device", "work_model", "BOUNDS_ERROR"]
+           "mask_indices_device", "work_model", "pinned_array", "BOUNDS_ERROR"]
 
 BOUNDS_ERROR = "An upper bound is less than the corresponding lower bound."   # scipy's text
 
@@ -77,6 +77,23 @@ def work_model(fit: str, n_echo: int):
 
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
+
+
+def pinned_array(shape, dtype=np.float32, like=None):
+    """A numpy array in page-locked host memory (backed by a torch pinned tensor that lives as long as the array).
+    ``like``: copy this array into it.  When ``reshaped_t2w`` (and optionally ``mask_indices``) handed to
+    :func:`fit_voxels_batch` are page-locked, the call needs no staging: the kernel gathers the masked rows straight
+    from host memory over PCIe and stores the results straight back (``run_host_mapped`` in csrc/t2fit_kernels.cu)."""
+    import torch
+    if like is not None:
+        like = np.asarray(like)
+        shape, dtype = like.shape, like.dtype
+    t = torch.empty(tuple(np.atleast_1d(shape)) if not isinstance(shape, tuple) else shape,
+                    dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+    a = t.numpy()
+    if like is not None:
+        np.copyto(a, like)
+    return a
 
 
 def _host_block(m, fields):

@@ -658,6 +658,8 @@ struct Context {
     int* d_tile_counts = nullptr;
     int64_t* d_tile_offsets = nullptr;
     int64_t* d_total = nullptr;
+    int64_t* d_idx = nullptr;                // mapped-input host calls: device copy of a pageable mask_idx
+    int64_t d_idx_cap = 0;
     int64_t* h_total = nullptr;
     int64_t tiles_cap = 0;
     unsigned long long* d_queue = nullptr;   // [kQueues] voxel queue counters of the L-BFGS-B launches (round robin)
@@ -767,9 +769,84 @@ double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+// Host-memory call whose INPUT is page-locked too (cudaHostAlloc / torch pin_memory / cudaHostRegister) and whose compact
+// result arrays are page-locked: no staging at all.  ONE launch over all voxels; the kernel gathers the masked rows
+// straight from host memory over PCIe (only the masked rows cross the bus, consecutive voxels coalesce into 128-byte
+// reads, ~190 k threads in flight hide the latency) and stores the results straight back.  No host thread touches the
+// data, so N ranks on one node do not compete for host cores.  Returns 1 if this path does not apply.
+int run_host_mapped(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitConsts& fc, const lb::LbConsts* lc) {
+    // T2FIT_HOST_IN = mapped | staged | auto (default).  Measured on c2 (profiles/r01_notes.md): with all 16 host cores
+    // to itself the staged pipeline is ~12 % faster (1.35-1.45 ms vs 1.55-1.6 ms per volume); with 8 ranks sharing the
+    // cores it is 1.4x (2 ranks) to 4x (8 ranks) slower.  auto: mapped when this process has fewer than 12 staging threads.
+    const char* env_in = getenv("T2FIT_HOST_IN");       // read per call (tests switch it)
+    const int mode = !env_in ? 0 : !strcmp(env_in, "mapped") ? 1 : !strcmp(env_in, "staged") ? 2 : 0;
+    const bool want = mode == 1 || (mode == 0 && c->workers->size() < 12);
+    const bool mono = p.model == T2FIT_MODEL_GAUSSIAN;
+    if (!want || o.dense || !p.echoes || !is_pinned(p.echoes)) return 1;
+    if (o.trace_cap > 0 && (o.trace_f || o.trace_step || o.trace_len)) return 1;
+    if (!(is_pinned(o.t2) && is_pinned(o.k) && is_pinned(o.res) && is_pinned(o.fun) && is_pinned(o.nit) && is_pinned(o.status) &&
+          (mono || is_pinned(o.sigma)))) return 1;
+    KernelIO io{};
+    auto map = [&](const void* h, void** d) { *d = nullptr; return !h || cudaHostGetDevicePointer(d, const_cast<void*>(h), 0) == cudaSuccess; };
+    void* d_echo = nullptr;
+    if (!(map(p.echoes, &d_echo) && map(o.t2, (void**)&io.t2) && map(o.k, (void**)&io.k) && map(mono ? nullptr : o.sigma, (void**)&io.sigma) &&
+          map(o.res, (void**)&io.res) && map(o.fun, (void**)&io.fun) && map(o.nit, (void**)&io.nit) && map(o.status, (void**)&io.status))) {
+        cudaGetLastError();
+        return 1;
+    }
+    cudaStream_t st = c->slots[0].stream;
+    if (!st) { int rc0 = ensure_slots(c, p.n_echo); if (rc0) return rc0; st = c->slots[0].stream; }
+    const int64_t M = p.n_fit;
+    if (p.mask_idx) {
+        // range check (the reference would raise IndexError), all host threads
+        std::atomic<bool> bad{false};
+        c->workers->run([&](int part, int parts) {
+            const int64_t lo = M * part / parts, hi = M * (part + 1) / parts;
+            bool b = false;
+            for (int64_t i = lo; i < hi; ++i) b |= (p.mask_idx[i] < 0) | (p.mask_idx[i] >= p.n_vox);
+            if (b) bad.store(true);
+        });
+        if (bad.load()) return fail(T2FIT_EINVAL, "mask_idx out of range");
+        void* d_idx = nullptr;
+        if (is_pinned(p.mask_idx) && map(p.mask_idx, &d_idx)) {
+            io.idx = static_cast<const int64_t*>(d_idx);      // read in place too (measured: 1.6 ms vs 2.35 ms with a DMA copy first)
+        } else {                                      // pageable index vector: one copy to the device (8 B per voxel)
+            cudaGetLastError();
+            if (c->d_idx_cap < M) {
+                if (c->d_idx) cudaFree(c->d_idx);
+                c->d_idx = nullptr; c->d_idx_cap = 0;
+                CU_TRY(cudaMalloc(&c->d_idx, sizeof(int64_t) * M));
+                c->d_idx_cap = M;
+            }
+            CU_TRY(cudaMemcpyAsync(c->d_idx, p.mask_idx, sizeof(int64_t) * M, cudaMemcpyHostToDevice, st));
+            io.idx = c->d_idx;
+        }
+    }
+    if (c->counts_dirty) {
+        CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), st));
+        c->counts_dirty = false;
+    }
+    io.echoes = static_cast<const float*>(d_echo); io.ld = p.ld; io.n_fit = M;
+    io.counts = c->d_counts; io.dense = 0; io.layout = p.layout;
+    io.vec_ok = (reinterpret_cast<uintptr_t>(d_echo) % 16) == 0;
+    int rc = lc ? launch_lbfgsb(c, *lc, io, p.model, p.n_echo, st) : launch_fit(c, fc, io, p.model, p.n_echo, p.layout, st);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), st));
+    CU_TRY(cudaStreamSynchronize(st));
+    int64_t bad_n = 0;
+    for (int s = 1; s < 4; ++s) { o.status_count[s] = (int64_t)c->h_counts[s]; bad_n += o.status_count[s]; }
+    o.status_count[0] = M - bad_n;
+    static const bool profile = getenv("T2FIT_HOST_PROFILE") != nullptr;
+    if (profile) fprintf(stderr, "[t2fit host] M=%lld mapped input (no staging)\n", (long long)M);
+    return T2FIT_OK;
+}
+
 int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitConsts& fc, const lb::LbConsts* lc) {
     int rc = ensure_slots(c, p.n_echo);
     if (rc) return rc;
+    rc = run_host_mapped(c, p, o, fc, lc);
+    if (rc != 1) return rc;
     // callback traces (L-BFGS-B solver, sampled voxels): per-slot device scratch for this call only
     const bool tracing = lc && p.n_fit > 0 && o.trace_cap > 0 && (o.trace_f || o.trace_step || o.trace_len);
     struct TraceScratch { float* f = nullptr; float* s = nullptr; int32_t* n = nullptr; } tsc[kSlots];
@@ -1040,6 +1117,7 @@ void t2fit_shutdown(void) {
     if (c->d_tile_offsets) cudaFree(c->d_tile_offsets);
     if (c->d_queue) cudaFree(c->d_queue);
     if (c->d_total) cudaFree(c->d_total);
+    if (c->d_idx) cudaFree(c->d_idx);
     if (c->h_total) cudaFreeHost(c->h_total);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->fill_stream) cudaStreamDestroy(c->fill_stream);

@@ -399,3 +399,25 @@ def test_compute_residuals_mirror(gpu_lib, fit):
         want = fo.residual_map(y, te, fit, norm, k, t2v, sg, np.zeros(n, np.float32), idx, mask)
         assert got.shape == shape and (got[~mask] == 0).all()
         assert np.allclose(got, want, rtol=2e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("fit,solver", [("gaussian", "fast"), ("gaussian_rician", "lbfgsb")])
+def test_page_locked_input_needs_no_staging(gpu_lib, fit, solver, monkeypatch):
+    """Host call with page-locked input: ONE kernel reads the masked rows from host memory and writes the results back
+    (run_host_mapped); bit-identical to the staged pipeline, pinned or pageable index vector, out-of-range indices raise."""
+    from fetal_t2mapping_b200 import synth
+    y, mask, te, _ = synth.make_volume("c1", scale=0.4)
+    flat = np.abs(y.reshape(-1, te.size)) + 1.0
+    idx = np.flatnonzero(mask.reshape(-1))
+    _, fp = gpu_lib.preset(fit, True)
+    monkeypatch.setenv("T2FIT_HOST_IN", "staged")
+    ref = gpu_lib.fit_voxels_batch(flat, idx, te, fit, fp, prior=False, solver=solver)
+    monkeypatch.setenv("T2FIT_HOST_IN", "mapped")
+    flat_p = gpu_lib.pinned_array(None, like=flat)
+    for ix in (idx, gpu_lib.pinned_array(None, like=idx), None):
+        r = gpu_lib.fit_voxels_batch(flat_p, ix, te, fit, fp, prior=False, solver=solver)
+        sel = slice(None) if ix is not None else idx
+        for f in ("t2", "k", "sigma", "res", "fun", "nit", "status"):
+            assert np.array_equal(getattr(r, f)[sel], getattr(ref, f)), f
+    with pytest.raises(IndexError):
+        gpu_lib.fit_voxels_batch(flat_p, np.array([0, flat.shape[0]]), te, fit, fp, prior=False, solver=solver)

@@ -42,3 +42,15 @@ for _ in range(5):
     r = t2.fit_voxels_batch(flat, idx, te, "gaussian", fp, prior=False)
 pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+
+# page-locked input: no staging (run_host_mapped)
+flat_p = t2.pinned_array(None, like=flat)
+idx_p = t2.pinned_array(None, like=idx)
+for name, a, b in (("pinned input, pageable idx", flat_p, idx), ("pinned input, pinned idx", flat_p, idx_p)):
+    ts = []
+    for i in range(8):
+        t0 = time.perf_counter()
+        rp = t2.fit_voxels_batch(a, b, te, "gaussian", fp, prior=False)
+        ts.append(1e3 * (time.perf_counter() - t0))
+    print(name, ["%.3f" % x for x in ts], flush=True)
+    assert np.array_equal(rp.t2, r.t2) and np.array_equal(rp.status, r.status)
