@@ -1,0 +1,53 @@
+"""N > 1 on real GPUs (skipped unless the box shows at least two): one process per GPU, NCCL; every rank fits its slab of
+the masked list with the CUDA path and ONE all-gather stitches the parameter vectors (distributed.fit_voxels_sharded)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, tmp, fit):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), LOCAL_WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import fetal_t2mapping_b200 as t2
+    from fetal_t2mapping_b200 import distributed as D, synth
+    t2.init(rank)
+    y, mask, te, _ = synth.make_volume("c1", scale=0.35)
+    flat = torch.from_numpy(np.abs(y.reshape(-1, te.size)) + 1.0).cuda()
+    idx = torch.from_numpy(np.flatnonzero(mask.reshape(-1))).cuda()
+    _, fp = t2.preset(fit, True)
+    out = D.fit_voxels_sharded(flat, idx, te, fit, fp, prior=False)
+    torch.cuda.synchronize()
+    np.save(os.path.join(tmp, f"t2_{rank}.npy"), out["t2"].cpu().numpy())
+    np.save(os.path.join(tmp, f"st_{rank}.npy"), out["status"].cpu().numpy())
+    if rank == 0:
+        single = t2.fit_voxels_batch(flat, idx, te, fit, fp, prior=False)
+        torch.cuda.synchronize()
+        np.save(os.path.join(tmp, "single.npy"), single.t2.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fit", ["gaussian", "gaussian_rician"])
+def test_two_gpu_sharded_fit_equals_single_gpu(tmp_path, fit):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    world, port = 2, 29600 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path), fit), nprocs=world, join=True)
+    single = np.load(tmp_path / "single.npy")
+    for r in range(world):
+        got = np.load(tmp_path / f"t2_{r}.npy")
+        assert got.shape == single.shape and np.array_equal(got, single)       # every rank holds the full, identical vector
+        assert (np.load(tmp_path / f"st_{r}.npy") == 0).all()
