@@ -98,6 +98,10 @@ SYMBOLS = [
                                    C.c_void_p]),
     ("t2fit_roi_stats", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_double),
                                   C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_void_p]),
+    ("t2fit_shared_alloc", C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    ("t2fit_shared_free", C.c_int, [C.c_void_p]),
+    ("t2fit_shared_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    ("t2fit_shared_close", C.c_int, [C.c_void_p]),
     ("t2fit_pack_soa", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                  C.c_void_p]),
     ("t2fit_scatter", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int64,

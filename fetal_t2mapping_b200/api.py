@@ -25,7 +25,7 @@ import numpy as np
 from . import _abi
 from .presets import NO_PRIOR_K_UB, NO_PRIOR_T2_BOUNDS
 
-__all__ = ["fit_voxels_batch", "t2map_volume", "compute_residuals", "FitResult", "init", "shutdown", "device_info",
+__all__ = ["fit_voxels_batch", "fit_voxels_into", "t2map_volume", "compute_residuals", "FitResult", "init", "shutdown", "device_info",
            "mask_indices_device", "work_model", "pinned_array", "BOUNDS_ERROR"]
 
 BOUNDS_ERROR = "An upper bound is less than the corresponding lower bound."   # scipy's text
@@ -352,6 +352,36 @@ def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=
     return FitResult(out["t2"], out["k"], out["sigma"], out["res"], out["fun"], out["nit"], out["status"], fit,
                      counts if counts is not None else (0, 0, 0, 0), solver, out.get("trace_f"), out.get("trace_step"),
                      out.get("trace_len"))
+
+
+def fit_voxels_into(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior, norm, out, *, solver="auto"):
+    """Device-memory fit whose compact results go to caller-given raw device pointers: ``out`` maps 't2', 'k', 'res'
+    (and 'sigma' for the 3-parameter fits; optionally 'status', 'nit', 'fun') to integer addresses of arrays with room
+    for ``len(mask_indices)`` elements -- local memory or a peer GPU's buffer mapped with ``t2fit_shared_open`` (the
+    fused gather of ``distributed.fit_voxels_sharded``).  Asynchronous on the current torch stream."""
+    import torch
+    lib = init()
+    solver = resolve_solver(fit, solver)
+    p, o = _abi.Problem(), _abi.Outputs()
+    keep = [_fill_problem(p, fit, fit_params, TEeffs, prior, norm, 0, 0.0, "loglinear", solver)]
+    y = reshaped_t2w
+    if not (_is_torch(y) and y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and y.dim() == 2):
+        raise ValueError("device input must be a contiguous float32 CUDA tensor [N, E]")
+    idx = mask_indices
+    if idx is not None and not (_is_torch(idx) and idx.is_cuda and idx.dtype == torch.int64 and idx.is_contiguous()):
+        idx = torch.as_tensor(np.ascontiguousarray(np.asarray(idx.cpu() if _is_torch(idx) else idx), dtype=np.int64), device=y.device)
+    if y.shape[1] != p.n_echo:
+        raise ValueError(f"reshaped_t2w has {y.shape[1]} echoes, TEeffs has {p.n_echo}")
+    p.echoes, p.memory, p.layout = y.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_AOS
+    p.mask_idx = idx.data_ptr() if idx is not None else None
+    p.n_vox, p.n_fit = y.shape[0], (y.shape[0] if idx is None else idx.numel())
+    o.t2, o.k, o.res = out["t2"], out["k"], out["res"]
+    o.sigma = out.get("sigma") if fit != "gaussian" else None
+    o.status, o.nit, o.fun = out.get("status"), out.get("nit"), out.get("fun")
+    o.dense = 0
+    _run(lib, p, o, torch.cuda.current_stream(y.device).cuda_stream)
+    keep += [y, idx]
+    return p.n_fit
 
 
 def mask_indices_device(mask, n_masks=None):

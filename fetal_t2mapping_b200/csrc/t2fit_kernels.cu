@@ -1303,6 +1303,45 @@ int t2fit_roi_stats(const float* const* maps, int32_t n_maps, const int32_t* lab
     return T2FIT_OK;
 }
 
+int t2fit_shared_alloc(int64_t bytes, void** dev_ptr, unsigned char handle[T2FIT_IPC_HANDLE_BYTES]) {
+    Context* c = g_ctx;
+    if (!c) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
+    if (bytes <= 0 || !dev_ptr || !handle) return fail(T2FIT_EINVAL, "bad shared_alloc arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == T2FIT_IPC_HANDLE_BYTES, "IPC handle size");
+    CU_TRY(cudaSetDevice(c->device));
+    void* p = nullptr;
+    CU_TRY(cudaMalloc(&p, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(T2FIT_ECUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    memcpy(handle, &h, sizeof(h));
+    *dev_ptr = p;
+    return T2FIT_OK;
+}
+
+int t2fit_shared_free(void* dev_ptr) {
+    if (!g_ctx) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
+    if (dev_ptr) CU_TRY(cudaFree(dev_ptr));
+    return T2FIT_OK;
+}
+
+int t2fit_shared_open(const unsigned char handle[T2FIT_IPC_HANDLE_BYTES], void** dev_ptr) {
+    Context* c = g_ctx;
+    if (!c) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
+    if (!handle || !dev_ptr) return fail(T2FIT_EINVAL, "bad shared_open arguments");
+    CU_TRY(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    CU_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));     // maps the peer GPU's memory (NVLink)
+    return T2FIT_OK;
+}
+
+int t2fit_shared_close(void* dev_ptr) {
+    if (!g_ctx) return fail(T2FIT_ENOTINIT, "t2fit_init() has not succeeded");
+    if (dev_ptr) CU_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return T2FIT_OK;
+}
+
 int t2fit_pack_soa(const float* aos, int64_t n_vox, int32_t n_echo, const int64_t* mask_idx, int64_t n_fit, float* soa,
                    int64_t ld, void* stream) {
     Context* c = g_ctx;

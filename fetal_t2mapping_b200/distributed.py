@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["slab_bounds", "fit_voxels_sharded", "gather_slabs"]
+__all__ = ["slab_bounds", "fit_voxels_sharded", "gather_slabs", "fit_voxels_fused_gather"]
 
 ALIGN = 128
 
@@ -84,3 +84,64 @@ def fit_voxels_sharded(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prio
         full = gather_slabs(local, bounds, group)
     return {"t2": full[0], "k": full[1], "sigma": full[2], "res": full[3], "status": full[4].to(torch.uint8),
             "bounds": bounds, "rank": rank}
+
+
+class _DeviceBytes:
+    """Raw device memory as a ``__cuda_array_interface__`` provider (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def fit_voxels_fused_gather(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=True, norm=False, *, root=0, group=None,
+                            solver="auto"):
+    """The fit with the final gather FUSED into the kernels: rank r fits slab r of ``mask_indices`` and its kernel's
+    epilogue stores (t2, k, sigma, res, status) straight into the ROOT GPU's full-length buffer over NVLink (peer stores
+    through a CUDA-IPC mapping; no collective launch, the transfer overlaps the fit).  Device tensors in.  Returns the
+    full-length tensors on ``root`` (None on the other ranks) -- the reference's consumer of the maps is one process
+    (NIfTI writers, run_t2mapping.py:471-479)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import _abi
+    from .api import fit_voxels_into, init
+    lib = init()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_fit = int(mask_indices.shape[0])
+    bounds = slab_bounds(n_fit, world)
+    a, b = bounds[rank]
+    nbytes = 4 * 4 * n_fit + n_fit                         # [t2 | k | sigma | res] float32, then status uint8
+    ptr = C.c_void_p()
+    payload = [None]
+    if rank == root:
+        handle = C.create_string_buffer(64)
+        _abi.check(lib, lib.t2fit_shared_alloc(max(nbytes, 1), C.byref(ptr), handle), "t2fit_shared_alloc")
+        payload = [handle.raw]
+    dist.broadcast_object_list(payload, src=root, group=group)
+    if rank != root:
+        _abi.check(lib, lib.t2fit_shared_open(payload[0], C.byref(ptr)), "t2fit_shared_open")
+    base = ptr.value
+    try:
+        if b > a:
+            out = {"t2": base + 4 * a, "k": base + 4 * (n_fit + a), "sigma": base + 4 * (2 * n_fit + a),
+                   "res": base + 4 * (3 * n_fit + a), "status": base + 16 * n_fit + a}
+            fit_voxels_into(reshaped_t2w, mask_indices[a:b], TEeffs, fit, fit_params, prior, norm, out, solver=solver)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)                          # every rank's stores have landed in the root's memory
+        result = None
+        if rank == root:
+            raw = torch.as_tensor(_DeviceBytes(base, max(nbytes, 1)), device=reshaped_t2w.device)
+            f = raw[:16 * n_fit].view(torch.float32).view(4, n_fit).clone()
+            if fit == "gaussian":
+                f[2].zero_()                               # the 2-parameter fit never writes sigma
+            result = {"t2": f[0], "k": f[1], "sigma": f[2], "res": f[3], "status": raw[16 * n_fit:16 * n_fit + n_fit].clone(),
+                      "bounds": bounds, "rank": rank}
+            del raw
+            torch.cuda.synchronize()
+        dist.barrier(group=group)
+        return result
+    finally:
+        if rank == root:
+            lib.t2fit_shared_free(ptr)
+        else:
+            lib.t2fit_shared_close(ptr)

@@ -177,6 +177,18 @@ int t2fit_mask_union(const void *const *planes, int32_t n_planes, int32_t dtype,
 int t2fit_roi_stats(const float *const *maps, int32_t n_maps, const int32_t *label, int64_t n_vox, int32_t n_roi,
                     double *mean_out, double *std_out, int64_t *count_out, void *stream);
 
+/* Fused final gather: instead of fitting into local vectors and then running a collective, every rank's
+ * fit kernel stores its slab of results STRAIGHT INTO THE ROOT GPU'S BUFFER over NVLink (peer stores from the kernel
+ * epilogue; no collective launch, the transfer overlaps the fit).  The root allocates the full-length buffer with
+ * t2fit_shared_alloc and publishes the 64-byte handle (any transport: torch.distributed, MPI, a file); the other
+ * processes map it with t2fit_shared_open and pass `mapped + slab offset` as the t2fit_outputs pointers of an ordinary
+ * T2FIT_MEM_DEVICE t2fit_run; a barrier after the ranks have synchronised their streams completes the gather. */
+#define T2FIT_IPC_HANDLE_BYTES 64
+int t2fit_shared_alloc(int64_t bytes, void **dev_ptr, unsigned char handle[T2FIT_IPC_HANDLE_BYTES]);
+int t2fit_shared_free(void *dev_ptr);
+int t2fit_shared_open(const unsigned char handle[T2FIT_IPC_HANDLE_BYTES], void **dev_ptr); /* in ANOTHER process */
+int t2fit_shared_close(void *dev_ptr);
+
 /* pack_masked_soa: gather rows mask_idx[i] of the AOS array into the echo-contiguous SOA buffer
  * soa[e*ld + i] (device pointers).  The host-memory path of t2fit_run does this on the CPU side
  * while staging; this is the device-resident variant. */

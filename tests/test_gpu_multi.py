@@ -28,6 +28,12 @@ def _worker(rank, world, port, tmp, fit):
     _, fp = t2.preset(fit, True)
     out = D.fit_voxels_sharded(flat, idx, te, fit, fp, prior=False)
     torch.cuda.synchronize()
+    fused = D.fit_voxels_fused_gather(flat, idx, te, fit, fp, prior=False, root=0)     # kernels store into rank 0's buffer
+    assert (fused is None) == (rank != 0)
+    if rank == 0:
+        for name in ("t2", "k", "sigma", "res"):
+            assert torch.equal(fused[name], out[name]), name
+        assert torch.equal(fused["status"], out["status"])
     np.save(os.path.join(tmp, f"t2_{rank}.npy"), out["t2"].cpu().numpy())
     np.save(os.path.join(tmp, f"st_{rank}.npy"), out["status"].cpu().numpy())
     if rank == 0:
