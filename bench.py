@@ -440,13 +440,22 @@ def run_gpu(args):
         tot_m = sum(sizes_l)
         nbytes = 13 * tot_m
         ptr, payload = C.c_void_p(), [None]
+        ok_local = 1
         if rank == 0:
             hbuf = C.create_string_buffer(64)
-            _abi.check(lib, lib.t2fit_shared_alloc(nbytes, C.byref(ptr), hbuf), "t2fit_shared_alloc")
-            payload = [hbuf.raw]
+            if lib.t2fit_shared_alloc(nbytes, C.byref(ptr), hbuf) != 0:
+                ok_local = 0
+            payload = [hbuf.raw if ok_local else None]
         dist.broadcast_object_list(payload, src=0)
-        if rank != 0:
-            _abi.check(lib, lib.t2fit_shared_open(payload[0], C.byref(ptr)), "t2fit_shared_open")
+        if rank != 0 and (payload[0] is None or lib.t2fit_shared_open(payload[0], C.byref(ptr)) != 0):
+            ok_local = 0
+        flag = torch.tensor([ok_local], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if world > 1 and int(flag[0]) == 0:                  # no peer mapping on this box: every rank skips consistently
+        if ptr.value:
+            (lib.t2fit_shared_free if rank == 0 else lib.t2fit_shared_close)(ptr)
+        fused_gather = {"unavailable": (lib.t2fit_last_error() or b"").decode() or "CUDA IPC peer mapping failed on a rank"}
+    elif world > 1:
         base, a0 = ptr.value, int(cuts[rank])
         outp = {"t2": base + 4 * a0, "k": base + 4 * (tot_m + a0), "res": base + 4 * (2 * tot_m + a0), "status": base + 12 * tot_m + a0}
         for _ in range(3):
