@@ -178,6 +178,22 @@ def main():
     if want("c3_rician_prior"):
         rows, te, t2, s0 = sample_rows("c3", 300, 0.2, 107)
         build_case(ref, "c3_rician_prior", rows, te, "rician", "lf", True, False, a.procs, truth=(t2, s0))
+    # the CLI's default echo times (3 TEs: [114,202,299] LF / [115,202,299] HF, run_t2mapping.py:540-545) for all three fits,
+    # incl. the HF rician preset whose x0 [17,40,0.15] lies outside its bounds and is clipped by scipy (:97-98)
+    def cli_rows(n, te, seed, scale, rician):
+        rng = np.random.default_rng(seed)
+        t2v = rng.uniform(40, 450, n).astype(np.float32)
+        s0 = (rng.uniform(500, 1400, n) * scale).astype(np.float32)
+        return synth.decay_signal(s0, t2v, te, rng, 14.0 * scale, rician), t2v, s0
+    cli = [("cli3_gaussian_lf_noprior", "gaussian", "lf", False, [114.0, 202.0, 299.0], 600, 1.0, False),
+           ("cli3_floor_hf_prior", "gaussian_rician", "hf", True, [115.0, 202.0, 299.0], 400, 1.6, True),
+           ("cli3_rician_hf_prior", "rician", "hf", True, [115.0, 202.0, 299.0], 300, 1.6, True),
+           ("cli3_rician_lf_noprior", "rician", "lf", False, [114.0, 202.0, 299.0], 300, 1.0, True)]
+    for i, (nm, fit, field, prior, te_l, n, scale, ric) in enumerate(cli):
+        if want(nm):
+            te = np.array(te_l)
+            rows, t2v, s0 = cli_rows(n, te, 300 + i, scale, ric)
+            build_case(ref, nm, rows, te, fit, field, prior, False, a.procs, truth=(t2v, s0))
     for fit, npar in (("gaussian", 3), ("gaussian_rician", 3)):
         for prior in (True, False):
             nm = f"edge_{fit}_{'prior' if prior else 'noprior'}"

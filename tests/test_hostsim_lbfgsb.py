@@ -54,7 +54,8 @@ def test_optimiser_core_follows_scipy_lbfgsb(name, m):
 
 
 @pytest.mark.parametrize("name", ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior", "c2_gaussian_hf_prior",
-                                  "c3_floor_noprior", "c3_floor_prior", "c5_floor_noprior", "c3_rician_prior", "norm_gaussian"])
+                                  "c3_floor_noprior", "c3_floor_prior", "c5_floor_noprior", "c3_rician_prior", "norm_gaussian",
+                                  "cli3_gaussian_lf_noprior", "cli3_floor_hf_prior", "cli3_rician_hf_prior", "cli3_rician_lf_noprior"])
 def test_emulation_reproduces_reference_fixtures(name):
     g = load_golden(name)
     fp = fit_params_of(g)
