@@ -6,11 +6,18 @@
 //                                residual epilogue, write compact or scatter into dense maps.
 //                                Replaces pool.map(fit_voxel) + compute_residuals + the scatter
 //                                (run_t2mapping.py:430-461).
+//   lbfgsb_kernel<OBJ>           the reference's own optimiser (L-BFGS-B + finite differences, FP64, t2fit_lbfgsb.cuh) for
+//                                all three objectives; persistent grid, lanes pull voxels from a queue.
+//   zero_fill_kernel             np.zeros_like x4 of the dense maps (:415-418) beside the fit, on a side stream
 //   mask_count / mask_scan / mask_write   mask union + ordered compaction (:383-384,:412,:421)
+//   mask_union_kernel            union straight from per-TE mask volumes + --in_vitro_fast label masking (:381-400)
+//   roi_stats_kernel             per-label nanmean / nanstd of the maps (save_phantom_csv, utils/t2map_utils.py:30-59)
 //   pack_soa_kernel              AoS rows -> echo-contiguous SoA (pack_masked_soa)
 //   scatter_kernel               compact -> dense maps (:455-458)
-// Host side: per-process context (one GPU per process), pinned staging ring + worker threads for
-// the host-memory path (pack AoS rows to SoA while the previous chunk is in flight).
+//   residual_kernel              compute_residuals as a stand-alone pass (utils/t2map_utils.py:62-89)
+// Host side: per-process context (one GPU per process); host-memory calls either stage chunks through pinned buffers with
+// worker threads (gather the next chunk while the previous ones are in flight) or, when the caller's arrays are
+// page-locked, let the kernels read / write them in place; CUDA-IPC buffers for the fused multi-GPU gather.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

@@ -333,7 +333,7 @@ def test_full_size_c2_properties(gpu_lib):
 @pytest.mark.parametrize("fit,solver", [("gaussian", "fast"), ("gaussian_rician", "fast"), ("gaussian_rician", "lbfgsb")])
 @pytest.mark.parametrize("shape", [(13, 11, 7), (40, 37, 29), (64, 64, 5)])
 def test_fused_zero_fill_ragged_volumes(gpu_lib, fit, solver, shape):
-    """The fill-role blocks of the fit launch must zero every unmasked slot (and all of sigma for the
+    """The zero-fill that accompanies a dense fit must zero every unmasked slot (and all of sigma for the
     2-parameter model) whatever the volume size, starting from NaN-poisoned maps, and must never touch a
     masked slot; mask bytes other than 1 count as masked."""
     import ctypes as C
