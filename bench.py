@@ -223,6 +223,8 @@ def run_gpu(args):
     o.t2, o.k, o.sigma, o.res = maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr(), maps[3].data_ptr()
     o.fun, o.nit, o.status, o.dense = fun_d.data_ptr(), nit_d.data_ptr(), st_d.data_ptr(), 1
     fused = os.environ.get("T2FIT_BENCH_FUSED_FILL", "1") == "1"
+    # zero-fill route of the library: inside the fit launch (default) or zero_fill_kernel on a side stream (T2FIT_FILL=stream)
+    fill_in_fit = fused and os.environ.get("T2FIT_FILL", "fused") != "stream"
     if fused:
         o.zero_fill_mask = mask_d.data_ptr()             # np.zeros_like x4 (:415-418) done by the fit launch itself
     stream = torch.cuda.current_stream(dev)
@@ -334,43 +336,53 @@ def run_gpu(args):
     ach_gbs = step_bytes / (kern_ms * 1e-3) / 1e9
     roof_hbm = {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach_gbs / peaks["hbm_gbs"], "traffic": traffic.get("step_dram_bytes"),
-                "peak_src": peaks["src"], "kernel": "fit_kernel || zero_fill_kernel (one step, concurrent streams)",
+                "peak_src": peaks["src"],
+                "kernel": ("fit_kernel<mono2,E=5,AoS,FILL> (one launch per step: fit + zero-fill of the dense maps)" if fill_in_fit
+                           else "fit_kernel || zero_fill_kernel (one step, concurrent streams)"),
                 "kernel_ms": kern_ms, "algorithmic_bytes": step_bytes}
     # the step is bound by HBM (the four dense float32 maps are 268 MB of mostly zeros); the fit kernel by FP32/MUFU
     roofline = dict(roof_hbm)
 
     # end to end through the public API with HOST buffers (numpy in, numpy out), every step: inputs from page-locked host
     # memory to the GPU, fit, results back into host arrays
-    def time_e2e(a_flat, a_idx, steps):
-        for _ in range(5):                                  # warm: pinned result blocks cached, staging threads awake
+    def time_e2e(a_flat, a_idx, steps, windows=3):
+        # warm for >= 0.5 s: pinned result blocks cached, staging threads awake, host cores out of their idle states (a
+        # 5-call warm-up left the first window 2x slower on some boxes); then `windows` timed windows of `steps` calls
+        t_w, n_w = time.perf_counter(), 0
+        while n_w < 5 or time.perf_counter() - t_w < 0.5:
             r_ = t2.fit_voxels_batch(a_flat, a_idx, te, "gaussian", fp, prior=False, norm=False)
-        barrier()
-        t0_ = time.perf_counter()
-        for _ in range(steps):
-            r_ = t2.fit_voxels_batch(a_flat, a_idx, te, "gaussian", fp, prior=False, norm=False)
-            _ = float(r_.res[0])
-        torch.cuda.synchronize()
-        dt_ = time.perf_counter() - t0_
-        if world > 1:
-            t_ = torch.tensor([dt_], device=dev, dtype=torch.float64)
-            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-            dt_ = float(t_[0])
-        return dt_, r_
+            n_w += 1
+        dts = []
+        for _ in range(windows):
+            barrier()
+            t0_ = time.perf_counter()
+            for _ in range(steps):
+                r_ = t2.fit_voxels_batch(a_flat, a_idx, te, "gaussian", fp, prior=False, norm=False)
+                _ = float(r_.res[0])
+            torch.cuda.synchronize()
+            dt_ = time.perf_counter() - t0_
+            if world > 1:
+                t_ = torch.tensor([dt_], device=dev, dtype=torch.float64)
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+                dt_ = float(t_[0])
+            dts.append(dt_)
+        return float(np.median(dts)), r_, dts
 
     e2e_steps = max(3, min(args.steps, 20))
     flat_p, idx_p = t2.pinned_array(None, like=flat), t2.pinned_array(None, like=idx)
-    e2e_s, r = time_e2e(flat_p, idx_p, e2e_steps)
+    e2e_s, r, e2e_windows = time_e2e(flat_p, idx_p, e2e_steps)
     assert np.array_equal(r.t2, t2v), "e2e path and device path disagree"
     mapped = int(os.environ.get("T2FIT_HOST_THREADS", "16")) < 12 and os.environ.get("T2FIT_HOST_IN", "auto") != "staged"
     e2e = {"value": m_total * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(m * (n_echo * 4 + 8)),
            "d2h_bytes_per_step": int(m * (4 * 4 + 4 + 1)), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "windows_ms_per_step": [round(1e3 * w / e2e_steps, 4) for w in e2e_windows],     # value = the median window
            "path": "fit_voxels_batch(page-locked numpy [N,E], mask_indices) -> numpy results: " +
                    ("ONE kernel gathers the masked rows straight from host memory over PCIe and stores the results straight "
                     "back (ranks share the host cores: no staging threads)" if mapped else
                     "threaded gather into pinned staging, H2D per 2.6 MB chunk, fit kernel storing results straight into the "
                     "page-locked numpy result arrays (zero-copy D2H)")}
     # the same call with the pageable arrays a drop-in caller has (np.reshape(...).astype(np.float32), np.where)
-    pg_s, r = time_e2e(flat, idx, e2e_steps)
+    pg_s, r, _ = time_e2e(flat, idx, e2e_steps)
     assert np.array_equal(r.t2, t2v)
     e2e["pageable_input"] = {"value": m_total * e2e_steps / pg_s, "ms_per_step": 1e3 * pg_s / e2e_steps}
     del flat_p, idx_p
@@ -496,9 +508,10 @@ def run_gpu(args):
                 "config": {"workload": WORKLOAD, "masked_voxels_per_gpu": int(m), "failed_voxels": n_failed, "volume_voxels_per_gpu": int(n_vox),
                            "n_echo": int(n_echo), "l2": "inputs+outputs per step (603 MB) exceed the 126 MB L2",
                            "partition": f"weak: one volume-sized slab per rank x {world}", "gather": "none in the timed step",
-                           "zero_fill": "zero_fill_kernel on a side stream, concurrent with fit_kernel" if fused else "torch zero_() before the fit launch"},
+                           "zero_fill": ("inside the fit launch: every fit thread zeroes a few 4-voxel words of the dense maps" if fill_in_fit else
+                                         "zero_fill_kernel on a side stream, concurrent with fit_kernel" if fused else "torch zero_() before the fit launch")},
                 "roofline": roofline, "roofline_fp32": roof_fp32, "roofline_hbm": roof_hbm, "cpu_baseline": cpu_baseline,
-                "solver_lbfgsb": lbfgsb, "parity": parity, "e2e": e2e, "gpu_launches": int(args.steps) * (2 if fused else 1), "clocks": clocks, "final_gather": final_gather, "fused_gather": fused_gather,
+                "solver_lbfgsb": lbfgsb, "parity": parity, "e2e": e2e, "gpu_launches": int(args.steps) * (2 if (fused and not fill_in_fit) else 1), "clocks": clocks, "final_gather": final_gather, "fused_gather": fused_gather,
                 "device": info["name"]}
         print(json.dumps(line), flush=True)
     if world > 1:

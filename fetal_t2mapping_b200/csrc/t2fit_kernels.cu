@@ -62,6 +62,11 @@ struct KernelIO {
     float* trace_step;
     int32_t* trace_len;
     int trace_cap;
+    // fused zero-fill (fit_kernel<..., FILL = true>): every fit thread also zeroes a few 4-voxel words of the dense maps
+    const uint8_t* fill_mask;    // dense [n_vox] mask, 4-byte aligned
+    int64_t fill_words;          // n_vox / 4 full words; the ragged tail is left to thread 0
+    int64_t fill_nvox;
+    int fill_wpt;                // words per thread (host: ceil(fill_words / launched threads))
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -104,6 +109,7 @@ __device__ __forceinline__ void load_soa(const float* __restrict__ base, int64_t
 // ------------------------------------------------------------------------------------------------
 // the fit kernel
 // ------------------------------------------------------------------------------------------------
+constexpr int kFusedFillMaxWpt = 16; // fused fill only while a fit thread gets at most this many mask words
 constexpr int kFillChunk = 512;    // dense voxels zero-filled by one warp per round (32 lanes x 4 words x 4 voxels)
 
 // ------------------------------------------------------------------------------------------------
@@ -184,17 +190,82 @@ constexpr int min_blocks(int model, int e) {
     return model == kMono2 ? (e <= 6 ? 5 : e <= 12 ? 4 : e <= 16 ? 3 : 2) : (e <= 8 ? 4 : e <= 16 ? 3 : 2);
 }
 
-template <int MODEL, int E, int LAYOUT>
+// Fused zero-fill (FILL): the np.zeros_like x4 of the dense maps (run_t2mapping.py:415-418) is spread over the fit
+// threads themselves.  Thread t of the launch owns the 4-voxel mask words t, t + T, t + 2T, ... (T = launched threads,
+// fill_wpt of them): their loads are issued together with the thread's own index load, and the zero stores (one
+// coalesced 16-byte store per map and word, fire-and-forget) go out while the thread waits for its echoes.  Every
+// resident warp carries both kinds of work, so the HBM-bound fill rides in the memory stalls of the fit without a
+// second kernel holding SM slots (the side-stream zero_fill_kernel remains for callers this path does not cover).
+template <int MODEL>
+__device__ __forceinline__ void fill_word(const KernelIO& io, int64_t w, uint32_t m) {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t v = w * 4;
+    if (MODEL == kMono2 || m == 0u) *reinterpret_cast<float4*>(io.sigma + v) = z4;   // the 2-parameter fit never writes sigma
+    if (m == 0u) {
+        *reinterpret_cast<float4*>(io.t2 + v) = z4;
+        *reinterpret_cast<float4*>(io.k + v) = z4;
+        *reinterpret_cast<float4*>(io.res + v) = z4;
+    } else if (m != 0x01010101u) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (((m >> (8 * q)) & 0xffu) == 0u) {
+                io.t2[v + q] = 0.f; io.k[v + q] = 0.f; io.res[v + q] = 0.f;
+                if (MODEL != kMono2) io.sigma[v + q] = 0.f;
+            }
+        }
+    }
+}
+
+template <int MODEL, int E, int LAYOUT, bool FILL>
 __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const __grid_constant__ FitConsts c,
                                                      const __grid_constant__ KernelIO io) {
+    constexpr int kGroup = 4;                              // mask words in flight per thread
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool valid = i < io.n_fit;
-    const int64_t ii = valid ? i : io.n_fit - 1;       // whole warps stay in the solver (warp votes)
+    const int64_t ii = valid ? i : io.n_fit - 1;           // whole warps stay in the solver (warp votes)
     const int64_t row = io.idx ? __ldg(io.idx + ii) : ii;
+    const int64_t nt = (int64_t)gridDim.x * kBlock;
+    uint32_t mw[kGroup];
+    if (FILL) {                                            // this thread's mask words: loads in flight beside the index load
+        const uint32_t* pm = reinterpret_cast<const uint32_t*>(io.fill_mask);
+#pragma unroll
+        for (int g = 0; g < kGroup; ++g) {
+            const int64_t w = i + g * nt;
+            mw[g] = (g < io.fill_wpt && w < io.fill_words) ? __ldg(pm + w) : 0x01010101u;
+        }
+    }
     float y[E];
     if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row, io.vec_ok != 0, y);
     else if (LAYOUT == T2FIT_LAYOUT_SOA) load_soa<E>(io.echoes, io.ld, ii, y);
-    else load_soa<E>(io.echoes, io.ld, row, y);          // PLANES: per-TE volumes, voxel `row` of every plane
+    else load_soa<E>(io.echoes, io.ld, row, y);            // PLANES: per-TE volumes, voxel `row` of every plane
+    if (FILL) {                                            // zero stores go out while the echoes are on their way
+#pragma unroll
+        for (int g = 0; g < kGroup; ++g) {
+            const int64_t w = i + g * nt;
+            if (g < io.fill_wpt && w < io.fill_words) fill_word<MODEL>(io, w, mw[g]);
+        }
+#pragma unroll 1
+        for (int g0 = kGroup; g0 < io.fill_wpt; g0 += kGroup) {     // sparse masks: more words than one group per thread
+            const uint32_t* pm = reinterpret_cast<const uint32_t*>(io.fill_mask);
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g) {
+                const int64_t w = i + (g0 + g) * nt;
+                mw[g] = (g0 + g < io.fill_wpt && w < io.fill_words) ? __ldg(pm + w) : 0x01010101u;
+            }
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g) {
+                const int64_t w = i + (g0 + g) * nt;
+                if (g0 + g < io.fill_wpt && w < io.fill_words) fill_word<MODEL>(io, w, mw[g]);
+            }
+        }
+        if (i == 0) {                                               // ragged tail of the volume (n_vox % 4 voxels)
+            for (int64_t v = io.fill_words * 4; v < io.fill_nvox; ++v) {
+                const bool unmasked = io.fill_mask[v] == 0;
+                if (unmasked) { io.t2[v] = 0.f; io.k[v] = 0.f; io.res[v] = 0.f; }
+                if (unmasked || MODEL == kMono2) io.sigma[v] = 0.f;
+            }
+        }
+    }
 
     const VoxelFit f = fit_voxel<float, MODEL, E>(y, c, valid);
 
@@ -529,10 +600,10 @@ __global__ void __launch_bounds__(256) residual_kernel(const __grid_constant__ F
 // ------------------------------------------------------------------------------------------------
 using FitFn = void (*)(const FitConsts, const KernelIO);
 
-template <int MODEL, int LAYOUT>
+template <int MODEL, int LAYOUT, bool FILL>
 FitFn pick_e(int n_echo) {
     switch (n_echo) {
-#define T2_CASE(E) case E: return fit_kernel<MODEL, E, LAYOUT>;
+#define T2_CASE(E) case E: return fit_kernel<MODEL, E, LAYOUT, FILL>;
         T2_CASE(2) T2_CASE(3) T2_CASE(4) T2_CASE(5) T2_CASE(6) T2_CASE(7) T2_CASE(8) T2_CASE(9) T2_CASE(10)
         T2_CASE(11) T2_CASE(12) T2_CASE(13) T2_CASE(14) T2_CASE(15) T2_CASE(16) T2_CASE(17) T2_CASE(18)
         T2_CASE(19) T2_CASE(20) T2_CASE(21) T2_CASE(22) T2_CASE(23) T2_CASE(24) T2_CASE(25) T2_CASE(26)
@@ -542,12 +613,20 @@ FitFn pick_e(int n_echo) {
     }
 }
 
-FitFn pick_kernel(int model, int n_echo, int layout) {
+template <bool FILL>
+FitFn pick_layout(int model, int n_echo, int layout) {
     if (model == T2FIT_MODEL_GAUSSIAN)
-        return layout == T2FIT_LAYOUT_AOS ? pick_e<kMono2, T2FIT_LAYOUT_AOS>(n_echo)
-               : layout == T2FIT_LAYOUT_SOA ? pick_e<kMono2, T2FIT_LAYOUT_SOA>(n_echo) : pick_e<kMono2, T2FIT_LAYOUT_PLANES>(n_echo);
-    return layout == T2FIT_LAYOUT_AOS ? pick_e<kFloor3, T2FIT_LAYOUT_AOS>(n_echo)
-           : layout == T2FIT_LAYOUT_SOA ? pick_e<kFloor3, T2FIT_LAYOUT_SOA>(n_echo) : pick_e<kFloor3, T2FIT_LAYOUT_PLANES>(n_echo);
+        return layout == T2FIT_LAYOUT_AOS ? pick_e<kMono2, T2FIT_LAYOUT_AOS, FILL>(n_echo)
+               : layout == T2FIT_LAYOUT_PLANES ? pick_e<kMono2, T2FIT_LAYOUT_PLANES, FILL>(n_echo)
+               : FILL ? nullptr : pick_e<kMono2, T2FIT_LAYOUT_SOA, false>(n_echo);
+    return layout == T2FIT_LAYOUT_AOS ? pick_e<kFloor3, T2FIT_LAYOUT_AOS, FILL>(n_echo)
+           : layout == T2FIT_LAYOUT_PLANES ? pick_e<kFloor3, T2FIT_LAYOUT_PLANES, FILL>(n_echo)
+           : FILL ? nullptr : pick_e<kFloor3, T2FIT_LAYOUT_SOA, false>(n_echo);
+}
+
+// fill: the launch also zero-fills the dense maps (AoS / PLANES input only; SoA input is compact by construction)
+FitFn pick_kernel(int model, int n_echo, int layout, bool fill) {
+    return fill ? pick_layout<true>(model, n_echo, layout) : pick_layout<false>(model, n_echo, layout);
 }
 
 using LbFn = void (*)(const lb::LbConsts, const KernelIO, unsigned long long*);
@@ -710,12 +789,31 @@ int ensure_slots(Context* c, int n_echo) {
     return T2FIT_OK;
 }
 
-int launch_fit(Context* c, const FitConsts& fc, KernelIO io, int model, int n_echo, int layout, cudaStream_t st) {
+// Mask words per fit thread if the fit launch can take the zero-fill of the dense maps on, else 0: all four maps
+// present and 16-byte aligned, AoS / PLANES input, and no more than a handful of words per thread (a sparse mask --
+// few fit threads for a large volume -- leaves the fill to the side-stream kernel).
+int fused_fill_wpt(const FillArgs& fa, int64_t n_fit, int layout) {
+    if (!(fa.vec && fa.t2 && fa.k && fa.res && fa.sigma) || layout == T2FIT_LAYOUT_SOA || n_fit <= 0) return 0;
+    const int64_t blocks = (n_fit + kBlock - 1) / kBlock;
+    const int64_t words = fa.n_vox / 4, threads = blocks * kBlock;
+    const int64_t wpt = std::max<int64_t>(1, (words + threads - 1) / threads);
+    return wpt <= kFusedFillMaxWpt ? (int)wpt : 0;
+}
+
+// fa (may be null): dense maps to zero-fill in the same launch; the caller has checked fused_fill_wpt() > 0.
+int launch_fit(Context* c, const FitConsts& fc, KernelIO io, int model, int n_echo, int layout, cudaStream_t st,
+               const FillArgs* fa = nullptr) {
     if (io.n_fit <= 0) return T2FIT_OK;
-    FitFn fn = pick_kernel(model, n_echo, layout);
-    if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
     const int64_t blocks = (io.n_fit + kBlock - 1) / kBlock;
     if (blocks > 0x7fffffffLL) return fail(T2FIT_EINVAL, "n_fit too large for one launch");
+    if (fa) {
+        io.fill_mask = fa->mask; io.fill_words = fa->n_vox / 4; io.fill_nvox = fa->n_vox;
+        io.fill_wpt = fused_fill_wpt(*fa, io.n_fit, layout);
+        io.sigma = fa->sigma;
+        if (io.fill_wpt <= 0) return fail(T2FIT_EINVAL, "internal: fused fill not applicable");
+    }
+    FitFn fn = pick_kernel(model, n_echo, layout, fa != nullptr);
+    if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
     fn<<<(unsigned)blocks, kBlock, 0, st>>>(fc, io);
     CU_TRY(cudaGetLastError());
     return T2FIT_OK;
@@ -1183,8 +1281,10 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
         io.trace_f = o->trace_f; io.trace_step = o->trace_step; io.trace_len = o->trace_len; io.trace_cap = o->trace_cap;
     }
     bool forked = false;
+    c->counts_dirty = true;
     if (o->dense && o->zero_fill_mask) {
-        // np.zeros_like x4 (:415-418) on the side stream, concurrent with the fit (disjoint slots)
+        // np.zeros_like x4 (:415-418): inside the fit launch (every fit thread zeroes a few words of the maps while it
+        // waits for its echoes) or, where that does not apply, by zero_fill_kernel on the side stream (disjoint slots)
         if ((reinterpret_cast<uintptr_t>(o->zero_fill_mask) % 4) != 0)
             return fail(T2FIT_EINVAL, "zero_fill_mask must be 4-byte aligned");
         FillArgs fa{};
@@ -1192,10 +1292,13 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
         fa.mask = o->zero_fill_mask; fa.n_vox = p->n_vox; fa.vec = 1;
         float* mp[4] = {o->t2, o->k, o->sigma, o->res};
         for (float* q : mp) if (q && (reinterpret_cast<uintptr_t>(q) % 16) != 0) fa.vec = 0;
+        const char* env_fill = getenv("T2FIT_FILL");      // fused (default) | stream; read per call (tests switch it)
+        const bool want_fused = !lbs && p->n_fit > 0 && !(env_fill && !strcmp(env_fill, "stream"));
+        if (want_fused && fused_fill_wpt(fa, p->n_fit, p->layout) > 0)
+            return launch_fit(c, fc, io, p->model, p->n_echo, p->layout, st, &fa);
         rc = launch_zero_fill(c, fa, p->model == T2FIT_MODEL_GAUSSIAN, st, &forked);
         if (rc) return rc;
     }
-    c->counts_dirty = true;
     rc = lbs ? launch_lbfgsb(c, lc, io, p->model, p->n_echo, st) : launch_fit(c, fc, io, p->model, p->n_echo, p->layout, st);
     if (forked) CU_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));           // join: results complete on `st`
     return rc;

@@ -332,10 +332,14 @@ def test_full_size_c2_properties(gpu_lib):
 
 @pytest.mark.parametrize("fit,solver", [("gaussian", "fast"), ("gaussian_rician", "fast"), ("gaussian_rician", "lbfgsb")])
 @pytest.mark.parametrize("shape", [(13, 11, 7), (40, 37, 29), (64, 64, 5)])
-def test_fused_zero_fill_ragged_volumes(gpu_lib, fit, solver, shape):
+@pytest.mark.parametrize("route,density", [("fused", 0.35), ("stream", 0.35), ("fused", 0.02), ("fused", 0.002)])
+def test_fused_zero_fill_ragged_volumes(gpu_lib, fit, solver, shape, route, density, monkeypatch):
     """The zero-fill that accompanies a dense fit must zero every unmasked slot (and all of sigma for the
     2-parameter model) whatever the volume size, starting from NaN-poisoned maps, and must never touch a
-    masked slot; mask bytes other than 1 count as masked."""
+    masked slot; mask bytes other than 1 count as masked.  Routes: inside the fit launch (a few mask words per fit
+    thread; density 0.02 makes that more than one group of words, 0.002 too many, so the side-stream kernel takes
+    over) and the side-stream kernel on request."""
+    monkeypatch.setenv("T2FIT_FILL", route)
     import ctypes as C
     import torch
     from fetal_t2mapping_b200 import _abi
@@ -345,7 +349,8 @@ def test_fused_zero_fill_ragged_volumes(gpu_lib, fit, solver, shape):
     te = np.array([114.0, 150.0, 202.0, 299.0])
     t2 = rng.uniform(60, 300, n)
     y = (rng.uniform(300, 900, n)[:, None] * np.exp(-te[None, :] / t2[:, None]) + rng.normal(0, 5, (n, 4))).astype(np.float32)
-    mask = (rng.random(n) < 0.35).astype(np.uint8) * rng.choice([1, 255, 7], n).astype(np.uint8)
+    mask = (rng.random(n) < density).astype(np.uint8) * rng.choice([1, 255, 7], n).astype(np.uint8)
+    mask[n // 2] = 1
     idx = np.flatnonzero(mask)
     _, fp = gpu_lib.preset(fit, True)
     lib = gpu_lib.init()

@@ -16,7 +16,8 @@ def main(path):
     per = {}
     for r in rows[2:]:
         name = r[ik]
-        key = "fit_kernel" if "fit_kernel" in name else "zero_fill_kernel" if "zero_fill" in name else "lbfgsb_kernel" if "lbfgsb" in name else None
+        fused = "fit_kernel" in name and "(bool)1" in name          # FILL = true: the launch also zero-fills the dense maps
+        key = "fused_fit_fill_kernel" if fused else "fit_kernel" if "fit_kernel" in name else "zero_fill_kernel" if "zero_fill" in name else "lbfgsb_kernel" if "lbfgsb" in name else None
         if key is None:
             continue
         b = float(r[ir]) * UNIT[units[ir]] + float(r[iw]) * UNIT[units[iw]]
@@ -25,7 +26,9 @@ def main(path):
     for k, v in per.items():
         out[f"{k}_dram_bytes_per_launch"] = sum(x[0] for x in v) / len(v)
         out[f"{k}_ncu_time_{units[it]}"] = sum(x[1] for x in v) / len(v)
-    if "fit_kernel" in per and "zero_fill_kernel" in per:
+    if "fused_fit_fill_kernel" in per:
+        out["step_dram_bytes"] = out["fused_fit_fill_kernel_dram_bytes_per_launch"]
+    elif "fit_kernel" in per and "zero_fill_kernel" in per:
         out["step_dram_bytes"] = out["fit_kernel_dram_bytes_per_launch"] + out["zero_fill_kernel_dram_bytes_per_launch"]
     json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))

@@ -64,6 +64,24 @@ def main():
         return f
 
     res = {}
+    if os.environ.get("MB_ONLY") == "variants":     # fill route (T2FIT_FILL is read per call)
+        for route in ("stream", "fused"):
+            os.environ["T2FIT_FILL"] = route
+            p, o, k5 = problem(m, True, True)
+            f = runner(p, o)
+            print(f"fill {route}: step, windows of 1000 reps:", [round(timeit(f, reps=1000), 1) for _ in range(4)])
+        return
+    if os.environ.get("MB_ONLY") == "step":         # for ncu: a few whole steps (fit + zero-fill), then a few plain fits
+        p, o, k5 = problem(m, True, True)
+        f = runner(p, o)
+        for _ in range(6):
+            f()
+        p, o, k4 = problem(m, True, False)
+        f = runner(p, o)
+        for _ in range(3):
+            f()
+        torch.cuda.synchronize()
+        return
     if os.environ.get("MB_ONLY") == "fill":
         p, o, k1 = problem(0, True, True)
         print("fill only", timeit(runner(p, o), reps=10))
