@@ -311,25 +311,39 @@ T2_HD FloorSums<R> floor_pass(const R (&y)[E], const FitConsts& c, R k, R r, R s
     return a;
 }
 
-template <typename R, int E>
-T2_HD void solve_floor3(const R (&y)[E], const FitConsts& c, R kl, R ku, R k0, R r0, R s0, R& k_out, R& r_out,
-                        R& s_out, R& cost_out, int& nit_out, int& status_out, bool lane_valid) {
-    // x = (k, r, sigma^2); the sigma box maps monotonically (sigma bounds are clamped to >= 0 on the host)
-    const R lo[3] = {kl, R(c.r_lo), R(c.lb[2]) * R(c.lb[2])};
-    const R hi[3] = {ku, R(c.r_hi), R(c.ub[2]) * R(c.ub[2])};
-    R x[3] = {clampr(k0, lo[0], hi[0]), clampr(r0, lo[1], hi[1]), clampr(s0 * s0, lo[2], hi[2])};
-    R xt[3] = {x[0], x[1], x[2]};
-    FloorSums<R> cur{};
-    R lambda = R(1e-3);
-    int nit = 0, status = kOk;
-    int phase = lane_valid ? 0 : 2;
-    bool have_cur = false;
-    const R tol = R(c.tol);
-    const int max_pass = c.max_iter;
-    for (int it = 0; it < max_pass; ++it) {
-        if (!warp_any(phase != 2)) break;
+// The optimiser as a resumable run: start() = clipped start point, step() = one pass over the echoes at the trial point
+// followed by the reaction to it (accept / reject, new trial point or stop).  The one-shot kernel steps all lanes of a
+// warp until the last one has stopped; the queue kernel hands a lane that has stopped the next voxel instead.
+template <typename R>
+struct FloorRun {
+    R kl, ku;                    // per-voxel bounds of k (the others are launch constants)
+    R x[3], xt[3];               // accepted point and trial point, x = (k, r, sigma^2)
+    FloorSums<R> cur;
+    R lambda;
+    int nit, status, it;
+    bool have_cur, active;
+
+    // the sigma box maps monotonically (sigma bounds are clamped to >= 0 on the host)
+    T2_HD R lo(const FitConsts& c, int i) const { return i == 0 ? kl : i == 1 ? R(c.r_lo) : R(c.lb[2]) * R(c.lb[2]); }
+    T2_HD R hi(const FitConsts& c, int i) const { return i == 0 ? ku : i == 1 ? R(c.r_hi) : R(c.ub[2]) * R(c.ub[2]); }
+
+    T2_HD void start(const FitConsts& c, R kl_, R ku_, R k0, R r0, R s0, bool run) {
+        kl = kl_; ku = ku_;
+        x[0] = clampr(k0, lo(c, 0), hi(c, 0)); x[1] = clampr(r0, lo(c, 1), hi(c, 1)); x[2] = clampr(s0 * s0, lo(c, 2), hi(c, 2));
+        xt[0] = x[0]; xt[1] = x[1]; xt[2] = x[2];
+        cur = FloorSums<R>{};
+        lambda = R(1e-3);
+        nit = 0; status = kOk; it = 0;
+        have_cur = false;
+        active = run;
+    }
+
+    template <int E>
+    T2_HD void step(const R (&y)[E], const FitConsts& c) {
+        const R tol = R(c.tol);
+        const int max_pass = c.max_iter;
         const FloorSums<R> t = floor_pass<R, E>(y, c, xt[0], xt[1], xt[2]);
-        if (phase != 2) {
+        if (active) {
             bool accepted = false;
             R step_rel = 0, dec_rel = 1;
             if (!have_cur || t.cost <= cur.cost) {          // accept (the first pass always)
@@ -349,16 +363,16 @@ T2_HD void solve_floor3(const R (&y)[E], const FitConsts& c, R kl, R ku, R k0, R
             }
             const bool last = (it == max_pass - 1);
             if (accepted && (step_rel <= tol || dec_rel <= R(1e-6))) {
-                phase = 2;
+                active = false;
             } else if (last) {
-                phase = 2; status = kNotConverged;
+                active = false; status = kNotConverged;
             } else {
                 // active set: on a bound with the (descent) direction J^T res pointing outward
                 const R g[3] = {cur.gk, cur.gr, cur.gs};
                 bool fixed[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
-                    fixed[i] = (x[i] <= lo[i] && g[i] <= R(0)) || (x[i] >= hi[i] && g[i] >= R(0)) || !(lo[i] < hi[i]);
+                    fixed[i] = (x[i] <= lo(c, i) && g[i] <= R(0)) || (x[i] >= hi(c, i) && g[i] >= R(0)) || !(lo(c, i) < hi(c, i));
                 // Marquardt scaling: d_i = 1/sqrt(H_ii)
                 const R dk = cur.hkk > R(0) ? fast_rsqrt(cur.hkk) : R(0);
                 const R dr = cur.hrr > R(0) ? fast_rsqrt(cur.hrr) : R(0);
@@ -386,25 +400,42 @@ T2_HD void solve_floor3(const R (&y)[E], const FitConsts& c, R kl, R ku, R k0, R
                 const R z2 = (c02 * b0 + c12 * b1 + c22 * b2) * idet;
                 const R d[3] = {z0 * dk, z1 * dr, z2 * ds};
                 R prop = 0;
-                bool all_fixed = f0 && f1 && f2;
+                const bool all_fixed = f0 && f1 && f2;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    R xn = clampr(x[i] + d[i], lo[i], hi[i]);
+                    R xn = clampr(x[i] + d[i], lo(c, i), hi(c, i));
                     if (!finite_r(xn)) xn = x[i];
                     prop = rmax(prop, absr(xn - x[i]) * fast_rcp(rmax(absr(x[i]), R(1e-12))));
                     xt[i] = xn;
                 }
                 if (all_fixed || prop <= tol * R(0.01)) {
-                    phase = 2;                          // KKT point (or the step has vanished)
+                    active = false;                     // KKT point (or the step has vanished)
                     xt[0] = x[0]; xt[1] = x[1]; xt[2] = x[2];
                 }
             }
+            ++it;
         }
     }
-    R sig = sqrt(x[2]);
-    if (x[2] <= lo[2]) sig = R(c.lb[2]);
-    if (x[2] >= hi[2]) sig = R(c.ub[2]);
-    k_out = x[0]; r_out = x[1]; s_out = sig; cost_out = cur.cost; nit_out = nit; status_out = status;
+
+    T2_HD R sigma(const FitConsts& c) const {
+        R sig = sqrt(x[2]);
+        if (x[2] <= lo(c, 2)) sig = R(c.lb[2]);
+        if (x[2] >= hi(c, 2)) sig = R(c.ub[2]);
+        return sig;
+    }
+};
+
+template <typename R, int E>
+T2_HD void solve_floor3(const R (&y)[E], const FitConsts& c, R kl, R ku, R k0, R r0, R s0, R& k_out, R& r_out,
+                        R& s_out, R& cost_out, int& nit_out, int& status_out, bool lane_valid) {
+    FloorRun<R> run;
+    run.start(c, kl, ku, k0, r0, s0, lane_valid);
+    const int max_pass = c.max_iter;
+    for (int it = 0; it < max_pass; ++it) {
+        if (!warp_any(run.active)) break;
+        run.template step<E>(y, c);
+    }
+    k_out = run.x[0]; r_out = run.x[1]; s_out = run.sigma(c); cost_out = run.cur.cost; nit_out = run.nit; status_out = run.status;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -416,9 +447,18 @@ T2_HD void solve_floor3(const R (&y)[E], const FitConsts& c, R kl, R ku, R k0, R
 //   * res  = sum_e (y_e - pred_e) / E   signed                (utils/t2map_utils.py:81-84)
 //   * fun  = sum_e (y_e - pred_e)^2 / E                       (run_t2mapping.py:147,155)
 // ---------------------------------------------------------------------------------------------
+// what the preamble of fit_voxel decides per voxel: bounds of k, validity, and the start point
+template <typename R>
+struct VoxelPre {
+    R kl, ku;
+    R k0, r0, s0;
+    int status;              // kOk, kNonFinite or kBadBounds
+};
+
+// validity, normalisation (in place), per-voxel bounds, initial guess
 template <typename R, int MODEL, int E>
-T2_HD VoxelFit fit_voxel(R (&y)[E], const FitConsts& c, bool lane_valid) {
-    VoxelFit out;
+T2_HD VoxelPre<R> voxel_prepare(R (&y)[E], const FitConsts& c) {
+    VoxelPre<R> p;
     const R y0_raw = y[0];
     R fin = 0;                                              // 0 if every echo is finite, NaN otherwise
 #pragma unroll
@@ -432,33 +472,34 @@ T2_HD VoxelFit fit_voxel(R (&y)[E], const FitConsts& c, bool lane_valid) {
 #pragma unroll
         for (int e = 0; e < E; ++e) { y[e] *= inv; fin += y[e] * R(0); }
     }
-    const R kl = c.no_prior ? y0_raw : R(c.lb[0]);          // run_t2mapping.py:243-245
-    const R ku = R(c.ub[0]);
-    int status = kOk;
-    if (c.no_prior && (y0_raw > ku)) status = kBadBounds;   // scipy: "An upper bound is less than ..."
-    else if (!(fin == R(0))) status = kNonFinite;
-    const bool run = lane_valid && status == kOk;           // lanes that do not run start as `done`
-
-    R k = 0, r = R(c.r_x0), s = 0;
-    int nit = 0, st = kOk;
-    if (MODEL == kMono2) {
-        const R r0 = (c.init_mode == kInitPreset) ? R(c.r_x0) : loglinear_rate<R, E>(y, c);
-        solve_mono2<R, E>(y, c, kl, ku, r0, r, nit, st, run);
-    } else {
-        R r0 = R(c.r_x0), k0 = R(c.x0[0]), s0 = R(c.x0[2]), cost = 0;
-        if (c.init_mode != kInitPreset) {
-            r0 = loglinear_rate<R, E>(y, c);
+    p.kl = c.no_prior ? y0_raw : R(c.lb[0]);                // run_t2mapping.py:243-245
+    p.ku = R(c.ub[0]);
+    p.status = kOk;
+    if (c.no_prior && (y0_raw > p.ku)) p.status = kBadBounds;   // scipy: "An upper bound is less than ..."
+    else if (!(fin == R(0))) p.status = kNonFinite;
+    p.r0 = R(c.r_x0); p.k0 = R(c.x0[0]); p.s0 = R(c.x0[2]);
+    if (c.init_mode != kInitPreset) {
+        p.r0 = loglinear_rate<R, E>(y, c);
+        if (MODEL != kMono2) {
             R sa = 0, sb = 0;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const R u = fast_ex2(R(c.nte2[e]) * r0);
+                const R u = fast_ex2(R(c.nte2[e]) * p.r0);
                 sa += u * u;
                 sb += y[e] * u;
             }
-            k0 = sa > R(0) ? fdiv(sb, sa) : k0;
+            p.k0 = sa > R(0) ? fdiv(sb, sa) : p.k0;
         }
-        solve_floor3<R, E>(y, c, kl, ku, k0, r0, s0, k, r, s, cost, nit, st, run);
     }
+    return p;
+}
+
+// what fit_voxel returns + the residual epilogue, from the solver's (k, r, s) -- ignored when pre.status != kOk
+template <typename R, int MODEL, int E>
+T2_HD VoxelFit voxel_finish(const R (&y)[E], const FitConsts& c, const VoxelPre<R>& pre, R k, R r, R s, int nit, int st) {
+    VoxelFit out;
+    const R kl = pre.kl, ku = pre.ku;
+    int status = pre.status;
     R t2;
     const bool solved = (status == kOk);
     if (solved) {
@@ -509,6 +550,21 @@ T2_HD VoxelFit fit_voxel(R (&y)[E], const FitConsts& c, bool lane_valid) {
     out.nit = nit;
     out.status = status;
     return out;
+}
+
+template <typename R, int MODEL, int E>
+T2_HD VoxelFit fit_voxel(R (&y)[E], const FitConsts& c, bool lane_valid) {
+    const VoxelPre<R> pre = voxel_prepare<R, MODEL, E>(y, c);
+    const bool run = lane_valid && pre.status == kOk;       // lanes that do not run start as `done`
+    R k = 0, r = R(c.r_x0), s = 0;
+    int nit = 0, st = kOk;
+    if (MODEL == kMono2) {
+        solve_mono2<R, E>(y, c, pre.kl, pre.ku, pre.r0, r, nit, st, run);
+    } else {
+        R cost = 0;
+        solve_floor3<R, E>(y, c, pre.kl, pre.ku, pre.k0, pre.r0, pre.s0, k, r, s, cost, nit, st, run);
+    }
+    return voxel_finish<R, MODEL, E>(y, c, pre, k, r, s, nit, st);
 }
 
 }  // namespace t2fit

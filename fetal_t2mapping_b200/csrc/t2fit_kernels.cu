@@ -109,6 +109,7 @@ __device__ __forceinline__ void load_soa(const float* __restrict__ base, int64_t
 // ------------------------------------------------------------------------------------------------
 // the fit kernel
 // ------------------------------------------------------------------------------------------------
+constexpr int kQueueRefill = 8;      // floor_queue_kernel: waiting lanes per warp that trigger epilogue + refill
 constexpr int kFusedFillMaxWpt = 16; // fused fill only while a fit thread gets at most this many mask words
 constexpr int kFillChunk = 512;    // dense voxels zero-filled by one warp per round (32 lanes x 4 words x 4 voxels)
 
@@ -287,6 +288,88 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
         for (int s = 1; s < 4; ++s) {
             const unsigned m = __ballot_sync(0xffffffffu, st == s);
             if (m && (threadIdx.x & 31) == 0) atomicAdd(io.counts + s, (unsigned long long)__popc(m));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// floor_queue_kernel: the 3-parameter fast solver as a persistent grid with a lane-level voxel queue.
+// The projected LM iteration needs 3..64 passes over the echoes depending on the voxel (noise-floor voxels run to the
+// cap), so a warp of the one-shot kernel spends most of its time waiting for its slowest lane (c5: 6.4 passes per voxel
+// on average, ~25 per warp).  Here a lane whose run has stopped gets the next voxel from a queue counter
+// (warp-aggregated atomicAdd) while its neighbours keep iterating.  Epilogue (residuals, stores) and prologue (echo
+// loads, log-linear start point) of the replaced lanes are batched: they run only once `refill` lanes of the warp
+// are waiting, so their instructions are shared by that many lanes.  Same per-voxel arithmetic as fit_kernel<kFloor3>
+// (voxel_prepare / FloorRun::step / voxel_finish), hence the same results.
+// ------------------------------------------------------------------------------------------------
+constexpr int kQBlock = 128;
+constexpr int queue_min_blocks(int e) { return e <= 8 ? 6 : e <= 16 ? 4 : 2; }
+
+template <int E, int LAYOUT>
+__global__ void __launch_bounds__(kQBlock, queue_min_blocks(E)) floor_queue_kernel(const __grid_constant__ FitConsts c,
+                                                                                   const __grid_constant__ KernelIO io,
+                                                                                   unsigned long long* __restrict__ queue,
+                                                                                   const int refill) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    FloorRun<float> run;
+    run.active = false;
+    VoxelPre<float> pre{};
+    float y[E];
+    int64_t i = 0, row = 0;
+    bool have = false;                       // this lane holds a voxel whose result has not been stored yet
+    bool more = true;                        // the queue still has voxels (warp-uniform)
+    unsigned cnt1 = 0, cnt2 = 0, cnt3 = 0;   // non-OK voxels of this lane, by status
+    for (;;) {
+        const unsigned m_done = __ballot_sync(kFull, have && !run.active);
+        const unsigned m_empty = __ballot_sync(kFull, !have);
+        const bool any_active = __any_sync(kFull, run.active);
+        const int waiting = __popc(m_done) + __popc(m_empty);
+        const bool turn = !any_active || ((waiting >= refill || !more) && (m_done != 0u || (more && m_empty != 0u)));
+        if (turn) {
+            if (have && !run.active) {       // epilogue of the lanes that have stopped
+                const VoxelFit f = voxel_finish<float, kFloor3, E>(y, c, pre, run.x[0], run.x[1], run.sigma(c), run.nit, run.status);
+                const int64_t o = io.dense ? row : i;
+                if (io.t2) io.t2[o] = f.t2;
+                if (io.k) io.k[o] = f.k;
+                if (io.sigma) io.sigma[o] = f.sigma;
+                if (io.res) io.res[o] = f.res;
+                if (io.fun) io.fun[i] = f.fun;
+                if (io.nit) io.nit[i] = f.nit;
+                if (io.status) io.status[i] = (uint8_t)f.status;
+                cnt1 += f.status == 1; cnt2 += f.status == 2; cnt3 += f.status == 3;
+                have = false;
+            }
+            if (more) {                      // next voxels for every lane without one
+                const unsigned m_need = __ballot_sync(kFull, !have);
+                const int n_need = __popc(m_need);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(queue, (unsigned long long)n_need);
+                base = __shfl_sync(kFull, base, 0);
+                more = (int64_t)(base + (unsigned long long)n_need) < io.n_fit;
+                const int64_t cand = (int64_t)base + __popc(m_need & ((1u << lane) - 1u));
+                if (!have && cand < io.n_fit) {
+                    i = cand;
+                    row = io.idx ? __ldg(io.idx + i) : i;
+                    if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row, io.vec_ok != 0, y);
+                    else if (LAYOUT == T2FIT_LAYOUT_SOA) load_soa<E>(io.echoes, io.ld, i, y);
+                    else load_soa<E>(io.echoes, io.ld, row, y);
+                    pre = voxel_prepare<float, kFloor3, E>(y, c);
+                    run.start(c, pre.kl, pre.ku, pre.k0, pre.r0, pre.s0, pre.status == kOk);
+                    have = true;
+                }
+            }
+            if (!__any_sync(kFull, have)) break;
+        }
+        if (__any_sync(kFull, run.active)) run.template step<E>(y, c);
+    }
+    // per-status voxel counts of the launch: one atomic per warp and status
+    if (io.counts) {
+        const unsigned t1 = __reduce_add_sync(kFull, cnt1), t2 = __reduce_add_sync(kFull, cnt2), t3 = __reduce_add_sync(kFull, cnt3);
+        if (lane == 0) {
+            if (t1) atomicAdd(io.counts + 1, (unsigned long long)t1);
+            if (t2) atomicAdd(io.counts + 2, (unsigned long long)t2);
+            if (t3) atomicAdd(io.counts + 3, (unsigned long long)t3);
         }
     }
 }
@@ -619,14 +702,35 @@ FitFn pick_layout(int model, int n_echo, int layout) {
         return layout == T2FIT_LAYOUT_AOS ? pick_e<kMono2, T2FIT_LAYOUT_AOS, FILL>(n_echo)
                : layout == T2FIT_LAYOUT_PLANES ? pick_e<kMono2, T2FIT_LAYOUT_PLANES, FILL>(n_echo)
                : FILL ? nullptr : pick_e<kMono2, T2FIT_LAYOUT_SOA, false>(n_echo);
-    return layout == T2FIT_LAYOUT_AOS ? pick_e<kFloor3, T2FIT_LAYOUT_AOS, FILL>(n_echo)
-           : layout == T2FIT_LAYOUT_PLANES ? pick_e<kFloor3, T2FIT_LAYOUT_PLANES, FILL>(n_echo)
-           : FILL ? nullptr : pick_e<kFloor3, T2FIT_LAYOUT_SOA, false>(n_echo);
+    if (FILL) return nullptr;            // the 3-parameter fit runs in floor_queue_kernel; its dense maps are zeroed by zero_fill_kernel
+    return layout == T2FIT_LAYOUT_AOS ? pick_e<kFloor3, T2FIT_LAYOUT_AOS, false>(n_echo)
+           : layout == T2FIT_LAYOUT_PLANES ? pick_e<kFloor3, T2FIT_LAYOUT_PLANES, false>(n_echo)
+           : pick_e<kFloor3, T2FIT_LAYOUT_SOA, false>(n_echo);
 }
 
 // fill: the launch also zero-fills the dense maps (AoS / PLANES input only; SoA input is compact by construction)
 FitFn pick_kernel(int model, int n_echo, int layout, bool fill) {
     return fill ? pick_layout<true>(model, n_echo, layout) : pick_layout<false>(model, n_echo, layout);
+}
+
+using QueueFn = void (*)(const FitConsts, const KernelIO, unsigned long long*, const int);
+
+template <int LAYOUT>
+QueueFn pick_queue_e(int n_echo) {
+    switch (n_echo) {
+#define T2_CASE(E) case E: return floor_queue_kernel<E, LAYOUT>;
+        T2_CASE(2) T2_CASE(3) T2_CASE(4) T2_CASE(5) T2_CASE(6) T2_CASE(7) T2_CASE(8) T2_CASE(9) T2_CASE(10)
+        T2_CASE(11) T2_CASE(12) T2_CASE(13) T2_CASE(14) T2_CASE(15) T2_CASE(16) T2_CASE(17) T2_CASE(18)
+        T2_CASE(19) T2_CASE(20) T2_CASE(21) T2_CASE(22) T2_CASE(23) T2_CASE(24) T2_CASE(25) T2_CASE(26)
+        T2_CASE(27) T2_CASE(28) T2_CASE(29) T2_CASE(30) T2_CASE(31) T2_CASE(32)
+#undef T2_CASE
+        default: return nullptr;
+    }
+}
+
+QueueFn pick_queue_kernel(int n_echo, int layout) {
+    return layout == T2FIT_LAYOUT_AOS ? pick_queue_e<T2FIT_LAYOUT_AOS>(n_echo)
+           : layout == T2FIT_LAYOUT_SOA ? pick_queue_e<T2FIT_LAYOUT_SOA>(n_echo) : pick_queue_e<T2FIT_LAYOUT_PLANES>(n_echo);
 }
 
 using LbFn = void (*)(const lb::LbConsts, const KernelIO, unsigned long long*);
@@ -800,10 +904,41 @@ int fused_fill_wpt(const FillArgs& fa, int64_t n_fit, int layout) {
     return wpt <= kFusedFillMaxWpt ? (int)wpt : 0;
 }
 
+int launch_floor_queue(Context* c, const FitConsts& fc, const KernelIO& io, int n_echo, int layout, cudaStream_t st) {
+    QueueFn fn = pick_queue_kernel(n_echo, layout);
+    if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
+    static std::mutex mu;
+    static std::vector<std::pair<QueueFn, int>> occ;         // resident blocks per SM, per kernel
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& e : occ) if (e.first == fn) per_sm = e.second;
+        if (per_sm == 0) {
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kQBlock, 0));
+            if (per_sm <= 0) per_sm = 1;
+            occ.emplace_back(fn, per_sm);
+        }
+    }
+    const char* er = getenv("T2FIT_QUEUE_REFILL");           // lanes of a warp that must be waiting before they are replaced
+    const int refill = er ? std::min(32, std::max(1, atoi(er))) : kQueueRefill;
+    const int64_t want = (io.n_fit + kQBlock - 1) / kQBlock;
+    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)per_sm * c->prop.multiProcessorCount);
+    unsigned long long* q = c->d_queue + (c->queue_next++ % kQueues);
+    CU_TRY(cudaMemsetAsync(q, 0, sizeof(unsigned long long), st));
+    fn<<<grid, kQBlock, 0, st>>>(fc, io, q, refill);
+    CU_TRY(cudaGetLastError());
+    return T2FIT_OK;
+}
+
 // fa (may be null): dense maps to zero-fill in the same launch; the caller has checked fused_fill_wpt() > 0.
 int launch_fit(Context* c, const FitConsts& fc, KernelIO io, int model, int n_echo, int layout, cudaStream_t st,
                const FillArgs* fa = nullptr) {
     if (io.n_fit <= 0) return T2FIT_OK;
+    if (model != T2FIT_MODEL_GAUSSIAN && !fa) {
+        // 3-parameter fit: persistent grid + voxel queue (T2FIT_FLOOR_KERNEL=oneshot keeps the one-thread-per-voxel launch)
+        const char* ek = getenv("T2FIT_FLOOR_KERNEL");
+        if (!(ek && !strcmp(ek, "oneshot"))) return launch_floor_queue(c, fc, io, n_echo, layout, st);
+    }
     const int64_t blocks = (io.n_fit + kBlock - 1) / kBlock;
     if (blocks > 0x7fffffffLL) return fail(T2FIT_EINVAL, "n_fit too large for one launch");
     if (fa) {
@@ -1293,7 +1428,7 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
         float* mp[4] = {o->t2, o->k, o->sigma, o->res};
         for (float* q : mp) if (q && (reinterpret_cast<uintptr_t>(q) % 16) != 0) fa.vec = 0;
         const char* env_fill = getenv("T2FIT_FILL");      // fused (default) | stream; read per call (tests switch it)
-        const bool want_fused = !lbs && p->n_fit > 0 && !(env_fill && !strcmp(env_fill, "stream"));
+        const bool want_fused = !lbs && p->model == T2FIT_MODEL_GAUSSIAN && p->n_fit > 0 && !(env_fill && !strcmp(env_fill, "stream"));
         if (want_fused && fused_fill_wpt(fa, p->n_fit, p->layout) > 0)
             return launch_fit(c, fc, io, p->model, p->n_echo, p->layout, st, &fa);
         rc = launch_zero_fill(c, fa, p->model == T2FIT_MODEL_GAUSSIAN, st, &forked);

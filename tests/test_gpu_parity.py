@@ -379,6 +379,59 @@ def test_fused_zero_fill_ragged_volumes(gpu_lib, fit, solver, shape, route, dens
     del keep
 
 
+@pytest.mark.parametrize("n_echo,layout", [(3, "aos"), (4, "aos"), (6, "soa"), (12, "aos"), (16, "planes")])
+@pytest.mark.parametrize("refill", [1, 8, 32])
+def test_floor_queue_kernel_equals_one_shot_kernel(gpu_lib, n_echo, layout, refill, monkeypatch):
+    """The 3-parameter fast solver runs in a persistent kernel whose lanes pull voxels from a queue; it must return, bit
+    for bit, what the one-thread-per-voxel launch returns (same per-voxel arithmetic), whatever the refill threshold,
+    for every input layout, with edge rows (NaN / Inf / zero / bounds-invalid) in the mix and a ragged voxel count."""
+    import ctypes as C
+    import torch
+    from fetal_t2mapping_b200 import _abi
+    from fetal_t2mapping_b200.api import _fill_problem
+    rng = np.random.default_rng(100 * n_echo + refill)
+    n = 20011
+    te = np.linspace(100.0, 700.0, n_echo)
+    t2v = np.exp(rng.uniform(np.log(10.0), np.log(2000.0), n))
+    s = rng.uniform(300, 3000, n)[:, None] * np.exp(-te[None, :] / t2v[:, None])
+    y = np.sqrt((s + rng.normal(0, 20, s.shape)) ** 2 + rng.normal(0, 20, s.shape) ** 2).astype(np.float32)
+    y[5, 1] = np.nan; y[77, 0] = np.inf; y[123] = 0.0; y[999, 0] = 2.0e4; y[n - 1, n_echo - 1] = -np.inf
+    idx = np.unique(np.concatenate([rng.choice(n, 17001, replace=False), [5, 77, 123, 999, n - 1]])).astype(np.int64)
+    _, fp = gpu_lib.preset("gaussian_rician", True)
+    lib = gpu_lib.init()
+    lay = {"aos": _abi.LAYOUT_AOS, "soa": _abi.LAYOUT_SOA, "planes": _abi.LAYOUT_PLANES}[layout]
+    if layout == "aos":
+        yd, ld = torch.from_numpy(y).cuda(), 0
+    elif layout == "planes":
+        yd, ld = torch.from_numpy(np.ascontiguousarray(y.T)).cuda(), n
+    else:
+        yd, ld = torch.from_numpy(np.ascontiguousarray(y[idx].T)).cuda(), idx.size
+    idxd = torch.from_numpy(idx).cuda()
+    outs = {}
+    for kern in ("oneshot", "queue"):
+        monkeypatch.setenv("T2FIT_FLOOR_KERNEL", kern)
+        monkeypatch.setenv("T2FIT_QUEUE_REFILL", str(refill))
+        p, o = _abi.Problem(), _abi.Outputs()
+        keep = _fill_problem(p, "gaussian_rician", fp, te, False, False, 0, 0.0, "loglinear", "fast")
+        p.echoes, p.memory, p.layout, p.ld = yd.data_ptr(), _abi.MEM_DEVICE, lay, ld
+        p.mask_idx, p.n_vox, p.n_fit = (0 if layout == "soa" else idxd.data_ptr()), n, idx.size
+        f32 = torch.full((5, idx.size), float("nan"), device="cuda")
+        nit = torch.full((idx.size,), -1, dtype=torch.int32, device="cuda")
+        st = torch.full((idx.size,), 9, dtype=torch.uint8, device="cuda")
+        o.t2, o.k, o.sigma, o.res, o.fun = (f32[j].data_ptr() for j in range(5))
+        o.nit, o.status = nit.data_ptr(), st.data_ptr()
+        rc = lib.t2fit_run(C.byref(p), C.byref(o), torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.t2fit_last_error()
+        cnt = (C.c_int64 * 4)()
+        assert lib.t2fit_status_counts(torch.cuda.current_stream().cuda_stream, cnt) == 0
+        outs[kern] = (f32.cpu().numpy(), nit.cpu().numpy(), st.cpu().numpy(), list(cnt)[1:])
+        del keep
+    a, b = outs["oneshot"], outs["queue"]
+    assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[3] == b[3] == [int((a[2] == s_).sum()) for s_ in (1, 2, 3)]
+    assert (a[2] == 1).sum() >= 2 and (a[2] == 3).sum() == 1 and (a[2] == 0).mean() > 0.5 and a[1].max() >= 3
+
+
 def test_out_of_range_mask_indices_raise(gpu_lib):
     y = np.ones((10, 3), np.float32)
     _, fp = gpu_lib.preset("gaussian", True)

@@ -2,6 +2,7 @@
 DRAM bytes (read + write) per launch of the fit kernel and of the zero-fill kernel.
     python tools/make_traffic.py gpurun_out/step_raw.csv"""
 import csv
+import re
 import json
 import os
 import sys
@@ -16,7 +17,8 @@ def main(path):
     per = {}
     for r in rows[2:]:
         name = r[ik]
-        fused = "fit_kernel" in name and "(bool)1" in name          # FILL = true: the launch also zero-fills the dense maps
+        # FILL = true (4th template argument): the launch also zero-fills the dense maps
+        fused = re.search(r"fit_kernel<[^>]*,\s*(\(bool\))?(1|true)>", name) is not None
         key = "fused_fit_fill_kernel" if fused else "fit_kernel" if "fit_kernel" in name else "zero_fill_kernel" if "zero_fill" in name else "lbfgsb_kernel" if "lbfgsb" in name else None
         if key is None:
             continue
