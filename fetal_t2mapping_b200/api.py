@@ -429,7 +429,7 @@ def t2map_volume(t2w, mask, TEeffs, fit, fit_params, prior=True, norm=False, **k
         mk = mk.view(torch.uint8) if mk.dtype == torch.bool else mk
         idx = mask_indices_device(mk)                                                   # :412,:421
         n_vox, m = y.shape[0], idx.numel()
-        # the four maps are zero-filled by zero_fill_kernel on a side stream, concurrently with the fit (:415-418)
+        # the four maps are zero-filled by the fit launch itself (or zero_fill_kernel on a side stream), see t2fit.h (:415-418)
         maps = torch.empty((4, n_vox), dtype=torch.float32, device=y.device)
         fused_mask = mk.reshape(-1)
         p.echoes, p.memory, p.mask_idx = y.data_ptr(), _abi.MEM_DEVICE, idx.data_ptr()

@@ -1,14 +1,16 @@
 // libt2fit: sm_100a kernels + the C ABI of include/t2fit.h.
 //
 // Kernels (DESIGN.md has the data layout and the roofline of each):
-//   fit_kernel<MODEL,E,LAYOUT>   one thread per masked voxel: gather echoes (AoS rows through
+//   fit_kernel<MODEL,E,LAYOUT,FILL>  one thread per masked voxel: gather echoes (AoS rows through
 //                                mask_idx, or SoA planes), solve in registers (t2fit_core.cuh),
 //                                residual epilogue, write compact or scatter into dense maps.
 //                                Replaces pool.map(fit_voxel) + compute_residuals + the scatter
-//                                (run_t2mapping.py:430-461).
+//                                (run_t2mapping.py:430-461).  FILL: the same threads also zero-fill the dense maps.
+//   floor_queue_kernel<E,LAYOUT> the 3-parameter fast solver: persistent grid, lanes pull voxels from a queue
+//                                (pass counts vary 3..64 between neighbouring voxels).
 //   lbfgsb_kernel<OBJ>           the reference's own optimiser (L-BFGS-B + finite differences, FP64, t2fit_lbfgsb.cuh) for
 //                                all three objectives; persistent grid, lanes pull voxels from a queue.
-//   zero_fill_kernel             np.zeros_like x4 of the dense maps (:415-418) beside the fit, on a side stream
+//   zero_fill_kernel             np.zeros_like x4 of the dense maps (:415-418) beside the fit, on a side stream (where FILL does not apply)
 //   mask_count / mask_scan / mask_write   mask union + ordered compaction (:383-384,:412,:421)
 //   mask_union_kernel            union straight from per-TE mask volumes + --in_vitro_fast label masking (:381-400)
 //   roi_stats_kernel             per-label nanmean / nanstd of the maps (save_phantom_csv, utils/t2map_utils.py:30-59)

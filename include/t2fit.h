@@ -123,12 +123,16 @@ typedef struct t2fit_outputs {
     int32_t *trace_len;
     int32_t trace_cap;
     const uint8_t *zero_fill_mask; /* device calls with dense != 0 only: the [n_vox] uint8 mask (1 byte per voxel,
-                                    nonzero = masked, consistent with mask_idx).  When given, the call also
-                                    zero-fills every unmasked slot of the four maps (np.zeros_like, :415-418)
-                                    -- and all of sigma for the 2-parameter model -- with a kernel on a side
-                                    stream that runs concurrently with the fit (forked from / joined into
-                                    `stream`), so the caller need not pre-zero them.  NULL = caller zero-fills.
-                                    One such call at a time per process (the fork/join events are shared). */
+                                    nonzero = masked, consistent with mask_idx, 4-byte aligned).  When given, the
+                                    call also zero-fills every unmasked slot of the four maps (np.zeros_like,
+                                    :415-418) -- and all of sigma for the 2-parameter model -- so the caller
+                                    need not pre-zero them.  2-parameter fast solver with all four maps given and
+                                    16-byte aligned: inside the fit launch itself (every fit thread zeroes a few
+                                    4-voxel words while it waits for its echoes).  Otherwise (3-parameter fits,
+                                    L-BFGS-B solver, very sparse masks, unaligned maps, T2FIT_FILL=stream): a
+                                    kernel on a side stream concurrent with the fit (forked from / joined into
+                                    `stream`; one such call at a time per process, the events are shared).
+                                    NULL = caller zero-fills. */
 } t2fit_outputs;
 
 /* Bind this process to one GPU (one process per GPU; device = LOCAL_RANK) and create its context
