@@ -372,13 +372,13 @@ def run_gpu(args):
     flat_p, idx_p = t2.pinned_array(None, like=flat), t2.pinned_array(None, like=idx)
     e2e_s, r, e2e_windows = time_e2e(flat_p, idx_p, e2e_steps)
     assert np.array_equal(r.t2, t2v), "e2e path and device path disagree"
-    mapped = int(os.environ.get("T2FIT_HOST_THREADS", "16")) < 12 and os.environ.get("T2FIT_HOST_IN", "auto") != "staged"
+    mapped = os.environ.get("T2FIT_HOST_IN", "auto") != "staged"      # page-locked arrays: no staging (run_host_mapped)
     e2e = {"value": m_total * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(m * (n_echo * 4 + 8)),
            "d2h_bytes_per_step": int(m * (4 * 4 + 4 + 1)), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
            "windows_ms_per_step": [round(1e3 * w / e2e_steps, 4) for w in e2e_windows],     # value = the median window
            "path": "fit_voxels_batch(page-locked numpy [N,E], mask_indices) -> numpy results: " +
-                   ("ONE kernel gathers the masked rows straight from host memory over PCIe and stores the results straight "
-                    "back (ranks share the host cores: no staging threads)" if mapped else
+                   ("ONE kernel gathers the masked rows (and the index vector) straight from host memory over PCIe and stores "
+                    "the results straight back into the page-locked numpy result arrays; no staging, no host thread touches the data" if mapped else
                     "threaded gather into pinned staging, H2D per 2.6 MB chunk, fit kernel storing results straight into the "
                     "page-locked numpy result arrays (zero-copy D2H)")}
     # the same call with the pageable arrays a drop-in caller has (np.reshape(...).astype(np.float32), np.where)

@@ -69,7 +69,18 @@ struct KernelIO {
     int64_t fill_words;          // n_vox / 4 full words; the ragged tail is left to thread 0
     int64_t fill_nvox;
     int fill_wpt;                // words per thread (host: ceil(fill_words / launched threads))
+    // > 0: idx comes unchecked from the caller's host memory -- entries outside [0, n_rows) are counted in counts[0] and
+    // read row 0 instead (the host raises IndexError afterwards, as the reference's fancy indexing would)
+    int64_t n_rows;
 };
+
+__device__ __forceinline__ int64_t guarded_row(const KernelIO& io, int64_t row) {
+    if (io.n_rows > 0 && (unsigned long long)row >= (unsigned long long)io.n_rows) {
+        atomicAdd(io.counts, 1ull);
+        row = 0;
+    }
+    return row;
+}
 
 // ------------------------------------------------------------------------------------------------
 // echo loads
@@ -226,7 +237,8 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool valid = i < io.n_fit;
     const int64_t ii = valid ? i : io.n_fit - 1;           // whole warps stay in the solver (warp votes)
-    const int64_t row = io.idx ? __ldg(io.idx + ii) : ii;
+    // (the FILL variant only ever sees device-resident, already checked index vectors)
+    const int64_t row = io.idx ? (FILL ? __ldg(io.idx + ii) : guarded_row(io, __ldg(io.idx + ii))) : ii;
     const int64_t nt = (int64_t)gridDim.x * kBlock;
     uint32_t mw[kGroup];
     if (FILL) {                                            // this thread's mask words: loads in flight beside the index load
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(kQBlock, queue_min_blocks(E)) floor_queue_kern
                 const int64_t cand = (int64_t)base + __popc(m_need & ((1u << lane) - 1u));
                 if (!have && cand < io.n_fit) {
                     i = cand;
-                    row = io.idx ? __ldg(io.idx + i) : i;
+                    row = io.idx ? guarded_row(io, __ldg(io.idx + i)) : i;
                     if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row, io.vec_ok != 0, y);
                     else if (LAYOUT == T2FIT_LAYOUT_SOA) load_soa<E>(io.echoes, io.ld, i, y);
                     else load_soa<E>(io.echoes, io.ld, row, y);
@@ -434,7 +446,7 @@ __global__ void __launch_bounds__(kLbBlock) lbfgsb_kernel(const __grid_constant_
                 const int64_t i = (int64_t)base + __popc(m & ((1u << lane) - 1u));
                 if (i < io.n_fit) {
                     cur = i;
-                    row = io.idx ? __ldg(io.idx + i) : i;
+                    row = io.idx ? guarded_row(io, __ldg(io.idx + i)) : i;
                     float yraw[kMaxEcho];
                     if (io.layout == T2FIT_LAYOUT_AOS) { for (int e = 0; e < E; ++e) yraw[e] = __ldg(io.echoes + row * E + e); }
                     else {
@@ -1017,13 +1029,15 @@ double now_ms() {
 // reads, ~190 k threads in flight hide the latency) and stores the results straight back.  No host thread touches the
 // data, so N ranks on one node do not compete for host cores.  Returns 1 if this path does not apply.
 int run_host_mapped(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitConsts& fc, const lb::LbConsts* lc) {
-    // T2FIT_HOST_IN = mapped | staged | auto (default).  Measured on c2 (profiles/r01_notes.md): with all 16 host cores
-    // to itself the staged pipeline is ~12 % faster (1.35-1.45 ms vs 1.55-1.6 ms per volume); with 8 ranks sharing the
-    // cores it is 1.4x (2 ranks) to 4x (8 ranks) slower.  auto: mapped when this process has fewer than 12 staging threads.
+    // T2FIT_HOST_IN = mapped | staged | auto (default = mapped whenever the arrays are page-locked).  Measured on c2
+    // (profiles/r01_notes.md): 1.16-1.17 ms per volume, call after call, with no host thread touching the data (the kernel
+    // runs at 47 GB/s PCIe reads + 41 GB/s writes); the staged pipeline with all 16 host cores to itself needs 1.35-1.55 ms
+    // with 4 ms outliers, and 1.4x (2 ranks) to 4x (8 ranks) more when ranks share the cores.
     const char* env_in = getenv("T2FIT_HOST_IN");       // read per call (tests switch it)
     const int mode = !env_in ? 0 : !strcmp(env_in, "mapped") ? 1 : !strcmp(env_in, "staged") ? 2 : 0;
-    const bool want = mode == 1 || (mode == 0 && c->workers->size() < 12);
+    const bool want = mode != 2;
     const bool mono = p.model == T2FIT_MODEL_GAUSSIAN;
+    const double t_begin = now_ms();
     if (!want || o.dense || !p.echoes || !is_pinned(p.echoes)) return 1;
     if (o.trace_cap > 0 && (o.trace_f || o.trace_step || o.trace_len)) return 1;
     if (!(is_pinned(o.t2) && is_pinned(o.k) && is_pinned(o.res) && is_pinned(o.fun) && is_pinned(o.nit) && is_pinned(o.status) &&
@@ -1040,15 +1054,8 @@ int run_host_mapped(Context* c, const t2fit_problem& p, t2fit_outputs& o, const 
     if (!st) { int rc0 = ensure_slots(c, p.n_echo); if (rc0) return rc0; st = c->slots[0].stream; }
     const int64_t M = p.n_fit;
     if (p.mask_idx) {
-        // range check (the reference would raise IndexError), all host threads
-        std::atomic<bool> bad{false};
-        c->workers->run([&](int part, int parts) {
-            const int64_t lo = M * part / parts, hi = M * (part + 1) / parts;
-            bool b = false;
-            for (int64_t i = lo; i < hi; ++i) b |= (p.mask_idx[i] < 0) | (p.mask_idx[i] >= p.n_vox);
-            if (b) bad.store(true);
-        });
-        if (bad.load()) return fail(T2FIT_EINVAL, "mask_idx out of range");
+        // no host pass over the index vector: the kernel checks the range itself (KernelIO::n_rows)
+        io.n_rows = p.n_vox;
         void* d_idx = nullptr;
         if (is_pinned(p.mask_idx) && map(p.mask_idx, &d_idx)) {
             io.idx = static_cast<const int64_t*>(d_idx);      // read in place too (measured: 1.6 ms vs 2.35 ms with a DMA copy first)
@@ -1073,14 +1080,16 @@ int run_host_mapped(Context* c, const t2fit_problem& p, t2fit_outputs& o, const 
     io.vec_ok = (reinterpret_cast<uintptr_t>(d_echo) % 16) == 0;
     int rc = lc ? launch_lbfgsb(c, *lc, io, p.model, p.n_echo, st) : launch_fit(c, fc, io, p.model, p.n_echo, p.layout, st);
     if (rc) return rc;
+    const double t_launched = now_ms();
     CU_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), st));
     CU_TRY(cudaStreamSynchronize(st));
+    if (c->h_counts[0] != 0) return fail(T2FIT_EINVAL, "mask_idx out of range");      // IndexError upstream
     int64_t bad_n = 0;
     for (int s = 1; s < 4; ++s) { o.status_count[s] = (int64_t)c->h_counts[s]; bad_n += o.status_count[s]; }
     o.status_count[0] = M - bad_n;
     static const bool profile = getenv("T2FIT_HOST_PROFILE") != nullptr;
-    if (profile) fprintf(stderr, "[t2fit host] M=%lld mapped input (no staging)\n", (long long)M);
+    if (profile) fprintf(stderr, "[t2fit host] M=%lld mapped input (no staging): %.3f ms to launch, %.3f ms in all\n", (long long)M, t_launched - t_begin, now_ms() - t_begin);
     return T2FIT_OK;
 }
 

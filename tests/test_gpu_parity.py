@@ -429,7 +429,8 @@ def test_floor_queue_kernel_equals_one_shot_kernel(gpu_lib, n_echo, layout, refi
     a, b = outs["oneshot"], outs["queue"]
     assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert a[3] == b[3] == [int((a[2] == s_).sum()) for s_ in (1, 2, 3)]
-    assert (a[2] == 1).sum() >= 2 and (a[2] == 3).sum() == 1 and (a[2] == 0).mean() > 0.5 and a[1].max() >= 3
+    assert (a[2] == 1).sum() >= 2 and (a[2] == 3).sum() >= 1 and (a[2] == 0).mean() > 0.5 and a[1].max() >= 3, \
+        [(a[2] == s_).sum() for s_ in range(4)] + [a[1].max()]
 
 
 def test_out_of_range_mask_indices_raise(gpu_lib):
@@ -483,5 +484,9 @@ def test_page_locked_input_needs_no_staging(gpu_lib, fit, solver, monkeypatch):
         sel = slice(None) if ix is not None else idx
         for f in ("t2", "k", "sigma", "res", "fun", "nit", "status"):
             assert np.array_equal(getattr(r, f)[sel], getattr(ref, f)), f
-    with pytest.raises(IndexError):
+    with pytest.raises(IndexError):      # checked by the kernel itself (no host pass over the index vector)
         gpu_lib.fit_voxels_batch(flat_p, np.array([0, flat.shape[0]]), te, fit, fp, prior=False, solver=solver)
+    with pytest.raises(IndexError):
+        gpu_lib.fit_voxels_batch(flat_p, np.array([-1, 3]), te, fit, fp, prior=False, solver=solver)
+    r = gpu_lib.fit_voxels_batch(flat_p, idx, te, fit, fp, prior=False, solver=solver)                      # still usable
+    assert np.array_equal(r.t2, ref.t2) and np.array_equal(r.status, ref.status)
