@@ -110,7 +110,8 @@ SYMBOLS = [
     ("t2fit_work_model", C.c_int, [C.c_int32, C.c_int32] + [C.POINTER(C.c_double)] * 5),
 ]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libt2fit.so")
+# T2FIT_LIB: developer knob, another build of the same library (e.g. an occupancy variant under measurement)
+LIB_PATH = os.environ.get("T2FIT_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libt2fit.so")
 
 _lib = None
 
