@@ -11,7 +11,7 @@ buffers on a copy stream, while the previous volume is being fitted on the compu
     host cast into pinned planes -> H2D (copy stream) -> mask union + label masking -> ordered mask
     indices -> fit + residuals + zero-filled dense maps (one t2fit_run) -> D2H of the four maps
 
-``depth`` staging slots are in flight.  Everything on the device runs through the C ABI
+``depth`` (>= 2, default 3) staging slots are in flight.  Everything on the device runs through the C ABI
 (``t2fit_mask_union``, ``t2fit_mask_indices``, ``t2fit_run``); torch provides pinned memory, streams
 and events only.
 """
@@ -87,7 +87,7 @@ def _torch_dtype(torch, np_dtype):
     return torch.float32
 
 
-def t2map_series(volumes, TEeffs, fit, fit_params, prior=True, norm=False, *, fast=False, solver="auto", depth=2):
+def t2map_series(volumes, TEeffs, fit, fit_params, prior=True, norm=False, *, fast=False, solver="auto", depth=3):
     """Fit a series of subjects/sessions, overlapping each volume's staging with the previous volume's fit.
 
     ``volumes``: iterable of ``(t2w_list, mask_list)`` or ``(t2w_list, mask_list, label)`` -- per-TE recon and
@@ -117,6 +117,42 @@ def t2map_series(volumes, TEeffs, fit, fit_params, prior=True, norm=False, *, fa
         return VolumeMaps(*(maps[i].reshape(s.shape3) for i in range(4)),
                           mask=mk.reshape(s.shape3).view(np.bool_), n_fit=s.n_fit, failed=nonfinite + gave_up)
 
+    def launch(s):
+        """Device part of a staged volume: mask union (+ label), ordered indices, fit into zero-filled dense maps, D2H."""
+        n_vox = s.n_vox
+        compute.wait_event(s.copied)
+        cs = compute.cuda_stream
+        planes = (C.c_void_p * n_echo)(*[s.d_masks[e].data_ptr() for e in range(n_echo)])
+        dt_code = _abi.DTYPES[str(s.d_masks.dtype).replace("torch.", "")]
+        l_code = _abi.DTYPES[str(s.d_label.dtype).replace("torch.", "")] if s.has_label else 0
+        _abi.check(lib, lib.t2fit_mask_union(planes, n_echo, dt_code, s.d_label.data_ptr() if s.has_label else None, l_code,
+                                             n_vox, s.d_mask.data_ptr(), cs), "t2fit_mask_union")
+        n = C.c_int64()
+        # returns the count, i.e. waits for this volume's H2D -- which has had the staging time of the NEXT volume to finish
+        _abi.check(lib, lib.t2fit_mask_indices(s.d_mask.data_ptr(), n_vox, 1, s.d_idx.data_ptr(), C.byref(n), cs),
+                   "t2fit_mask_indices")
+        s.n_fit = int(n.value)
+        p, o = _abi.Problem(), _abi.Outputs()
+        keep = _fill_problem(p, fit, fit_params, te, prior, norm, 0, 0.0, "loglinear", solver)
+        p.echoes, p.memory, p.layout, p.ld = s.d_planes.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_PLANES, n_vox
+        p.mask_idx, p.n_vox, p.n_fit = s.d_idx.data_ptr(), n_vox, s.n_fit
+        o.t2, o.k, o.sigma, o.res = (s.d_maps[i].data_ptr() for i in range(4))
+        o.dense, o.zero_fill_mask = 1, s.d_mask.data_ptr()
+        o.status = s.d_status.data_ptr()
+        _run(lib, p, o, cs)
+        del keep
+        with torch.cuda.stream(compute):
+            st = s.d_status[:s.n_fit]
+            s.h_cnt.copy_(torch.stack([(st == 1).sum(), (st == 2).sum(), (st == 3).sum()]), non_blocking=True)
+            s.h_maps.copy_(s.d_maps, non_blocking=True)
+            s.h_mask.copy_(s.d_mask, non_blocking=True)
+            s.done.record(compute)
+        pending.append(s)
+
+    # Software pipeline over the volumes: volume v is staged (host cast into page-locked planes, H2D enqueued on the copy
+    # stream) BEFORE the device part of volume v-1 is launched, so the one host wait of the device part (the voxel count of
+    # t2fit_mask_indices) meets an H2D that finished while v was being staged, and v's H2D overlaps the fit and D2H of v-1.
+    staged = None                  # the slot whose H2D is enqueued but whose device part has not been launched yet
     for item in volumes:
         t2w_list, mask_list = item[0], item[1]
         label = item[2] if len(item) > 2 else None
@@ -129,10 +165,13 @@ def t2map_series(volumes, TEeffs, fit, fit_params, prior=True, norm=False, *, fa
         key = (n_vox, m_dt, l_dt)
         ring = slots.setdefault(key, [])
         s = next((x for x in ring if not x.busy), None)
-        if s is None and len(ring) < depth:
+        if s is None and len(ring) < max(2, depth):
             s = _Slot(torch, dev, n_echo, n_vox, m_dt, l_dt)
             ring.append(s)
         while s is None:                                   # all slots of this shape in flight: drain the oldest
+            if not pending:
+                launch(staged)
+                staged = None
             yield finish(pending.pop(0))
             s = next((x for x in ring if not x.busy), None)
         s.busy, s.shape3 = True, shape3
@@ -154,35 +193,13 @@ def t2map_series(volumes, TEeffs, fit, fit_params, prior=True, norm=False, *, fa
             if s.has_label:
                 s.d_label.copy_(s.h_label, non_blocking=True)
             s.copied.record(copy_stream)
-        # ---- device: mask union (+ label), ordered indices, fit into zero-filled dense maps, D2H
-        compute.wait_event(s.copied)
-        cs = compute.cuda_stream
-        planes = (C.c_void_p * n_echo)(*[s.d_masks[e].data_ptr() for e in range(n_echo)])
-        dt_code = _abi.DTYPES[str(m_dt).replace("torch.", "")]
-        l_code = _abi.DTYPES[str(l_dt).replace("torch.", "")] if s.has_label else 0
-        _abi.check(lib, lib.t2fit_mask_union(planes, n_echo, dt_code, s.d_label.data_ptr() if s.has_label else None, l_code,
-                                             n_vox, s.d_mask.data_ptr(), cs), "t2fit_mask_union")
-        n = C.c_int64()
-        _abi.check(lib, lib.t2fit_mask_indices(s.d_mask.data_ptr(), n_vox, 1, s.d_idx.data_ptr(), C.byref(n), cs),
-                   "t2fit_mask_indices")
-        s.n_fit = int(n.value)
-        p, o = _abi.Problem(), _abi.Outputs()
-        keep = _fill_problem(p, fit, fit_params, te, prior, norm, 0, 0.0, "loglinear", solver)
-        p.echoes, p.memory, p.layout, p.ld = s.d_planes.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_PLANES, n_vox
-        p.mask_idx, p.n_vox, p.n_fit = s.d_idx.data_ptr(), n_vox, s.n_fit
-        o.t2, o.k, o.sigma, o.res = (s.d_maps[i].data_ptr() for i in range(4))
-        o.dense, o.zero_fill_mask = 1, s.d_mask.data_ptr()
-        o.status = s.d_status.data_ptr()
-        _run(lib, p, o, cs)
-        del keep
-        with torch.cuda.stream(compute):
-            st = s.d_status[:s.n_fit]
-            s.h_cnt.copy_(torch.stack([(st == 1).sum(), (st == 2).sum(), (st == 3).sum()]), non_blocking=True)
-            s.h_maps.copy_(s.d_maps, non_blocking=True)
-            s.h_mask.copy_(s.d_mask, non_blocking=True)
-            s.done.record(compute)
-        pending.append(s)
-        while len(pending) >= depth:
+        # ---- device part of the PREVIOUS volume
+        if staged is not None:
+            launch(staged)
+        staged = s
+        while len(pending) >= max(2, depth):
             yield finish(pending.pop(0))
+    if staged is not None:
+        launch(staged)
     while pending:
         yield finish(pending.pop(0))
