@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_ECHO = 32
 
 MODEL_GAUSSIAN = 0
@@ -22,6 +22,8 @@ LAYOUT_AOS = 0
 LAYOUT_SOA = 1
 LAYOUT_PLANES = 2
 DTYPES = {"uint8": 0, "int16": 1, "uint16": 2, "int32": 3, "float32": 4, "float64": 5, "bool": 0}
+# element types a HOST echo array may have (t2fit_problem.echo_dtype; 0 = float32)
+ECHO_DTYPES = {"float32": 0, "int16": 1, "uint16": 2, "int32": 3, "float64": 5}
 MEM_HOST = 0
 MEM_DEVICE = 1
 
@@ -61,6 +63,7 @@ class Problem(C.Structure):
         ("lbfgsb_maxls", C.c_int32),
         ("lbfgsb_maxiter", C.c_int32),
         ("lbfgsb_maxfun", C.c_int32),
+        ("echo_dtype", C.c_int32),
     ]
 
 

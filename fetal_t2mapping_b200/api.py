@@ -75,6 +75,18 @@ def work_model(fit: str, n_echo: int):
     return {k: x.value for k, x in zip(keys, v)}
 
 
+def _host_echoes(y, p):
+    """The host echo array as the library takes it.  The reference casts the whole volume (`.astype(np.float32)`,
+    run_t2mapping.py:411); a C-contiguous int16 / uint16 / int32 / float64 array -- what the NIfTI reader returns -- is
+    passed as it is instead and cast by the library while it gathers the masked rows (t2fit_problem.echo_dtype)."""
+    code = _abi.ECHO_DTYPES.get(y.dtype.name)
+    if code is None or not y.flags.c_contiguous:
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        code = 0
+    p.echo_dtype = code
+    return y
+
+
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
@@ -305,9 +317,7 @@ def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=
         stream = torch.cuda.current_stream(y.device).cuda_stream
         keep += [y, idx]
     else:
-        y = np.asarray(reshaped_t2w)
-        if y.dtype != np.float32 or not y.flags.c_contiguous:
-            y = np.ascontiguousarray(y, dtype=np.float32)           # .astype(np.float32) of :411
+        y = _host_echoes(np.asarray(reshaped_t2w), p)
         if y.ndim != 2:
             raise ValueError("reshaped_t2w must be [N, E]")
         n_vox, n_echo = y.shape
@@ -437,12 +447,10 @@ def t2map_volume(t2w, mask, TEeffs, fit, fit_params, prior=True, norm=False, **k
         mp = [maps[i].data_ptr() for i in range(4)]
         keep += [y, idx, mk]
     else:
-        y = np.reshape(np.asarray(t2w), (-1, n_echo))
-        if y.dtype != np.float32 or not y.flags.c_contiguous:
-            y = np.ascontiguousarray(y, dtype=np.float32)                               # :411
+        y = _host_echoes(np.reshape(np.asarray(t2w), (-1, n_echo)), p)                  # :411
         mk = np.asarray(mask)
-        mk = (np.sum(mk, axis=3) > 0) if mk.ndim == 4 else (mk > 0)                     # :383-384
-        idx = np.flatnonzero(mk.reshape(-1)).astype(np.int64)                           # :412,:421
+        mk = (np.sum(mk, axis=3) > 0) if mk.ndim == 4 else (mk if mk.dtype == np.bool_ else mk > 0)    # :383-384
+        idx = np.flatnonzero(mk.reshape(-1)).astype(np.int64, copy=False)               # :412,:421
         n_vox, m = y.shape[0], idx.size
         maps = np.zeros((4, n_vox), np.float32)                                         # :415-418
         p.echoes, p.memory, p.mask_idx = y.ctypes.data, _abi.MEM_HOST, idx.ctypes.data

@@ -1013,6 +1013,30 @@ int launch_zero_fill(Context* c, const FillArgs& fa, bool sigma_all, cudaStream_
 // next chunk (run-aware memcpy: consecutive mask indices are contiguous rows) while the GPU works on
 // the previous ones; per chunk ONE H2D copy, one kernel, and either direct D2H copies into the caller's
 // arrays (when those are page-locked) or one D2H into pinned staging + a threaded unpack / scatter.
+// Host echo arrays may hold int16 / uint16 / int32 / float64 elements (t2fit_problem::echo_dtype): the reference's
+// `.astype(np.float32)` (:411) is applied while the fitted rows are gathered into the float32 staging buffers.
+template <typename T>
+inline void cast_copy(float* dst, const T* src, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) dst[i] = (float)src[i];
+}
+inline size_t echo_elem_size(int dt) {
+    return dt == T2FIT_DT_F64 ? 8 : (dt == T2FIT_DT_I16 || dt == T2FIT_DT_U16) ? 2 : 4;
+}
+inline void echo_copy(float* dst, const void* base, int dt, int64_t off, int64_t n) {
+    switch (dt) {
+        case T2FIT_DT_I16: cast_copy(dst, static_cast<const int16_t*>(base) + off, n); break;
+        case T2FIT_DT_U16: cast_copy(dst, static_cast<const uint16_t*>(base) + off, n); break;
+        case T2FIT_DT_I32: cast_copy(dst, static_cast<const int32_t*>(base) + off, n); break;
+        case T2FIT_DT_F64: cast_copy(dst, static_cast<const double*>(base) + off, n); break;
+        default: memcpy(dst, static_cast<const float*>(base) + off, sizeof(float) * n); break;
+    }
+}
+inline float echo_at(const void* base, int dt, int64_t off) {
+    float v;
+    echo_copy(&v, base, dt, off, 1);
+    return v;
+}
+
 bool is_pinned(const void* p) {
     if (!p) return true;
     cudaPointerAttributes at{};
@@ -1041,6 +1065,7 @@ int run_host_mapped(Context* c, const t2fit_problem& p, t2fit_outputs& o, const 
     const bool mono = p.model == T2FIT_MODEL_GAUSSIAN;
     const double t_begin = now_ms();
     if (!want || o.dense || !p.echoes || !is_pinned(p.echoes)) return 1;
+    if (p.echo_dtype != 0 && p.echo_dtype != T2FIT_DT_F32) return 1;      // the kernels read float32: other element types are staged (cast)
     if (o.trace_cap > 0 && (o.trace_f || o.trace_step || o.trace_len)) return 1;
     if (!(is_pinned(o.t2) && is_pinned(o.k) && is_pinned(o.res) && is_pinned(o.fun) && is_pinned(o.nit) && is_pinned(o.status) &&
           (mono || is_pinned(o.sigma)))) return 1;
@@ -1131,6 +1156,7 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
     const int64_t n_chunks = (M + kChunk - 1) / kChunk;
     const bool mono = p.model == T2FIT_MODEL_GAUSSIAN;
     std::atomic<bool> bad_index{false};
+    const int edt = p.echo_dtype == T2FIT_DT_F32 ? 0 : p.echo_dtype;     // 0 = float32
     // compact results can go straight into the caller's arrays if every one of them is page-locked
     // How compact results reach the caller's arrays (T2FIT_HOST_OUT overrides, for measurements):
     //   zerocopy  every result array is page-locked: the kernel stores straight into host memory through its device
@@ -1197,9 +1223,9 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
         c->workers->run([&](int part, int parts) {
             const int64_t lo = n * part / parts, hi = n * (part + 1) / parts;
             if (hi <= lo) return;
-            if (p.layout == T2FIT_LAYOUT_AOS) {   // rows -> packed rows [n, E]; runs of consecutive indices in one memcpy
+            if (p.layout == T2FIT_LAYOUT_AOS) {   // rows -> packed rows [n, E]; runs of consecutive indices in one copy (+ cast)
                 if (!p.mask_idx) {
-                    memcpy(s.h_in + lo * E, p.echoes + (first + lo) * E, sizeof(float) * E * (hi - lo));
+                    echo_copy(s.h_in + lo * E, p.echoes, edt, (first + lo) * E, (int64_t)E * (hi - lo));
                 } else {
                     const int64_t* idx = p.mask_idx + first;
                     int64_t i = lo;
@@ -1207,13 +1233,13 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
                         int64_t j = i + 1;
                         while (j < hi && idx[j] == idx[j - 1] + 1) ++j;
                         if (idx[i] < 0 || idx[j - 1] >= p.n_vox) { bad_index.store(true); return; }   // IndexError upstream
-                        memcpy(s.h_in + i * E, p.echoes + idx[i] * E, sizeof(float) * E * (j - i));
+                        echo_copy(s.h_in + i * E, p.echoes, edt, idx[i] * E, (int64_t)E * (j - i));
                         i = j;
                     }
                 }
             } else if (p.layout == T2FIT_LAYOUT_SOA) {   // SoA planes [E, ld] -> planes [E, n]
                 for (int e = 0; e < E; ++e)
-                    memcpy(s.h_in + (int64_t)e * n + lo, p.echoes + (int64_t)e * p.ld + first + lo, sizeof(float) * (hi - lo));
+                    echo_copy(s.h_in + (int64_t)e * n + lo, p.echoes, edt, (int64_t)e * p.ld + first + lo, hi - lo);
             } else {                              // per-TE volumes [E, ld >= n_vox] -> planes [E, n] of the masked voxels
                 const int64_t* idx = p.mask_idx ? p.mask_idx + first : nullptr;
                 for (int64_t i = lo; i < hi; ++i) {
@@ -1221,10 +1247,11 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
                     if (v < 0 || v >= p.n_vox) { bad_index.store(true); return; }
                 }
                 for (int e = 0; e < E; ++e) {
-                    const float* src = p.echoes + (int64_t)e * p.ld;
+                    const int64_t plane = (int64_t)e * p.ld;
                     float* dst = s.h_in + (int64_t)e * n;
-                    if (idx) for (int64_t i = lo; i < hi; ++i) dst[i] = src[idx[i]];
-                    else memcpy(dst + lo, src + first + lo, sizeof(float) * (hi - lo));
+                    if (!idx) echo_copy(dst + lo, p.echoes, edt, plane + first + lo, hi - lo);
+                    else if (edt == 0) { const float* src = p.echoes + plane; for (int64_t i = lo; i < hi; ++i) dst[i] = src[idx[i]]; }
+                    else for (int64_t i = lo; i < hi; ++i) dst[i] = echo_at(p.echoes, edt, plane + idx[i]);
                 }
             }
         });
@@ -1414,6 +1441,10 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     if (p->layout == T2FIT_LAYOUT_PLANES && p->ld < p->n_vox) return fail(T2FIT_EINVAL, "ld < n_vox");
     if (p->layout != T2FIT_LAYOUT_SOA && !p->mask_idx && p->n_fit > p->n_vox) return fail(T2FIT_EINVAL, "n_fit > n_vox");
     if (o->dense && !p->mask_idx && p->n_fit > p->n_vox) return fail(T2FIT_EINVAL, "dense output needs n_vox >= n_fit");
+    const bool f32 = p->echo_dtype == 0 || p->echo_dtype == T2FIT_DT_F32;
+    if (!f32 && p->echo_dtype != T2FIT_DT_I16 && p->echo_dtype != T2FIT_DT_U16 && p->echo_dtype != T2FIT_DT_I32 && p->echo_dtype != T2FIT_DT_F64)
+        return fail(T2FIT_EINVAL, "bad echo_dtype");
+    if (!f32 && p->memory != T2FIT_MEM_HOST) return fail(T2FIT_EINVAL, "device-memory echoes must be float32");
     CU_TRY(cudaSetDevice(c->device));
     if (p->memory == T2FIT_MEM_HOST) return run_host(c, *p, *o, fc, lbs ? &lc : nullptr);
     if (p->memory != T2FIT_MEM_DEVICE) return fail(T2FIT_EINVAL, "bad memory kind");

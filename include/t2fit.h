@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define T2FIT_ABI_VERSION 2
+#define T2FIT_ABI_VERSION 3
 #define T2FIT_MAX_ECHO 32
 
 /* return codes */
@@ -102,6 +102,11 @@ typedef struct t2fit_problem {
        0 selects scipy's default: ftol 2.220446049250313e-09, gtol 1e-5, maxls 20, maxiter = maxfun = 15000. */
     double lbfgsb_ftol, lbfgsb_gtol;
     int32_t lbfgsb_maxls, lbfgsb_maxiter, lbfgsb_maxfun;
+    /* Element type of `echoes` for T2FIT_MEM_HOST calls: 0 = float32 (default), or T2FIT_DT_I16 / _U16 / _I32 / _F64 --
+       the volume as it comes out of the NIfTI reader.  The `.astype(np.float32)` of the reference (:411) then happens
+       while the masked rows are gathered into the staging buffers: only the n_fit fitted rows are cast, not all n_vox.
+       Device-memory calls take float32 only. */
+    int32_t echo_dtype;
 } t2fit_problem;
 
 /* Results.  Any pointer may be NULL (that output is skipped).  Parameter maps follow the reference's

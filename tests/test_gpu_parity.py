@@ -433,6 +433,52 @@ def test_floor_queue_kernel_equals_one_shot_kernel(gpu_lib, n_echo, layout, refi
         [(a[2] == s_).sum() for s_ in range(4)] + [a[1].max()]
 
 
+@pytest.mark.parametrize("dtype", ["float64", "int16", "uint16", "int32"])
+@pytest.mark.parametrize("fit", ["gaussian", "gaussian_rician"])
+def test_host_volume_dtypes_are_cast_while_gathering(gpu_lib, dtype, fit):
+    """`.astype(np.float32)` of the reference (:411) fused into the host gather: a float64 / integer host volume gives,
+    bit for bit, what its float32 copy gives -- through fit_voxels_batch and through t2map_volume."""
+    from fetal_t2mapping_b200 import synth
+    y, mask, te, _ = synth.make_volume("c1", scale=0.4)
+    vol = np.abs(y) + 1.0
+    vol = (vol.astype(np.float64) * (1.0 + 1e-9)) if dtype == "float64" else np.round(vol).astype(dtype)
+    flat = vol.reshape(-1, te.size)
+    idx = np.flatnonzero(mask.reshape(-1))
+    _, fp = gpu_lib.preset(fit, True)
+    ref = gpu_lib.fit_voxels_batch(flat.astype(np.float32), idx, te, fit, fp, prior=False, solver="fast")
+    got = gpu_lib.fit_voxels_batch(flat, idx, te, fit, fp, prior=False, solver="fast")
+    for f in ("t2", "k", "sigma", "res", "fun", "nit", "status"):
+        assert np.array_equal(getattr(got, f), getattr(ref, f)), f
+    all_rows = gpu_lib.fit_voxels_batch(flat, None, te, fit, fp, prior=False, solver="fast")      # no index vector
+    assert np.array_equal(all_rows.t2[idx], ref.t2)
+    m_ref = gpu_lib.t2map_volume(vol.astype(np.float32), mask, te, fit, fp, prior=False, solver="fast")
+    m_got = gpu_lib.t2map_volume(vol, mask, te, fit, fp, prior=False, solver="fast")
+    for a, b in zip(m_got, m_ref):
+        assert np.array_equal(a, b)
+    assert np.array_equal(m_got[0].reshape(-1)[idx], ref.t2)
+
+
+def test_device_echoes_must_be_float32(gpu_lib):
+    import ctypes as C
+    import torch
+    from fetal_t2mapping_b200 import _abi
+    from fetal_t2mapping_b200.api import _fill_problem
+    _, fp = gpu_lib.preset("gaussian", True)
+    lib = gpu_lib.init()
+    p, o = _abi.Problem(), _abi.Outputs()
+    keep = _fill_problem(p, "gaussian", fp, [114.0, 202.0, 299.0], False, False, 0, 0.0, "loglinear")
+    y = torch.ones((8, 3), device="cuda")
+    out = torch.empty(8, device="cuda")
+    p.echoes, p.memory, p.layout, p.n_vox, p.n_fit = y.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_AOS, 8, 8
+    p.echo_dtype = _abi.ECHO_DTYPES["float64"]
+    o.t2 = out.data_ptr()
+    assert lib.t2fit_run(C.byref(p), C.byref(o), None) == -1 and b"float32" in lib.t2fit_last_error()
+    p.echo_dtype = 77
+    p.memory = _abi.MEM_HOST
+    assert lib.t2fit_run(C.byref(p), C.byref(o), None) == -1
+    del keep
+
+
 def test_out_of_range_mask_indices_raise(gpu_lib):
     y = np.ones((10, 3), np.float32)
     _, fp = gpu_lib.preset("gaussian", True)
