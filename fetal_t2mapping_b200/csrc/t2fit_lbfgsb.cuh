@@ -470,8 +470,10 @@ struct Solver {
         } else {
             upcl = col;
         }
-        // old parts of blocks (1,1) and (2,2): variables that entered / left the free set
-        T2_ROLLED for (int iy = 0; iy < upcl; ++iy) {
+        // old parts of blocks (1,1) and (2,2): variables that entered / left the free set.  With an unchanged free set
+        // (the usual case) every correction below is +0 - 0: the two sweeps over WN1 are skipped.
+        const int upcl_old = (nenter > 0 || ileave < N) ? upcl : 0;
+        T2_ROLLED for (int iy = 0; iy < upcl_old; ++iy) {
             const int is = kM + iy, ipntr = (head + iy) % kM;
             T2_ROLLED for (int jy = 0; jy <= iy; ++jy) {
                 const int js = kM + jy, jpntr = (head + jy) % kM;
@@ -491,7 +493,7 @@ struct Solver {
             }
         }
         // old part of block (2,1)
-        T2_ROLLED for (int is0 = 0; is0 < upcl; ++is0) {
+        T2_ROLLED for (int is0 = 0; is0 < upcl_old; ++is0) {
             const int is = kM + is0, ipntr = (head + is0) % kM;
             T2_ROLLED for (int jy = 0; jy < upcl; ++jy) {
                 const int jpntr = (head + jy) % kM;
