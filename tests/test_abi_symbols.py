@@ -52,6 +52,28 @@ def test_struct_layout_matches_header(tmp_path):
             assert int(got[f"{st}.{f}"]) == getattr(cls, f).offset, f"{st}.{f}"
 
 
+def test_dtype_codes_match_header():
+    """The element-type codes of the ctypes mirror are the T2FIT_DT_* values of the header; host echo arrays map to them
+    (float32 = 0 = default) and anything else is cast to float32 by the mirror."""
+    import numpy as np
+    from fetal_t2mapping_b200.api import _host_echoes
+    hdr = open(os.path.join(ROOT, "include", "t2fit.h")).read()
+    codes = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define T2FIT_DT_(\w+) (\d+)", hdr)}
+    names = {"U8": "uint8", "I16": "int16", "U16": "uint16", "I32": "int32", "F32": "float32", "F64": "float64"}
+    assert {names[k]: v for k, v in codes.items()} == {k: v for k, v in _abi.DTYPES.items() if k != "bool"}
+    for name, code in _abi.ECHO_DTYPES.items():
+        assert code == (0 if name == "float32" else _abi.DTYPES[name])
+    for dt in ("float32", "float64", "int16", "uint16", "int32"):
+        p = _abi.Problem()
+        a = np.arange(12, dtype=dt).reshape(4, 3)
+        b = _host_echoes(a, p)
+        assert b is a and p.echo_dtype == _abi.ECHO_DTYPES[dt]
+    for a in (np.arange(12, dtype=np.uint8).reshape(4, 3), np.arange(24, dtype=np.float64).reshape(4, 6)[:, ::2]):
+        p = _abi.Problem()
+        b = _host_echoes(a, p)                                  # unsupported type / not contiguous: cast as the reference does
+        assert b.dtype == np.float32 and b.flags.c_contiguous and p.echo_dtype == 0 and np.array_equal(b, a)
+
+
 def test_library_contains_sm100a_sass_only():
     out = os.popen(f"cuobjdump -lelf {_abi.LIB_PATH} 2>/dev/null").read()
     if not out.strip():
