@@ -407,6 +407,41 @@ def run_gpu(args):
         except Exception as ex:              # secondary number: never lose the headline line over it
             lbfgsb = {"error": repr(ex)}
 
+    # the 3-parameter fast solver (floor_queue_kernel) on a slab of BASELINE config 5 (unmasked, 16 TE, Rician data made on the
+    # device): secondary number, outside the timed region, rank 0 only
+    floor3 = None
+    if not args.no_lbfgsb and rank == 0:
+        try:
+            n5, e5 = 1 << 22, 16
+            te5 = np.linspace(100, 700, e5)
+            g5 = torch.Generator(device=dev).manual_seed(4)
+            t5 = torch.exp(torch.empty(n5, device=dev).uniform_(np.log(10.0), np.log(2000.0), generator=g5))
+            a5 = torch.empty(n5, device=dev).uniform_(300.0, 3000.0, generator=g5)
+            s5 = a5[:, None] * torch.exp(-torch.tensor(te5, device=dev, dtype=torch.float32)[None, :] / t5[:, None])
+            y5 = torch.sqrt((s5 + torch.randn((n5, e5), device=dev, generator=g5) * 20.0) ** 2 +
+                            (torch.randn((n5, e5), device=dev, generator=g5) * 20.0) ** 2)
+            del s5, a5
+            fp5 = t2.preset("gaussian_rician", True)[1]
+            best5 = 1e30
+            for _ in range(3):
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
+                r5 = t2.fit_voxels_batch(y5, None, te5, "gaussian_rician", fp5, prior=False, norm=False, solver="fast", check_bounds=False)
+                g1.record(stream)
+                torch.cuda.synchronize()
+                best5 = min(best5, g0.elapsed_time(g1))
+            ok5 = r5.status == 0
+            rel5 = (r5.t2[ok5] - t5[ok5]).abs() / t5[ok5]
+            floor3 = {"fits_per_s": n5 / (best5 * 1e-3), "ms": best5, "voxels": n5, "n_echo": e5,
+                      "mean_accepted_iterations": float(r5.nit.float().mean()), "not_converged": float((~ok5).float().mean()),
+                      "median_rel_error_vs_true_t2": float(rel5.median()),
+                      "workload": "slab of BASELINE config 5: unmasked, 16 TE 100..700 ms, T2 log-uniform 10..2000 ms, Rician sigma 20, "
+                                  "gaussian_rician LF preset --no_prior",
+                      "kernel": "floor_queue_kernel<16,AoS> (persistent grid, lanes pull voxels from a queue)", "dtype": "f32"}
+            del y5, t5, r5
+        except Exception as ex:              # secondary number: never lose the headline line over it
+            floor3 = {"error": repr(ex)}
+
     # Delta-T2 against the reference's scipy fit (BASELINE metric): the voxels the CPU arm just fitted, refitted by both CUDA solvers
     parity = None
     if cpu_rows is not None:
@@ -511,7 +546,7 @@ def run_gpu(args):
                            "zero_fill": ("inside the fit launch: every fit thread zeroes a few 4-voxel words of the dense maps" if fill_in_fit else
                                          "zero_fill_kernel on a side stream, concurrent with fit_kernel" if fused else "torch zero_() before the fit launch")},
                 "roofline": roofline, "roofline_fp32": roof_fp32, "roofline_hbm": roof_hbm, "cpu_baseline": cpu_baseline,
-                "solver_lbfgsb": lbfgsb, "parity": parity, "e2e": e2e, "gpu_launches": int(args.steps) * (2 if (fused and not fill_in_fit) else 1), "clocks": clocks, "final_gather": final_gather, "fused_gather": fused_gather,
+                "solver_lbfgsb": lbfgsb, "solver_floor3_fast": floor3, "parity": parity, "e2e": e2e, "gpu_launches": int(args.steps) * (2 if (fused and not fill_in_fit) else 1), "clocks": clocks, "final_gather": final_gather, "fused_gather": fused_gather,
                 "device": info["name"]}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -37,6 +37,7 @@
 #include <vector>
 
 #include "t2fit_consts.h"
+#include "t2fit_workers.h"
 
 using namespace t2fit;
 
@@ -773,54 +774,6 @@ int fail(int code, const std::string& msg) { tl_err = msg; return code; }
     } while (0)
 
 // minimal fork-join pool for the host-memory path (pack / unpack of staging chunks)
-class Workers {
-  public:
-    explicit Workers(int n) : n_(std::max(1, n)) {
-        for (int t = 1; t < n_; ++t) threads_.emplace_back([this, t] { loop(t); });
-    }
-    ~Workers() {
-        { std::lock_guard<std::mutex> g(m_); stop_ = true; ++gen_; }
-        cv_.notify_all();
-        for (auto& t : threads_) t.join();
-    }
-    int size() const { return n_; }
-    // fn(part, n_parts) on every worker, caller included; returns when all are done
-    void run(const std::function<void(int, int)>& fn) {
-        { std::lock_guard<std::mutex> g(m_); fn_ = &fn; pending_ = n_ - 1; ++gen_; }
-        cv_.notify_all();
-        fn(0, n_);
-        std::unique_lock<std::mutex> l(m_);
-        done_cv_.wait(l, [this] { return pending_ == 0; });
-        fn_ = nullptr;
-    }
-
-  private:
-    void loop(int t) {
-        uint64_t seen = 0;
-        for (;;) {
-            const std::function<void(int, int)>* fn;
-            {
-                std::unique_lock<std::mutex> l(m_);
-                cv_.wait(l, [&] { return gen_ != seen; });
-                seen = gen_;
-                if (stop_) return;
-                fn = fn_;
-            }
-            if (fn) (*fn)(t, n_);
-            { std::lock_guard<std::mutex> g(m_); --pending_; }
-            done_cv_.notify_one();
-        }
-    }
-    int n_;
-    std::vector<std::thread> threads_;
-    std::mutex m_;
-    std::condition_variable cv_, done_cv_;
-    const std::function<void(int, int)>* fn_ = nullptr;
-    uint64_t gen_ = 0;
-    int pending_ = 0;
-    bool stop_ = false;
-};
-
 constexpr int kSlots = 3;
 // voxels per staging chunk (T2FIT_HOST_CHUNK overrides, for tuning)
 // Sized by BYTES, not voxels: measured on the B200 boxes (profiles/r01_notes.md), per-chunk transfers of ~2.6 MB pipeline
