@@ -69,7 +69,7 @@ struct KernelIO {
     const uint8_t* fill_mask;    // dense [n_vox] mask, 4-byte aligned
     int64_t fill_words;          // n_vox / 4 full words; the ragged tail is left to thread 0
     int64_t fill_nvox;
-    int fill_wpt;                // words per thread (host: ceil(fill_words / launched threads))
+    int fill_wpb;                // mask words per block (host: ceil(fill_words / blocks), rounded up to whole 128-byte lines of the maps)
     // > 0: idx comes unchecked from the caller's host memory -- entries outside [0, n_rows) are counted in counts[0] and
     // read row 0 instead (the host raises IndexError afterwards, as the reference's fancy indexing would)
     int64_t n_rows;
@@ -242,14 +242,16 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
     const int64_t ii = valid ? i : io.n_fit - 1;           // whole warps stay in the solver (warp votes)
     // (the FILL variant only ever sees device-resident, already checked index vectors)
     const int64_t row = io.idx ? (FILL ? __ldg(io.idx + ii) : guarded_row(io, __ldg(io.idx + ii))) : ii;
-    const int64_t nt = (int64_t)gridDim.x * kBlock;
+    // FILL: block b owns the contiguous window of fill_wpb mask words starting at b * fill_wpb (one window per map and block:
+    // few concurrent write streams); thread t takes words t, t + 256, ... of the window
+    const int64_t w0 = (int64_t)blockIdx.x * io.fill_wpb;
     uint32_t mw[kGroup];
     if (FILL) {                                            // this thread's mask words: loads in flight beside the index load
         const uint32_t* pm = reinterpret_cast<const uint32_t*>(io.fill_mask);
 #pragma unroll
         for (int g = 0; g < kGroup; ++g) {
-            const int64_t w = i + g * nt;
-            mw[g] = (g < io.fill_wpt && w < io.fill_words) ? __ldg(pm + w) : 0x01010101u;
+            const int lw = (int)threadIdx.x + g * kBlock;
+            mw[g] = (lw < io.fill_wpb && w0 + lw < io.fill_words) ? __ldg(pm + w0 + lw) : 0x01010101u;
         }
     }
     float y[E];
@@ -259,21 +261,21 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
     if (FILL) {                                            // zero stores go out while the echoes are on their way
 #pragma unroll
         for (int g = 0; g < kGroup; ++g) {
-            const int64_t w = i + g * nt;
-            if (g < io.fill_wpt && w < io.fill_words) fill_word<MODEL>(io, w, mw[g]);
+            const int lw = (int)threadIdx.x + g * kBlock;
+            if (lw < io.fill_wpb && w0 + lw < io.fill_words) fill_word<MODEL>(io, w0 + lw, mw[g]);
         }
 #pragma unroll 1
-        for (int g0 = kGroup; g0 < io.fill_wpt; g0 += kGroup) {     // sparse masks: more words than one group per thread
+        for (int g0 = kGroup; g0 * kBlock < io.fill_wpb; g0 += kGroup) {     // sparse masks: more words than one group per thread
             const uint32_t* pm = reinterpret_cast<const uint32_t*>(io.fill_mask);
 #pragma unroll
             for (int g = 0; g < kGroup; ++g) {
-                const int64_t w = i + (g0 + g) * nt;
-                mw[g] = (g0 + g < io.fill_wpt && w < io.fill_words) ? __ldg(pm + w) : 0x01010101u;
+                const int lw = (int)threadIdx.x + (g0 + g) * kBlock;
+                mw[g] = (lw < io.fill_wpb && w0 + lw < io.fill_words) ? __ldg(pm + w0 + lw) : 0x01010101u;
             }
 #pragma unroll
             for (int g = 0; g < kGroup; ++g) {
-                const int64_t w = i + (g0 + g) * nt;
-                if (g0 + g < io.fill_wpt && w < io.fill_words) fill_word<MODEL>(io, w, mw[g]);
+                const int lw = (int)threadIdx.x + (g0 + g) * kBlock;
+                if (lw < io.fill_wpb && w0 + lw < io.fill_words) fill_word<MODEL>(io, w0 + lw, mw[g]);
             }
         }
         if (i == 0) {                                               // ragged tail of the volume (n_vox % 4 voxels)
@@ -862,15 +864,15 @@ int ensure_slots(Context* c, int n_echo) {
     return T2FIT_OK;
 }
 
-// Mask words per fit thread if the fit launch can take the zero-fill of the dense maps on, else 0: all four maps
-// present and 16-byte aligned, AoS / PLANES input, and no more than a handful of words per thread (a sparse mask --
-// few fit threads for a large volume -- leaves the fill to the side-stream kernel).
-int fused_fill_wpt(const FillArgs& fa, int64_t n_fit, int layout) {
+// Mask words per block if the fit launch can take the zero-fill of the dense maps on, else 0: all four maps present and
+// 16-byte aligned, AoS / PLANES input, and no more than a handful of words per thread (a sparse mask -- few fit threads for a
+// large volume -- leaves the fill to the side-stream kernel).  Rounded up to 8 words = whole 128-byte lines of every map.
+int fused_fill_wpb(const FillArgs& fa, int64_t n_fit, int layout) {
     if (!(fa.vec && fa.t2 && fa.k && fa.res && fa.sigma) || layout == T2FIT_LAYOUT_SOA || n_fit <= 0) return 0;
     const int64_t blocks = (n_fit + kBlock - 1) / kBlock;
-    const int64_t words = fa.n_vox / 4, threads = blocks * kBlock;
-    const int64_t wpt = std::max<int64_t>(1, (words + threads - 1) / threads);
-    return wpt <= kFusedFillMaxWpt ? (int)wpt : 0;
+    const int64_t words = fa.n_vox / 4;
+    const int64_t wpb = std::max<int64_t>(8, (((words + blocks - 1) / blocks) + 7) & ~(int64_t)7);
+    return wpb <= (int64_t)kFusedFillMaxWpt * kBlock ? (int)wpb : 0;
 }
 
 int launch_floor_queue(Context* c, const FitConsts& fc, const KernelIO& io, int n_echo, int layout, cudaStream_t st) {
@@ -899,7 +901,7 @@ int launch_floor_queue(Context* c, const FitConsts& fc, const KernelIO& io, int 
     return T2FIT_OK;
 }
 
-// fa (may be null): dense maps to zero-fill in the same launch; the caller has checked fused_fill_wpt() > 0.
+// fa (may be null): dense maps to zero-fill in the same launch; the caller has checked fused_fill_wpb() > 0.
 int launch_fit(Context* c, const FitConsts& fc, KernelIO io, int model, int n_echo, int layout, cudaStream_t st,
                const FillArgs* fa = nullptr) {
     if (io.n_fit <= 0) return T2FIT_OK;
@@ -912,9 +914,9 @@ int launch_fit(Context* c, const FitConsts& fc, KernelIO io, int model, int n_ec
     if (blocks > 0x7fffffffLL) return fail(T2FIT_EINVAL, "n_fit too large for one launch");
     if (fa) {
         io.fill_mask = fa->mask; io.fill_words = fa->n_vox / 4; io.fill_nvox = fa->n_vox;
-        io.fill_wpt = fused_fill_wpt(*fa, io.n_fit, layout);
+        io.fill_wpb = fused_fill_wpb(*fa, io.n_fit, layout);
         io.sigma = fa->sigma;
-        if (io.fill_wpt <= 0) return fail(T2FIT_EINVAL, "internal: fused fill not applicable");
+        if (io.fill_wpb <= 0) return fail(T2FIT_EINVAL, "internal: fused fill not applicable");
     }
     FitFn fn = pick_kernel(model, n_echo, layout, fa != nullptr);
     if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
@@ -1426,7 +1428,7 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
         for (float* q : mp) if (q && (reinterpret_cast<uintptr_t>(q) % 16) != 0) fa.vec = 0;
         const char* env_fill = getenv("T2FIT_FILL");      // fused (default) | stream; read per call (tests switch it)
         const bool want_fused = !lbs && p->model == T2FIT_MODEL_GAUSSIAN && p->n_fit > 0 && !(env_fill && !strcmp(env_fill, "stream"));
-        if (want_fused && fused_fill_wpt(fa, p->n_fit, p->layout) > 0)
+        if (want_fused && fused_fill_wpb(fa, p->n_fit, p->layout) > 0)
             return launch_fit(c, fc, io, p->model, p->n_echo, p->layout, st, &fa);
         rc = launch_zero_fill(c, fa, p->model == T2FIT_MODEL_GAUSSIAN, st, &forked);
         if (rc) return rc;

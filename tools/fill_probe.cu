@@ -76,7 +76,7 @@ int main() {
         float ms; cudaEventElapsedTime(&ms, a, b);
         printf("variant %d grid %5d: %7.2f us  (%.2f TB/s of 268 MB)\n", v, grid, ms / 20 * 1e3, 268.4e6 / (ms / 20 * 1e-3) / 1e12);
     };
-    for (int v = 0; v < 4; ++v) for (int grid : {148, 296, 592, 1184, 4096}) run(v, grid);
+    for (int v = 0; v < 4; ++v) for (int grid : {148, 296, 592, 1184, 4096, 6328, 16384}) run(v, grid);
     for (int it = 0; it < 3; ++it) cudaMemsetAsync(maps, 0, 4 * n * sizeof(float));
     cudaEventRecord(a);
     for (int it = 0; it < 20; ++it) cudaMemsetAsync(maps, 0, 4 * n * sizeof(float));
