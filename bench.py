@@ -11,8 +11,11 @@ zero the four dense maps, fit every masked voxel, residual epilogue, scatter int
 plus convergence flags / iteration counts / final errors per voxel.
 
   value     whole-job fits/s with the volume already resident in HBM (AoS [N,E] float32 + mask_indices)
-  e2e       same metric through fit_voxels_batch() with HOST numpy buffers: pack, H2D, fit, D2H inside
-  roofline  the fit kernel alone, CUDA events around each launch inside the timed region
+  e2e       same metric through fit_voxels_batch() with HOST (page-locked) numpy buffers, host<->device traffic inside
+  roofline  the step launch (fit + zero-fill of the dense maps in one kernel) against the measured HBM peak: algorithmic
+            bytes / step time from CUDA events over the timed region; roofline_fp32: the plain fit launch alone
+            (events around each launch) against the FP32 / MUFU peaks
+  solver_lbfgsb / solver_floor3_fast / parity   secondary blocks outside the timed region
   cpu_baseline  the oracle port (scipy L-BFGS-B exactly as the reference drives it) on a bounded sample
 N > 1: weak scaling, one volume-sized slab of masked voxels per rank, no data-path collective; the
 final NCCL gather of the parameter maps is timed separately ("final_gather").
