@@ -37,6 +37,7 @@
 #include <vector>
 
 #include "t2fit_consts.h"
+#include "t2fit_lbfgsb_coop.cuh"
 #include "t2fit_workers.h"
 
 using namespace t2fit;
@@ -474,6 +475,89 @@ __global__ void __launch_bounds__(kLbBlock) lbfgsb_kernel(const __grid_constant_
         if (run.active) {
             run.pass(c);
             if (!run.active) lb_store<OBJ>(c, io, run, cur, row);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lbfgsb_coop_kernel: the same reference-faithful solver with ONE VOXEL PER GROUP OF G LANES and the optimiser state in
+// SHARED MEMORY (t2fit_lbfgsb_coop.cuh).  Persistent blocks, one per SM, as many groups as fit into the 227 KB of shared
+// memory (~7.6 KB per voxel); every group pulls its next voxel from the global queue as soon as its current one has
+// terminated.  The groups of a warp run the same code: where they are in the same phase they share its instructions,
+// where they are not (different iteration counts, different numbers of correction pairs) the warp pays the longest of
+// them, not the sum.  No block-level barrier anywhere: groups only ever synchronise among their own lanes.
+// ------------------------------------------------------------------------------------------------
+template <int OBJ, int G>
+__global__ void __launch_bounds__(G == 8 ? 256 : G == 16 ? 512 : 1024, 1) lbfgsb_coop_kernel(const __grid_constant__ lb::LbConsts c,
+                                                            const __grid_constant__ KernelIO io,
+                                                            unsigned long long* __restrict__ queue, const int stride_bytes) {
+    extern __shared__ __align__(16) unsigned char coop_smem[];
+    using Run = lb::CoopRun<OBJ, G>;
+    const int gi = threadIdx.x / G;
+    Run* run = reinterpret_cast<Run*>(coop_smem + (size_t)gi * stride_bytes);
+    lb::Group<G> grp;
+    grp.lane = threadIdx.x % G;
+    grp.mask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (((threadIdx.x & 31) / G) * G));
+    const int E = c.n_echo;
+    bool have = false, exhausted = false;
+    long long cur = -1, row = 0;
+    for (;;) {
+        if (!have && !exhausted) {
+            long long i = 0;
+            if (grp.master()) i = (long long)atomicAdd(queue, 1ull);
+            i = grp.shfl(i, 0);
+            if (i < io.n_fit) {
+                cur = i;
+                row = io.idx ? __ldg(io.idx + i) : i;
+                if (io.n_rows > 0 && (unsigned long long)row >= (unsigned long long)io.n_rows) {      // unchecked host index vector
+                    if (grp.master()) atomicAdd(io.counts, 1ull);
+                    row = 0;
+                }
+                for (int e = grp.lane; e < E; e += G) {
+                    float v;
+                    if (io.layout == T2FIT_LAYOUT_AOS) v = __ldg(io.echoes + row * E + e);
+                    else v = __ldg(io.echoes + (int64_t)e * io.ld + (io.layout == T2FIT_LAYOUT_SOA ? i : row));
+                    run->yraw[e] = v;
+                }
+                grp.sync();
+                const bool tr = io.trace_cap > 0;
+                run->start(grp, c, (tr && io.trace_f) ? io.trace_f + i * io.trace_cap : nullptr,
+                           (tr && io.trace_step) ? io.trace_step + i * io.trace_cap : nullptr, tr ? io.trace_cap : 0);
+                have = true;
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!have) break;                                   // queue empty and nothing in flight: this group is done
+        if (run->active) run->pass(grp, c);
+        if (!run->active) {
+            // epilogue as lb_store: float32(x) into the maps, residual from those stored values; the echo terms across the
+            // lanes, their sum on the master lane in the serial order
+            const float kf = (float)run->s.x[0], t2f = (float)run->s.x[1], sf = (OBJ == 0) ? 0.f : (float)run->s.x[OBJ == 0 ? 0 : 2];
+            double* term = run->s.scr.fterm;
+            for (int e = grp.lane; e < E; e += G) {
+                double pred = (double)kf * exp(-c.te[e] / (double)t2f);
+                if (OBJ != 0) pred = sqrt(pred * pred + (double)sf * (double)sf);
+                term[e] = (double)run->y[e] - (double)(float)pred;
+            }
+            grp.sync();
+            if (grp.master()) {
+                const lb::LbVoxel v = run->finish();
+                double acc = 0.0;
+                for (int e = 0; e < E; ++e) acc += term[e];
+                const int64_t o = io.dense ? row : cur;
+                if (io.t2) io.t2[o] = t2f;
+                if (io.k) io.k[o] = kf;
+                if (OBJ != 0 && io.sigma) io.sigma[o] = sf;
+                if (io.res) io.res[o] = (float)(acc / (double)E);
+                if (io.fun) io.fun[cur] = (float)v.fun;
+                if (io.nit) io.nit[cur] = v.nit;
+                if (io.status) io.status[cur] = (uint8_t)v.status;
+                if (io.trace_len) io.trace_len[cur] = v.trace_len;
+                if (v.status != 0 && io.counts) atomicAdd(io.counts + v.status, 1ull);
+            }
+            grp.sync();
+            have = false;
         }
     }
 }
@@ -925,8 +1009,16 @@ int launch_fit(Context* c, const FitConsts& fc, KernelIO io, int model, int n_ec
     return T2FIT_OK;
 }
 
+int launch_lbfgsb_coop(Context* c, const lb::LbConsts& lc, const KernelIO& io, int model, int lanes, cudaStream_t st);
+
 int launch_lbfgsb(Context* c, const lb::LbConsts& lc, KernelIO io, int model, int n_echo, cudaStream_t st) {
     if (io.n_fit <= 0) return T2FIT_OK;
+    if (n_echo < 2 || n_echo > kMaxEcho) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
+    // T2FIT_LB_KERNEL = coop8 (default) | coop16 | coop32 | thread: lane group per voxel with the state in shared memory, or the
+    // one-thread-per-voxel kernel with the state in local memory (read per call: tests and A/B runs switch it)
+    const char* ek = getenv("T2FIT_LB_KERNEL");
+    const int lanes = !ek ? 8 : !strcmp(ek, "coop8") ? 8 : !strcmp(ek, "coop16") ? 16 : !strcmp(ek, "coop32") ? 32 : 0;
+    if (lanes) return launch_lbfgsb_coop(c, lc, io, model, lanes, st);
     LbFn fn = pick_lb_kernel(model, n_echo);
     if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
     // persistent grid sized to what is resident at once; voxels are handed out through a queue counter
@@ -941,6 +1033,52 @@ int launch_lbfgsb(Context* c, const lb::LbConsts& lc, KernelIO io, int model, in
     unsigned long long* q = c->d_queue + (c->queue_next++ % kQueues);
     CU_TRY(cudaMemsetAsync(q, 0, sizeof(unsigned long long), st));
     fn<<<grid, kLbBlock, 0, st>>>(lc, io, q);
+    CU_TRY(cudaGetLastError());
+    return T2FIT_OK;
+}
+
+// cooperative form: one block per SM, as many lane groups as the shared memory holds
+using LbCoopFn = void (*)(const lb::LbConsts, const KernelIO, unsigned long long*, const int);
+
+template <int G>
+LbCoopFn pick_lb_coop(int model, size_t* run_bytes) {
+    if (model == T2FIT_MODEL_GAUSSIAN) { *run_bytes = sizeof(lb::CoopRun<0, G>); return lbfgsb_coop_kernel<0, G>; }
+    if (model == T2FIT_MODEL_GAUSSIAN_RICIAN) { *run_bytes = sizeof(lb::CoopRun<1, G>); return lbfgsb_coop_kernel<1, G>; }
+    *run_bytes = sizeof(lb::CoopRun<2, G>);
+    return lbfgsb_coop_kernel<2, G>;
+}
+
+int launch_lbfgsb_coop(Context* c, const lb::LbConsts& lc, const KernelIO& io, int model, int lanes, cudaStream_t st) {
+    size_t run_bytes = 0;
+    LbCoopFn fn = lanes == 8 ? pick_lb_coop<8>(model, &run_bytes) : lanes == 16 ? pick_lb_coop<16>(model, &run_bytes)
+                                                                                 : pick_lb_coop<32>(model, &run_bytes);
+    // per-voxel stride: a multiple of 16 bytes and = 8 (mod 16) in 8-byte words, so that the two groups of a half-warp
+    // (G = 8) hit different banks when they read the same element of their own state
+    size_t words = (run_bytes + 7) / 8;
+    words += (8 + 16 - (words % 16)) % 16;
+    const int stride = (int)(words * 8);
+    const int smem_max = (int)c->prop.sharedMemPerBlockOptin;
+    const int per_warp = 32 / lanes;
+    int groups = (smem_max / stride) / per_warp * per_warp;
+    groups = std::min(groups, 1024 / lanes);
+    static const int env_groups = [] { const char* e = getenv("T2FIT_LB_GROUPS"); return e ? atoi(e) : 0; }();
+    if (env_groups > 0) groups = std::min(groups, env_groups / per_warp * per_warp);
+    if (groups < per_warp) return fail(T2FIT_EINVAL, "shared memory too small for the cooperative L-BFGS-B kernel");
+    const int smem = groups * stride;
+    static std::mutex mu;
+    static std::vector<LbCoopFn> prepared;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (std::find(prepared.begin(), prepared.end(), fn) == prepared.end()) {
+            CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+            prepared.push_back(fn);
+        }
+    }
+    const int64_t want = (io.n_fit + groups - 1) / groups;
+    const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)c->prop.multiProcessorCount);
+    unsigned long long* q = c->d_queue + (c->queue_next++ % kQueues);
+    CU_TRY(cudaMemsetAsync(q, 0, sizeof(unsigned long long), st));
+    fn<<<grid, groups * lanes, smem, st>>>(lc, io, q, stride);
     CU_TRY(cudaGetLastError());
     return T2FIT_OK;
 }

@@ -137,41 +137,48 @@ T2_NI double i0e(double x) {
 // ---------------------------------------------------------------------------------------------
 // The echo count is a run-time value here (one kernel per objective): the optimiser core, not the
 // objective, dominates the cost of this solver.
+// One echo's term of the objective at parameters p (shared by the thread-per-voxel and the cooperative kernels, which
+// evaluate the echoes of one objective call on different lanes: the per-call quantities k^2, sigma^2, log(sigma^2) are
+// recomputed per echo, deterministically the same values).
+template <int OBJ>
+T2_HD double objective_term(const double* p, float y, double te) {
+    if constexpr (OBJ == 0) {                                   // gauss_obj :141-147
+        const double k = p[0], t2 = p[1];
+        const double m = mul(k, exp((-te) / t2));                    // k * np.exp(-t / t2)
+        const double r = sub((double)y, m);
+        return mul(r, r);
+    } else if constexpr (OBJ == 1) {                            // gauss_rician_obj :149-155
+        const double k2 = mul(p[0], p[0]), t2 = p[1], s2 = mul(p[2], p[2]);
+        const double m = sqrt(add(mul(k2, exp(mul(-2.0, te) / t2)), s2));
+        const double r = sub((double)y, m);
+        return mul(r, r);
+    } else {                                                    // rician_obj :157-177 (negative log-likelihood)
+        const double k = p[0], t2 = p[1], s2 = mul(p[2], p[2]);
+        const double ls2 = log(s2), ts2 = mul(2.0, s2);
+        const double m = mul(k, exp((-te) / t2));
+        const double x = mul(m, (double)y) / s2;
+        const float lg = logf(y);                                   // np.log(float32) stays float32
+        const float y2 = mulf(y, y);                                // signal**2 stays float32
+        const double a = sub((double)lg, ls2);
+        const double b = add((double)y2, mul(m, m)) / ts2;
+        const double cc = add(fabs(x), log(i0e(x)));
+        return add(sub(a, b), cc);
+    }
+}
+
+// np.sum of the E terms and the final scaling (mean for the two least-squares objectives, negated sum for the NLL)
+template <int OBJ>
+T2_HD double objective_reduce(const double* v, int E) {
+    if constexpr (OBJ == 2) return -np_sum(v, E);
+    else return np_sum(v, E) / (double)E;
+}
+
 template <int OBJ>
 T2_NI double objective(const double* p, const float* y32, const LbConsts& c) {
     const int E = c.n_echo;
     double v[kMaxEcho];
-    if constexpr (OBJ == 0) {                                   // gauss_obj :141-147
-        const double k = p[0], t2 = p[1];
-        for (int e = 0; e < E; ++e) {
-            const double m = mul(k, exp((-c.te[e]) / t2));           // k * np.exp(-t / t2)
-            const double r = sub((double)y32[e], m);
-            v[e] = mul(r, r);
-        }
-        return np_sum(v, E) / (double)E;
-    } else if constexpr (OBJ == 1) {                            // gauss_rician_obj :149-155
-        const double k2 = mul(p[0], p[0]), t2 = p[1], s2 = mul(p[2], p[2]);
-        for (int e = 0; e < E; ++e) {
-            const double m = sqrt(add(mul(k2, exp(mul(-2.0, c.te[e]) / t2)), s2));
-            const double r = sub((double)y32[e], m);
-            v[e] = mul(r, r);
-        }
-        return np_sum(v, E) / (double)E;
-    } else {                                                    // rician_obj :157-177 (negative log-likelihood)
-        const double k = p[0], t2 = p[1], s2 = mul(p[2], p[2]);
-        const double ls2 = log(s2), ts2 = mul(2.0, s2);
-        for (int e = 0; e < E; ++e) {
-            const double m = mul(k, exp((-c.te[e]) / t2));
-            const double x = mul(m, (double)y32[e]) / s2;
-            const float lg = logf(y32[e]);                          // np.log(float32) stays float32
-            const float y2 = mulf(y32[e], y32[e]);                  // signal**2 stays float32
-            const double a = sub((double)lg, ls2);
-            const double b = add((double)y2, mul(m, m)) / ts2;
-            const double cc = add(fabs(x), log(i0e(x)));
-            v[e] = add(sub(a, b), cc);
-        }
-        return -np_sum(v, E);
-    }
+    for (int e = 0; e < E; ++e) v[e] = objective_term<OBJ>(p, y32[e], c.te[e]);
+    return objective_reduce<OBJ>(v, E);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -793,6 +800,16 @@ struct Solver {
         fold = dnorm = dtd = gd = gdold = stp = stpmx = sbgnrm = 0.0;
         iter = ifun = iback = nfgv = 0;
         result = kRunning;
+        // scipy hands setulb a zero-initialised workspace for every minimize() call (wa = zeros(...)), and the algorithm
+        // does read entries it never computed: formk adds only the NEWEST pair's row / column to WN1, so a pair stored
+        // while formk was skipped (no free variable at the Cauchy point) leaves its row unset, and the Cauchy search
+        // returns before clearing c when no variable moves.  Without this the result of a voxel depended on the voxel
+        // the thread had fitted before (1 of 1500 voxels of the c3 fixture).
+        T2_ROLLED for (int i = 0; i < M2; ++i) { T2_ROLLED for (int j = 0; j < M2; ++j) { wn1[i][j] = 0.0; wn[i][j] = 0.0; } pc[i] = 0.0; cc[i] = 0.0; }
+        T2_ROLLED for (int i = 0; i < kM; ++i) {
+            T2_ROLLED for (int j = 0; j < kM; ++j) { sy[i][j] = 0.0; ss[i][j] = 0.0; wt[i][j] = 0.0; }
+            T2_ROLLED for (int j = 0; j < N; ++j) { ws[i][j] = 0.0; wy[i][j] = 0.0; }
+        }
     }
 
     // f, g at the start point have been evaluated

@@ -11,32 +11,41 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libt2fit_hostsim.so")
 SRC = os.path.join(HERE, "hostsim.cpp")
 DEPS = [SRC] + [os.path.join(HERE, "..", "..", "fetal_t2mapping_b200", "csrc", f)
-                for f in ("t2fit_core.cuh", "t2fit_consts.h", "t2fit_lbfgsb.cuh", "t2fit_i0e_coeffs.h")] + [os.path.join(HERE, "..", "..", "include", "t2fit.h")]
+                for f in ("t2fit_core.cuh", "t2fit_consts.h", "t2fit_lbfgsb.cuh", "t2fit_lbfgsb_coop.cuh", "t2fit_i0e_coeffs.h")] + \
+    [os.path.join(HERE, "lane_emu.h")] + [os.path.join(HERE, "..", "..", "include", "t2fit.h")]
 
 
-def build(force=False):
-    if not force and os.path.isfile(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in DEPS):
-        return SO
-    # -mfma + contraction: the device fuses a*b+c, so cancellation noise (e.g. D - k*C at a converged
-    # point) is as small on the host simulation as on the GPU
-    cmd = ["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=fast", "-shared", "-fPIC", "-x", "c++", SRC, "-o", SO, "-lm"]
+SO_STRICT = os.path.join(HERE, "libt2fit_hostsim_strict.so")
+
+
+def build(force=False, strict=False):
+    """strict=False: -mfma + contraction, as the device fuses a*b+c (cancellation noise, e.g. D - k*C at a converged point,
+    is then as small on the host simulation as on the GPU).  strict=True: no contraction at all -- every product and sum
+    rounds separately whatever the expression shape, so two implementations that perform the same operations in the same
+    order agree BIT FOR BIT (the serial and the cooperative L-BFGS-B solver, tests/test_hostsim_coop.py)."""
+    so = SO_STRICT if strict else SO
+    if not force and os.path.isfile(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in DEPS):
+        return so
+    fp = ["-ffp-contract=off"] if strict else ["-mfma", "-ffp-contract=fast"]
+    cmd = ["g++", "-O2", "-std=c++17"] + fp + ["-shared", "-fPIC", "-x", "c++", SRC, "-o", so, "-lm"]
     subprocess.run(cmd, check=True, cwd=HERE)
-    return SO
+    return so
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(build())
-        _lib.hostsim_fit.restype = C.c_int
-        _lib.hostsim_last_error.restype = C.c_char_p
-        _lib.hostsim_lbfgsb.restype = C.c_int
-        _lib.hostsim_i0e.restype = C.c_double
-        _lib.hostsim_i0e.argtypes = [C.c_double]
-    return _lib
+def lib(strict=False):
+    if strict not in _libs:
+        l = C.CDLL(build(strict=strict))
+        l.hostsim_fit.restype = C.c_int
+        l.hostsim_last_error.restype = C.c_char_p
+        l.hostsim_lbfgsb.restype = C.c_int
+        l.hostsim_lbfgsb_coop.restype = C.c_int
+        l.hostsim_i0e.restype = C.c_double
+        l.hostsim_i0e.argtypes = [C.c_double]
+        _libs[strict] = l
+    return _libs[strict]
 
 
 def make_problem(rows, te, fit, x0, bounds, prior, norm, max_iter=0, tol=0.0, init=0, options=None):
@@ -84,8 +93,10 @@ def fit(rows, te, fit, x0, bounds, prior, norm=False, use_double=False, **kw):
     return out
 
 
-def lbfgsb(rows, te, fit, x0, bounds, prior, norm=False, options=None, trace_cap=0, tol=0.0):
-    """The reference-faithful solver (csrc/t2fit_lbfgsb.cuh) compiled for the host."""
+def lbfgsb(rows, te, fit, x0, bounds, prior, norm=False, options=None, trace_cap=0, tol=0.0, strict=False, coop_lanes=0,
+           reverse=False):
+    """The reference-faithful solver compiled for the host: the serial form (csrc/t2fit_lbfgsb.cuh) or, with
+    ``coop_lanes`` = 4 / 8 / 16 / 32, the cooperative form (csrc/t2fit_lbfgsb_coop.cuh) on the lane emulator."""
     p, keep = make_problem(rows, te, fit, x0, bounds, prior, norm, options=options or {}, tol=tol)
     m = keep[0].shape[0]
     out = {"x": np.zeros((m, 3), np.float64), "fun": np.zeros(m, np.float64), "nit": np.zeros(m, np.int32),
@@ -94,10 +105,14 @@ def lbfgsb(rows, te, fit, x0, bounds, prior, norm=False, options=None, trace_cap
     ts = np.full((m, max(trace_cap, 1)), np.nan, np.float32)
     tl = np.zeros(m, np.int32)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib().hostsim_lbfgsb(C.byref(p), vp(out["x"]), vp(out["fun"]), vp(out["nit"]), vp(out["nfev"]), vp(out["status"]),
-                              vp(out["result"]), vp(tf) if trace_cap else None, vp(ts) if trace_cap else None, vp(tl),
-                              C.c_int(trace_cap))
+    args = (vp(out["x"]), vp(out["fun"]), vp(out["nit"]), vp(out["nfev"]), vp(out["status"]), vp(out["result"]),
+            vp(tf) if trace_cap else None, vp(ts) if trace_cap else None, vp(tl), C.c_int(trace_cap))
+    L = lib(strict)
+    if coop_lanes:
+        rc = L.hostsim_lbfgsb_coop(C.byref(p), C.c_int(coop_lanes), C.c_int(int(reverse)), *args)
+    else:
+        rc = L.hostsim_lbfgsb(C.byref(p), *args)
     if rc:
-        raise ValueError(lib().hostsim_last_error().decode())
+        raise ValueError(L.hostsim_last_error().decode())
     out["trace_f"], out["trace_step"], out["trace_len"] = tf, ts, tl
     return out

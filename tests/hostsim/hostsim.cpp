@@ -7,8 +7,11 @@
 // not a fallback: the product fails loudly without a CUDA device.
 #define T2FIT_HOSTSIM 1
 #include "../../fetal_t2mapping_b200/csrc/t2fit_consts.h"
+#include "../../fetal_t2mapping_b200/csrc/t2fit_lbfgsb_coop.cuh"
 
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string>
 
 using namespace t2fit;
@@ -66,6 +69,7 @@ static int dispatch_lb(int n_echo, const float* rows, int64_t m, const lb::LbCon
                        int trace_cap) {
     for (int64_t i = 0; i < m; ++i) {
         lb::VoxelRun<OBJ> run;
+        memset((void*)&run, 0xA5, sizeof(run));            // stale memory of the previous voxel: nothing may depend on it
         run.start(rows + i * n_echo, c, trace_f ? trace_f + i * trace_cap : nullptr,
                   trace_step ? trace_step + i * trace_cap : nullptr, (trace_f || trace_step) ? trace_cap : 0);
         while (run.active) run.pass(c);
@@ -91,3 +95,62 @@ extern "C" int hostsim_lbfgsb(const t2fit_problem* p, double* x, double* fun, in
 }
 
 extern "C" double hostsim_i0e(double x) { return lb::i0e(x); }
+
+// ------------------------------------------------------------------------------------------------
+// cooperative (lane-group-per-voxel) form of the same solver on the lane emulator: G fibers per voxel, lanes scheduled
+// forwards (reverse = 0) or backwards (reverse = 1) between barriers
+// ------------------------------------------------------------------------------------------------
+template <int OBJ, int G>
+static int dispatch_lb_coop(int n_echo, const float* rows, int64_t m, const lb::LbConsts& c, int reverse, double* x, double* fun,
+                            int32_t* nit, int32_t* nfev, uint8_t* status, int32_t* result, float* trace_f, float* trace_step,
+                            int32_t* trace_len, int trace_cap) {
+    auto* run = new lb::CoopRun<OBJ, G>();
+    emu::Lanes em(G, reverse != 0);
+    for (int64_t i = 0; i < m; ++i) {
+        memset((void*)run, 0xA5, sizeof(*run));          // stale shared memory of the previous voxel: nothing may depend on it
+        for (int e = 0; e < n_echo; ++e) run->yraw[e] = rows[i * n_echo + e];
+        float* tf = trace_f ? trace_f + i * trace_cap : nullptr;
+        float* ts = trace_step ? trace_step + i * trace_cap : nullptr;
+        const int cap = (trace_f || trace_step) ? trace_cap : 0;
+        em.run([&](int lane) {
+            lb::Group<G> grp;
+            grp.lane = lane; grp.em = &em;
+            run->start(grp, c, tf, ts, cap);
+            while (run->active) run->pass(grp, c);
+        });
+        const lb::LbVoxel v = run->finish();
+        x[3 * i] = v.x[0]; x[3 * i + 1] = v.x[1]; x[3 * i + 2] = v.x[2];
+        fun[i] = v.fun; nit[i] = v.nit; nfev[i] = v.nfev; status[i] = (uint8_t)v.status; result[i] = v.result;
+        if (trace_len) trace_len[i] = v.trace_len;
+    }
+    delete run;
+    return 0;
+}
+
+template <int G>
+static int dispatch_lb_coop_g(const t2fit_problem* p, const lb::LbConsts& c, int reverse, double* x, double* fun, int32_t* nit,
+                              int32_t* nfev, uint8_t* status, int32_t* result, float* trace_f, float* trace_step,
+                              int32_t* trace_len, int trace_cap) {
+    switch (p->model) {
+        case T2FIT_MODEL_GAUSSIAN: return dispatch_lb_coop<0, G>(p->n_echo, p->echoes, p->n_fit, c, reverse, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+        case T2FIT_MODEL_GAUSSIAN_RICIAN: return dispatch_lb_coop<1, G>(p->n_echo, p->echoes, p->n_fit, c, reverse, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+        default: return dispatch_lb_coop<2, G>(p->n_echo, p->echoes, p->n_fit, c, reverse, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+    }
+}
+
+extern "C" int hostsim_lbfgsb_coop(const t2fit_problem* p, int lanes, int reverse, double* x, double* fun, int32_t* nit,
+                                   int32_t* nfev, uint8_t* status, int32_t* result, float* trace_f, float* trace_step,
+                                   int32_t* trace_len, int trace_cap) {
+    lb::LbConsts c;
+    memset(&c, 0, sizeof(c));
+    int rc = make_lb_consts(*p, c, g_err);
+    if (rc) return rc;
+    if (c.fd_step < 0.0) { g_err = "the cooperative solver has no analytic-gradient hook"; return T2FIT_EINVAL; }
+    switch (lanes) {
+        case 4: return dispatch_lb_coop_g<4>(p, c, reverse, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+        case 8: return dispatch_lb_coop_g<8>(p, c, reverse, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+        case 16: return dispatch_lb_coop_g<16>(p, c, reverse, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+        case 32: return dispatch_lb_coop_g<32>(p, c, reverse, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+        default: g_err = "lanes must be 4, 8, 16 or 32"; return T2FIT_EINVAL;
+    }
+}
