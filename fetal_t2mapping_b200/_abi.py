@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_ECHO = 32
 
 MODEL_GAUSSIAN = 0
@@ -24,11 +24,12 @@ LAYOUT_PLANES = 2
 DTYPES = {"uint8": 0, "int16": 1, "uint16": 2, "int32": 3, "float32": 4, "float64": 5, "bool": 0}
 # element types a HOST echo array may have (t2fit_problem.echo_dtype; 0 = float32)
 ECHO_DTYPES = {"float32": 0, "int16": 1, "uint16": 2, "int32": 3, "float64": 5}
+IDX_I64, IDX_I32 = 0, 1
 MEM_HOST = 0
 MEM_DEVICE = 1
 
 ST_OK, ST_NONFINITE, ST_NOTCONVERGED, ST_BADBOUNDS = 0, 1, 2, 3
-INIT_LOGLINEAR, INIT_PRESET = 0, 1
+INIT_LOGLINEAR, INIT_PRESET, INIT_BEST = 0, 1, 2
 
 ERRORS = {0: "OK", -1: "EINVAL", -2: "ENODEVICE", -3: "ENOTINIT", -4: "ECUDA", -5: "ENOMEM"}
 
@@ -64,6 +65,7 @@ class Problem(C.Structure):
         ("lbfgsb_maxiter", C.c_int32),
         ("lbfgsb_maxfun", C.c_int32),
         ("echo_dtype", C.c_int32),
+        ("idx_dtype", C.c_int32),
     ]
 
 
@@ -84,6 +86,7 @@ class Outputs(C.Structure):
         ("trace_len", C.c_void_p),
         ("trace_cap", C.c_int32),
         ("zero_fill_mask", C.c_void_p),
+        ("counts_dev", C.c_void_p),
     ]
 
 

@@ -25,7 +25,7 @@ import numpy as np
 from . import _abi
 from .presets import NO_PRIOR_K_UB, NO_PRIOR_T2_BOUNDS
 
-__all__ = ["fit_voxels_batch", "fit_voxels_into", "t2map_volume", "compute_residuals", "FitResult", "init", "shutdown", "device_info",
+__all__ = ["fit_voxels_batch", "fit_voxels_into", "check_counts", "t2map_volume", "compute_residuals", "FitResult", "init", "shutdown", "device_info",
            "mask_indices_device", "work_model", "pinned_array", "BOUNDS_ERROR"]
 
 BOUNDS_ERROR = "An upper bound is less than the corresponding lower bound."   # scipy's text
@@ -202,6 +202,22 @@ class FitResult:
         return [(r[i], bool(ok[i]), int(nit[i]), float(fun[i]), infos[i]) for i in range(r.shape[0])]
 
 
+def _device_counts(torch, device):
+    """[4] zeroed int64 device counters for ONE device-memory call (t2fit_outputs.counts_dev): slot 0 = mask indices out
+    of range, 1..3 = voxels per non-OK status.  Every call of the mirror owns its counters, so nothing leaks between calls
+    or streams."""
+    return torch.zeros(4, dtype=torch.int64, device=device)
+
+
+def _raise_for_counts(cnt):
+    """What the reference does for such voxels: numpy's fancy indexing raises IndexError for an index outside the array,
+    scipy raises ValueError for lb > ub inside the first such voxel and pool.map aborts the whole map."""
+    if cnt[0] > 0:
+        raise IndexError("mask_indices out of range")
+    if cnt[3] > 0:
+        raise ValueError(BOUNDS_ERROR)
+
+
 def resolve_solver(fit, solver):
     """``auto``: the float32 Newton/LM kernels for 'gaussian' (they reach the bounded minimiser the reference's
     ftol=1e-6 run approaches); the reference's own optimiser (L-BFGS-B restated in FP64) for 'gaussian_rician' and
@@ -249,7 +265,9 @@ def _fill_problem(p, fit, fit_params, TEeffs, prior, norm, max_iter, tol, init_m
     p.norm = int(bool(norm))
     p.max_iter = int(max_iter)
     p.tol = float(tol)
-    p.init = {"loglinear": _abi.INIT_LOGLINEAR, "preset": _abi.INIT_PRESET}[init_mode]
+    if init_mode == "auto":                # 3-parameter fast solver: multi-start (several local minima); 2-parameter: log-linear
+        init_mode = "best" if fit != "gaussian" else "loglinear"
+    p.init = {"loglinear": _abi.INIT_LOGLINEAR, "preset": _abi.INIT_PRESET, "best": _abi.INIT_BEST}[init_mode]
     return te      # keep alive
 
 
@@ -265,7 +283,7 @@ def _run(lib, p, o, stream):
 
 
 def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=True, norm=False, *,
-                     solver="auto", trace_cap=0, max_iter=0, tol=0.0, init_mode="loglinear", check_bounds=True,
+                     solver="auto", trace_cap=0, max_iter=0, tol=0.0, init_mode="auto", check_bounds=True,
                      dense_out=None, want=("nit", "fun", "status")) -> FitResult:
     """Fit every voxel ``mask_indices[i]`` of ``reshaped_t2w`` (float32 ``[N, E]``, run_t2mapping.py:411).
 
@@ -295,9 +313,11 @@ def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=
         idx = mask_indices
         if idx is not None:
             if not _is_torch(idx):
-                idx = torch.as_tensor(np.ascontiguousarray(idx, dtype=np.int64), device=y.device)
-            if idx.dtype != torch.int64 or not idx.is_contiguous():
+                idx = np.asarray(idx)
+                idx = torch.as_tensor(np.ascontiguousarray(idx, dtype=np.int32 if idx.dtype == np.int32 else np.int64), device=y.device)
+            if idx.dtype not in (torch.int64, torch.int32) or not idx.is_contiguous():
                 idx = idx.to(torch.int64).contiguous()
+            p.idx_dtype = _abi.IDX_I32 if idx.dtype == torch.int32 else _abi.IDX_I64
         m = n_vox if idx is None else idx.numel()
 
         def alloc(dt=torch.float32):
@@ -315,13 +335,19 @@ def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=
         p.mask_idx = idx.data_ptr() if idx is not None else None
         ptr = lambda t: t.data_ptr() if t is not None else None
         stream = torch.cuda.current_stream(y.device).cuda_stream
-        keep += [y, idx]
+        dcnt = _device_counts(torch, y.device)
+        o.counts_dev = dcnt.data_ptr()
+        keep += [y, idx, dcnt]
     else:
         y = _host_echoes(np.asarray(reshaped_t2w), p)
         if y.ndim != 2:
             raise ValueError("reshaped_t2w must be [N, E]")
         n_vox, n_echo = y.shape
-        idx = None if mask_indices is None else np.ascontiguousarray(mask_indices, dtype=np.int64)
+        idx = None
+        if mask_indices is not None:               # int32 indices are taken as they are (half the index bytes over PCIe)
+            idx = np.asarray(mask_indices)
+            idx = np.ascontiguousarray(idx, dtype=np.int32 if idx.dtype == np.int32 else np.int64)
+            p.idx_dtype = _abi.IDX_I32 if idx.dtype == np.int32 else _abi.IDX_I64
         m = n_vox if idx is None else idx.size
         fields = [("t2", np.float32), ("k", np.float32), ("res", np.float32)]
         fields += [("sigma", np.float32)] if fit != "gaussian" else []                  # 2-parameter fit: zeros, made on first access
@@ -350,36 +376,43 @@ def fit_voxels_batch(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=
     _run(lib, p, o, stream)
     if dev:
         counts = None
-        if check_bounds:
-            cnt = (C.c_int64 * 4)()
-            _abi.check(lib, lib.t2fit_status_counts(stream, cnt), "t2fit_status_counts")
+        if check_bounds:                           # one small D2H: waits for the call (check_bounds=False stays asynchronous)
+            cnt = [int(v) for v in dcnt.cpu()]
+            _raise_for_counts(cnt)
             counts = (m - cnt[1] - cnt[2] - cnt[3], cnt[1], cnt[2], cnt[3])
     else:
         counts = tuple(o.status_count)
-    if counts is not None and counts[3] > 0:
-        # scipy raises inside the first such voxel and the reference's pool.map aborts the whole map
-        raise ValueError(BOUNDS_ERROR)
+        if counts[3] > 0:
+            # scipy raises inside the first such voxel and the reference's pool.map aborts the whole map
+            raise ValueError(BOUNDS_ERROR)
     return FitResult(out["t2"], out["k"], out["sigma"], out["res"], out["fun"], out["nit"], out["status"], fit,
                      counts if counts is not None else (0, 0, 0, 0), solver, out.get("trace_f"), out.get("trace_step"),
                      out.get("trace_len"))
 
 
-def fit_voxels_into(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior, norm, out, *, solver="auto"):
+def fit_voxels_into(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior, norm, out, *, solver="auto", counts=None):
     """Device-memory fit whose compact results go to caller-given raw device pointers: ``out`` maps 't2', 'k', 'res'
     (and 'sigma' for the 3-parameter fits; optionally 'status', 'nit', 'fun') to integer addresses of arrays with room
     for ``len(mask_indices)`` elements -- local memory or a peer GPU's buffer mapped with ``t2fit_shared_open`` (the
-    fused gather of ``distributed.fit_voxels_sharded``).  Asynchronous on the current torch stream."""
+    fused gather of ``distributed.fit_voxels_sharded``).  Asynchronous on the current torch stream.  ``counts``: a zeroed
+    int64 CUDA tensor [4] the call adds its histogram to (slot 0 indices out of range, 1..3 voxels per non-OK status);
+    the caller reads it when it synchronises and raises as :func:`fit_voxels_batch` does (``check_counts``)."""
     import torch
     lib = init()
     solver = resolve_solver(fit, solver)
     p, o = _abi.Problem(), _abi.Outputs()
-    keep = [_fill_problem(p, fit, fit_params, TEeffs, prior, norm, 0, 0.0, "loglinear", solver)]
+    keep = [_fill_problem(p, fit, fit_params, TEeffs, prior, norm, 0, 0.0, "auto", solver)]
     y = reshaped_t2w
     if not (_is_torch(y) and y.is_cuda and y.dtype == torch.float32 and y.is_contiguous() and y.dim() == 2):
         raise ValueError("device input must be a contiguous float32 CUDA tensor [N, E]")
     idx = mask_indices
-    if idx is not None and not (_is_torch(idx) and idx.is_cuda and idx.dtype == torch.int64 and idx.is_contiguous()):
+    if idx is not None and not (_is_torch(idx) and idx.is_cuda and idx.dtype in (torch.int64, torch.int32) and idx.is_contiguous()):
         idx = torch.as_tensor(np.ascontiguousarray(np.asarray(idx.cpu() if _is_torch(idx) else idx), dtype=np.int64), device=y.device)
+    if idx is not None:
+        p.idx_dtype = _abi.IDX_I32 if idx.dtype == torch.int32 else _abi.IDX_I64
+    if counts is None:
+        counts = _device_counts(torch, y.device)           # never the per-process counters: nothing leaks into later calls
+    o.counts_dev = counts.data_ptr()
     if y.shape[1] != p.n_echo:
         raise ValueError(f"reshaped_t2w has {y.shape[1]} echoes, TEeffs has {p.n_echo}")
     p.echoes, p.memory, p.layout = y.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_AOS
@@ -390,8 +423,13 @@ def fit_voxels_into(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior, 
     o.status, o.nit, o.fun = out.get("status"), out.get("nit"), out.get("fun")
     o.dense = 0
     _run(lib, p, o, torch.cuda.current_stream(y.device).cuda_stream)
-    keep += [y, idx]
+    keep += [y, idx, counts]
     return p.n_fit
+
+
+def check_counts(counts):
+    """Raise what the reference raises for the histogram of a device call (synchronises on the tensor)."""
+    _raise_for_counts([int(v) for v in counts.cpu()])
 
 
 def mask_indices_device(mask, n_masks=None):
@@ -426,7 +464,7 @@ def t2map_volume(t2w, mask, TEeffs, fit, fit_params, prior=True, norm=False, **k
     p, o = _abi.Problem(), _abi.Outputs()
     solver = resolve_solver(fit, kw.get("solver", "auto"))
     keep = [_fill_problem(p, fit, fit_params, TEeffs, prior, norm, kw.get("max_iter", 0), kw.get("tol", 0.0),
-                          kw.get("init_mode", "loglinear"), solver)]
+                          kw.get("init_mode", "auto"), solver)]
     fused_mask = None
     if _is_torch(t2w):
         import torch
@@ -445,7 +483,9 @@ def t2map_volume(t2w, mask, TEeffs, fit, fit_params, prior=True, norm=False, **k
         p.echoes, p.memory, p.mask_idx = y.data_ptr(), _abi.MEM_DEVICE, idx.data_ptr()
         stream = torch.cuda.current_stream(y.device).cuda_stream
         mp = [maps[i].data_ptr() for i in range(4)]
-        keep += [y, idx, mk]
+        dcnt = _device_counts(torch, y.device)
+        o.counts_dev = dcnt.data_ptr()
+        keep += [y, idx, mk, dcnt]
     else:
         y = _host_echoes(np.reshape(np.asarray(t2w), (-1, n_echo)), p)                  # :411
         mk = np.asarray(mask)
@@ -467,12 +507,8 @@ def t2map_volume(t2w, mask, TEeffs, fit, fit_params, prior=True, norm=False, **k
         o.zero_fill_mask = fused_mask.data_ptr()
     _run(lib, p, o, stream)
     if stream is not None:
-        cnt = (C.c_int64 * 4)()
-        _abi.check(lib, lib.t2fit_status_counts(stream, cnt), "t2fit_status_counts")
-        bad = cnt[3]
-    else:
-        bad = o.status_count[3]
-    if bad > 0:
+        _raise_for_counts([int(v) for v in dcnt.cpu()])
+    elif o.status_count[3] > 0:
         raise ValueError(BOUNDS_ERROR)
     return tuple(maps[i].reshape(shape3) for i in range(4))
 

@@ -86,6 +86,13 @@ inline int make_consts(const t2fit_problem& p, FitConsts& c, std::string& err) {
         if (!(lb[i] <= ub[i])) { err = "An upper bound is less than the corresponding lower bound."; return T2FIT_EINVAL; }
     }
     if (!(lb[1] > 0.0)) { err = "T2 lower bound must be positive"; return T2FIT_EINVAL; }
+    if (np_ == 3) {
+        // the fast 3-parameter solver works in sigma^2 (the model depends on sigma only through it): its box is
+        // [max(lb,0)^2, ub^2].  A negative / absent (-inf) lower bound means sigma >= 0; an upper bound below 0 leaves
+        // no sigma >= 0 in the box and is rejected (the L-BFGS-B solver handles such boxes in sigma itself).
+        if (!(lb[2] >= 0.0)) lb[2] = 0.0;
+        if (!(ub[2] >= lb[2])) { err = "sigma upper bound must be >= max(sigma lower bound, 0) for the fast solver (use the L-BFGS-B solver)"; return T2FIT_EINVAL; }
+    }
     double mean_te = 0;
     for (int e = 0; e < p.n_echo; ++e) {
         if (!isfinite(p.te_ms[e])) { err = "non-finite echo time"; return T2FIT_EINVAL; }

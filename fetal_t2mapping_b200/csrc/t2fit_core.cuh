@@ -314,6 +314,8 @@ T2_HD FloorSums<R> floor_pass(const R (&y)[E], const FitConsts& c, R k, R r, R s
 // The optimiser as a resumable run: start() = clipped start point, step() = one pass over the echoes at the trial point
 // followed by the reaction to it (accept / reject, new trial point or stop).  The one-shot kernel steps all lanes of a
 // warp until the last one has stopped; the queue kernel hands a lane that has stopped the next voxel instead.
+constexpr int kFloorStarts = 4;   // kInitBest: log-linear, preset x0, T2 on its lower bound, T2 mid-box
+
 template <typename R>
 struct FloorRun {
     R kl, ku;                    // per-voxel bounds of k (the others are launch constants)
@@ -322,6 +324,12 @@ struct FloorRun {
     R lambda;
     int nit, status, it;
     bool have_cur, active;
+    // kInitBest (multi-start): the objective has several local minima on noise-floor voxels (T2 on its lower bound with
+    // sigma carrying the signal, T2 on its upper bound with k carrying it, the decaying solution in between); the run is
+    // restarted from kFloorStarts start points and the lowest cost is kept
+    int phase;                   // start point in use
+    R bx[3], bcost;              // best finished run so far
+    int bstatus, nit_sum;
 
     // the sigma box maps monotonically (sigma bounds are clamped to >= 0 on the host)
     T2_HD R lo(const FitConsts& c, int i) const { return i == 0 ? kl : i == 1 ? R(c.r_lo) : R(c.lb[2]) * R(c.lb[2]); }
@@ -336,6 +344,46 @@ struct FloorRun {
         nit = 0; status = kOk; it = 0;
         have_cur = false;
         active = run;
+        phase = 0; bcost = R(INFINITY); bstatus = kOk; nit_sum = 0;
+        bx[0] = x[0]; bx[1] = x[1]; bx[2] = x[2];
+    }
+
+    // kInitBest: the run from start `phase` has stopped.  Keep it if it is the best so far, then either restart from the
+    // next start point (returns with active = true) or hand back the best run.
+    template <int E>
+    T2_HD void next_start(const R (&y)[E], const FitConsts& c) {
+        nit_sum += nit;
+        const R cost = have_cur ? cur.cost : R(INFINITY);
+        // a run that hit the pass cap only wins against other capped runs
+        const bool better = (status == kOk && (bstatus != kOk || cost < bcost)) || (status != kOk && bstatus != kOk && cost < bcost) ||
+                            phase == 0;
+        if (better) { bx[0] = x[0]; bx[1] = x[1]; bx[2] = x[2]; bcost = cost; bstatus = status; }
+        ++phase;
+        if (phase >= kFloorStarts) {
+            x[0] = bx[0]; x[1] = bx[1]; x[2] = bx[2]; cur.cost = bcost; status = bstatus; nit = nit_sum;
+            active = false;
+            return;
+        }
+        R k0, r0, s0;
+        if (phase == 1) { k0 = R(c.x0[0]); r0 = R(c.r_x0); s0 = R(c.x0[2]); }           // the reference's start: clipped preset x0
+        else {
+            r0 = phase == 2 ? R(c.r_hi) : sqrt(R(c.r_lo) * R(c.r_hi));                   // T2 on its lower bound / mid-box (geometric)
+            R sa = 0, sb = 0, sy = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const R u = fast_ex2(R(c.nte2[e]) * r0);
+                sa += u * u; sb += y[e] * u; sy += y[e] * y[e];
+            }
+            k0 = sa > R(0) ? fdiv(sb, sa) : kl;
+            if (!finite_r(k0)) k0 = kl;
+            s0 = phase == 2 ? sqrt(sy * (R(1) / R(E))) : R(c.x0[2]);                     // the floor carries the signal / preset sigma
+        }
+        x[0] = clampr(k0, lo(c, 0), hi(c, 0)); x[1] = clampr(r0, lo(c, 1), hi(c, 1)); x[2] = clampr(s0 * s0, lo(c, 2), hi(c, 2));
+        xt[0] = x[0]; xt[1] = x[1]; xt[2] = x[2];
+        lambda = R(1e-3);
+        nit = 0; status = kOk; it = 0;
+        have_cur = false;
+        active = true;
     }
 
     template <int E>
@@ -414,6 +462,7 @@ struct FloorRun {
                 }
             }
             ++it;
+            if (!active && c.init_mode == kInitBest) next_start<E>(y, c);
         }
     }
 
@@ -430,7 +479,7 @@ T2_HD void solve_floor3(const R (&y)[E], const FitConsts& c, R kl, R ku, R k0, R
                         R& s_out, R& cost_out, int& nit_out, int& status_out, bool lane_valid) {
     FloorRun<R> run;
     run.start(c, kl, ku, k0, r0, s0, lane_valid);
-    const int max_pass = c.max_iter;
+    const int max_pass = c.max_iter * (c.init_mode == kInitBest ? kFloorStarts : 1);
     for (int it = 0; it < max_pass; ++it) {
         if (!warp_any(run.active)) break;
         run.template step<E>(y, c);

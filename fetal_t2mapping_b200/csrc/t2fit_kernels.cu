@@ -49,6 +49,7 @@ constexpr int kBlock = 256;
 struct KernelIO {
     const float* echoes;
     const int64_t* idx;   // may be null
+    const int32_t* idx32; // the same vector as int32 (t2fit_problem::idx_dtype = T2FIT_IDX_I32); at most one of the two is set
     int64_t ld;
     int64_t n_fit;
     float* t2;
@@ -82,6 +83,11 @@ __device__ __forceinline__ int64_t guarded_row(const KernelIO& io, int64_t row) 
         row = 0;
     }
     return row;
+}
+__device__ __forceinline__ bool has_idx(const KernelIO& io) { return io.idx != nullptr || io.idx32 != nullptr; }
+// mask_indices[i] (int64 or int32 vector), unchecked
+__device__ __forceinline__ int64_t raw_row(const KernelIO& io, int64_t i) {
+    return io.idx ? __ldg(io.idx + i) : (int64_t)__ldg(io.idx32 + i);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -241,8 +247,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool valid = i < io.n_fit;
     const int64_t ii = valid ? i : io.n_fit - 1;           // whole warps stay in the solver (warp votes)
-    // (the FILL variant only ever sees device-resident, already checked index vectors)
-    const int64_t row = io.idx ? (FILL ? __ldg(io.idx + ii) : guarded_row(io, __ldg(io.idx + ii))) : ii;
+    const int64_t row = has_idx(io) ? guarded_row(io, raw_row(io, ii)) : ii;
     // FILL: block b owns the contiguous window of fill_wpb mask words starting at b * fill_wpb (one window per map and block:
     // few concurrent write streams); thread t takes words t, t + 256, ... of the window
     const int64_t w0 = (int64_t)blockIdx.x * io.fill_wpb;
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(kQBlock, queue_min_blocks(E)) floor_queue_kern
                 const int64_t cand = (int64_t)base + __popc(m_need & ((1u << lane) - 1u));
                 if (!have && cand < io.n_fit) {
                     i = cand;
-                    row = io.idx ? guarded_row(io, __ldg(io.idx + i)) : i;
+                    row = has_idx(io) ? guarded_row(io, raw_row(io, i)) : i;
                     if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row, io.vec_ok != 0, y);
                     else if (LAYOUT == T2FIT_LAYOUT_SOA) load_soa<E>(io.echoes, io.ld, i, y);
                     else load_soa<E>(io.echoes, io.ld, row, y);
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(kLbBlock) lbfgsb_kernel(const __grid_constant_
                 const int64_t i = (int64_t)base + __popc(m & ((1u << lane) - 1u));
                 if (i < io.n_fit) {
                     cur = i;
-                    row = io.idx ? guarded_row(io, __ldg(io.idx + i)) : i;
+                    row = has_idx(io) ? guarded_row(io, raw_row(io, i)) : i;
                     float yraw[kMaxEcho];
                     if (io.layout == T2FIT_LAYOUT_AOS) { for (int e = 0; e < E; ++e) yraw[e] = __ldg(io.echoes + row * E + e); }
                     else {
@@ -508,7 +513,7 @@ __global__ void __launch_bounds__(G == 8 ? 256 : G == 16 ? 512 : 1024, 1) lbfgsb
             i = grp.shfl(i, 0);
             if (i < io.n_fit) {
                 cur = i;
-                row = io.idx ? __ldg(io.idx + i) : i;
+                row = has_idx(io) ? raw_row(io, i) : i;
                 if (io.n_rows > 0 && (unsigned long long)row >= (unsigned long long)io.n_rows) {      // unchecked host index vector
                     if (grp.master()) atomicAdd(io.counts, 1ull);
                     row = 0;
@@ -1014,10 +1019,11 @@ int launch_lbfgsb_coop(Context* c, const lb::LbConsts& lc, const KernelIO& io, i
 int launch_lbfgsb(Context* c, const lb::LbConsts& lc, KernelIO io, int model, int n_echo, cudaStream_t st) {
     if (io.n_fit <= 0) return T2FIT_OK;
     if (n_echo < 2 || n_echo > kMaxEcho) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
-    // T2FIT_LB_KERNEL = coop8 (default) | coop16 | coop32 | thread: lane group per voxel with the state in shared memory, or the
-    // one-thread-per-voxel kernel with the state in local memory (read per call: tests and A/B runs switch it)
+    // T2FIT_LB_KERNEL = thread (default) | coop8 | coop16 | coop32: the one-thread-per-voxel kernel with the state in local
+    // memory, or a lane group per voxel with the state in shared memory (bit-identical results; measured 2.6-3x slower,
+    // profiles/r02_notes.md -- kept as the cross-check of the thread kernel).  Read per call: tests and A/B runs switch it.
     const char* ek = getenv("T2FIT_LB_KERNEL");
-    const int lanes = !ek ? 8 : !strcmp(ek, "coop8") ? 8 : !strcmp(ek, "coop16") ? 16 : !strcmp(ek, "coop32") ? 32 : 0;
+    const int lanes = !ek ? 0 : !strcmp(ek, "coop8") ? 8 : !strcmp(ek, "coop16") ? 16 : !strcmp(ek, "coop32") ? 32 : 0;
     if (lanes) return launch_lbfgsb_coop(c, lc, io, model, lanes, st);
     LbFn fn = pick_lb_kernel(model, n_echo);
     if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
@@ -1130,6 +1136,11 @@ inline float echo_at(const void* base, int dt, int64_t off) {
     return v;
 }
 
+// mask_indices[i] of a HOST index vector (int64, or int32 when t2fit_problem::idx_dtype says so)
+inline int64_t host_idx(const t2fit_problem& p, int64_t i) {
+    return p.idx_dtype == T2FIT_IDX_I32 ? (int64_t)reinterpret_cast<const int32_t*>(p.mask_idx)[i] : p.mask_idx[i];
+}
+
 bool is_pinned(const void* p) {
     if (!p) return true;
     cudaPointerAttributes at{};
@@ -1176,10 +1187,12 @@ int run_host_mapped(Context* c, const t2fit_problem& p, t2fit_outputs& o, const 
     if (p.mask_idx) {
         // no host pass over the index vector: the kernel checks the range itself (KernelIO::n_rows)
         io.n_rows = p.n_vox;
+        const bool i32 = p.idx_dtype == T2FIT_IDX_I32;
+        const size_t isz = i32 ? sizeof(int32_t) : sizeof(int64_t);
         void* d_idx = nullptr;
         if (is_pinned(p.mask_idx) && map(p.mask_idx, &d_idx)) {
-            io.idx = static_cast<const int64_t*>(d_idx);      // read in place too (measured: 1.6 ms vs 2.35 ms with a DMA copy first)
-        } else {                                      // pageable index vector: one copy to the device (8 B per voxel)
+            // read in place too (measured: 1.6 ms vs 2.35 ms with a DMA copy first)
+        } else {                                      // pageable index vector: one copy to the device (4 or 8 B per voxel)
             cudaGetLastError();
             if (c->d_idx_cap < M) {
                 if (c->d_idx) cudaFree(c->d_idx);
@@ -1187,9 +1200,11 @@ int run_host_mapped(Context* c, const t2fit_problem& p, t2fit_outputs& o, const 
                 CU_TRY(cudaMalloc(&c->d_idx, sizeof(int64_t) * M));
                 c->d_idx_cap = M;
             }
-            CU_TRY(cudaMemcpyAsync(c->d_idx, p.mask_idx, sizeof(int64_t) * M, cudaMemcpyHostToDevice, st));
-            io.idx = c->d_idx;
+            CU_TRY(cudaMemcpyAsync(c->d_idx, p.mask_idx, isz * M, cudaMemcpyHostToDevice, st));
+            d_idx = c->d_idx;
         }
+        if (i32) io.idx32 = static_cast<const int32_t*>(d_idx);
+        else io.idx = static_cast<const int64_t*>(d_idx);
     }
     if (c->counts_dirty) {
         CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), st));
@@ -1292,7 +1307,7 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
                 if (m == 2 && mono) continue;                     // sigma map stays as the caller zeroed it
                 const float* src = hf + (int64_t)m * n;
                 if (o.dense && m < 4 && p.mask_idx) {
-                    for (int64_t i = lo; i < hi; ++i) dst[p.mask_idx[first + i]] = src[i];   // scatter (:455-458)
+                    for (int64_t i = lo; i < hi; ++i) dst[host_idx(p, first + i)] = src[i];   // scatter (:455-458)
                 } else {
                     memcpy(dst + first + lo, src + lo, sizeof(float) * (hi - lo));
                 }
@@ -1320,13 +1335,13 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
                 if (!p.mask_idx) {
                     echo_copy(s.h_in + lo * E, p.echoes, edt, (first + lo) * E, (int64_t)E * (hi - lo));
                 } else {
-                    const int64_t* idx = p.mask_idx + first;
                     int64_t i = lo;
                     while (i < hi) {
                         int64_t j = i + 1;
-                        while (j < hi && idx[j] == idx[j - 1] + 1) ++j;
-                        if (idx[i] < 0 || idx[j - 1] >= p.n_vox) { bad_index.store(true); return; }   // IndexError upstream
-                        echo_copy(s.h_in + i * E, p.echoes, edt, idx[i] * E, (int64_t)E * (j - i));
+                        while (j < hi && host_idx(p, first + j) == host_idx(p, first + j - 1) + 1) ++j;
+                        const int64_t r0 = host_idx(p, first + i), r1 = host_idx(p, first + j - 1);
+                        if (r0 < 0 || r1 >= p.n_vox) { bad_index.store(true); return; }   // IndexError upstream
+                        echo_copy(s.h_in + i * E, p.echoes, edt, r0 * E, (int64_t)E * (j - i));
                         i = j;
                     }
                 }
@@ -1334,17 +1349,17 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
                 for (int e = 0; e < E; ++e)
                     echo_copy(s.h_in + (int64_t)e * n + lo, p.echoes, edt, (int64_t)e * p.ld + first + lo, hi - lo);
             } else {                              // per-TE volumes [E, ld >= n_vox] -> planes [E, n] of the masked voxels
-                const int64_t* idx = p.mask_idx ? p.mask_idx + first : nullptr;
+                const bool idx = p.mask_idx != nullptr;
                 for (int64_t i = lo; i < hi; ++i) {
-                    const int64_t v = idx ? idx[i] : first + i;
+                    const int64_t v = idx ? host_idx(p, first + i) : first + i;
                     if (v < 0 || v >= p.n_vox) { bad_index.store(true); return; }
                 }
                 for (int e = 0; e < E; ++e) {
                     const int64_t plane = (int64_t)e * p.ld;
                     float* dst = s.h_in + (int64_t)e * n;
                     if (!idx) echo_copy(dst + lo, p.echoes, edt, plane + first + lo, hi - lo);
-                    else if (edt == 0) { const float* src = p.echoes + plane; for (int64_t i = lo; i < hi; ++i) dst[i] = src[idx[i]]; }
-                    else for (int64_t i = lo; i < hi; ++i) dst[i] = echo_at(p.echoes, edt, plane + idx[i]);
+                    else if (edt == 0) { const float* src = p.echoes + plane; for (int64_t i = lo; i < hi; ++i) dst[i] = src[host_idx(p, first + i)]; }
+                    else for (int64_t i = lo; i < hi; ++i) dst[i] = echo_at(p.echoes, edt, plane + host_idx(p, first + i));
                 }
             }
         });
@@ -1544,16 +1559,28 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
 
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
     KernelIO io{};
-    io.echoes = p->echoes; io.idx = p->mask_idx; io.ld = p->ld; io.n_fit = p->n_fit;
+    io.echoes = p->echoes; io.ld = p->ld; io.n_fit = p->n_fit;
+    if (p->idx_dtype == T2FIT_IDX_I32) io.idx32 = reinterpret_cast<const int32_t*>(p->mask_idx);
+    else io.idx = p->mask_idx;
+    // a caller-supplied index vector is range-checked by the kernels (entries outside [0, n_vox) are counted in slot 0 of
+    // the counters and read / write voxel 0 instead): the reference's fancy indexing raises IndexError there
+    if (p->mask_idx && p->layout != T2FIT_LAYOUT_SOA) io.n_rows = p->n_vox;
     io.t2 = o->t2; io.k = o->k; io.sigma = o->sigma; io.res = o->res; io.fun = o->fun; io.nit = o->nit;
-    io.status = o->status; io.counts = c->d_counts; io.dense = o->dense;
+    io.status = o->status; io.dense = o->dense;
+    // status histogram of THIS call: the caller's own device counters, or the per-process ones (cleared first if an earlier
+    // call left counts nobody asked for, so that they cannot leak into this call's t2fit_status_counts)
+    if (o->counts_dev) io.counts = reinterpret_cast<unsigned long long*>(o->counts_dev);
+    else {
+        io.counts = c->d_counts;
+        if (c->counts_dirty) CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), st));
+    }
     io.vec_ok = (reinterpret_cast<uintptr_t>(p->echoes) % 16) == 0;
     io.layout = p->layout;
     if (lbs && o->trace_cap > 0) {
         io.trace_f = o->trace_f; io.trace_step = o->trace_step; io.trace_len = o->trace_len; io.trace_cap = o->trace_cap;
     }
     bool forked = false;
-    c->counts_dirty = true;
+    if (!o->counts_dev) c->counts_dirty = true;
     if (o->dense && o->zero_fill_mask) {
         // np.zeros_like x4 (:415-418): inside the fit launch (every fit thread zeroes a few words of the maps while it
         // waits for its echoes) or, where that does not apply, by zero_fill_kernel on the side stream (disjoint slots)
@@ -1583,8 +1610,7 @@ int t2fit_status_counts(void* stream, int64_t counts[4]) {
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
     CU_TRY(cudaMemcpyAsync(c->h_counts, c->d_counts, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    for (int s = 0; s < 4; ++s) counts[s] = (int64_t)c->h_counts[s];
-    counts[0] = -1;  // OK count = n_fit - sum(others); the caller knows n_fit
+    for (int s = 0; s < 4; ++s) counts[s] = (int64_t)c->h_counts[s];   // slot 0: mask_idx entries out of range (IndexError upstream)
     CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), st));   // counts are "since the last query"
     CU_TRY(cudaStreamSynchronize(st));
     c->counts_dirty = false;

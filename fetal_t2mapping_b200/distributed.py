@@ -2,66 +2,167 @@
 
 Replaces the reference's only parallel runtime, ``multiprocessing.Pool(processes=20).map`` over
 ``mask_indices`` (run_t2mapping.py:442-443).  Voxels are independent, so there is no exchange step
-during the fit; the only inter-GPU traffic is ONE final gather of the parameter vectors
-(NCCL over NVLink, ``all_gather_into_tensor``).  Slabs are cut from the compacted masked list
-(balanced by masked count, 128-voxel aligned), not from z-slabs of the volume, so a brain mask
-does not unbalance the GPUs.
+during the fit; the only inter-GPU traffic is ONE final gather of the result vectors.  Slabs are cut
+from the compacted masked list (balanced by masked count, 128-voxel aligned), not from z-slabs of the
+volume, so a brain mask does not unbalance the GPUs.
 
-Host logic only -- the fit of a slab is ``api.fit_voxels_batch`` (CUDA).  ``fit_fn`` is injectable
-so the partition / gather logic is testable with ``gloo`` on CPU.
+* every rank needs ONLY ITS SLAB of the input: ``fit_slab_sharded`` takes the rows of the rank's own voxels
+  (``slab_rows``), ``fit_voxels_sharded`` keeps the reference-shaped arguments (whole ``reshaped_t2w`` +
+  ``mask_indices``) and reads only the slab's rows of them;
+* the gather writes straight into the final layout: slabs are padded to one length L, every field is gathered with one
+  ``all_gather_into_tensor`` into a ``[world * L]`` buffer whose first ``n_fit`` elements ARE the result (the padding sits
+  behind the last slab); ``status`` travels as uint8;
+* a rank whose fit raises (scipy's ``ValueError`` under ``--no_prior``, an index error, a CUDA error) tells the others
+  before the collective: an error flag is all-reduced first and every rank raises, as ``pool.map`` aborts the whole map
+  in the reference -- nobody is left waiting in a collective;
+* ``fit_voxels_fused_gather``: no collective at all -- the fit kernels' epilogues store their slab straight into the
+  root GPU's buffer over NVLink (CUDA IPC peer mapping).
+
+Host logic only -- the fit of a slab is ``api.fit_voxels_batch`` (CUDA).  ``fit_fn`` is injectable so the partition /
+gather / error logic is testable with ``gloo`` on CPU.
 """
 from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["slab_bounds", "fit_voxels_sharded", "gather_slabs", "fit_voxels_fused_gather"]
+__all__ = ["slab_bounds", "slab_length", "fit_voxels_sharded", "fit_slab_sharded", "gather_slabs", "gather_fields",
+           "fit_voxels_fused_gather", "ShardError"]
 
 ALIGN = 128
+FIELDS = ("t2", "k", "sigma", "res", "status")
+
+
+class ShardError(RuntimeError):
+    """Another rank's fit failed; this rank's own slab was fine."""
+
+
+def slab_length(n_fit: int, world: int, align: int = ALIGN) -> int:
+    """The common (padded) slab length L: ceil(n_fit / world) rounded up to ``align``."""
+    per = -(-max(n_fit, 0) // world)
+    return max(align, -(-per // align) * align)
 
 
 def slab_bounds(n_fit: int, world: int, align: int = ALIGN):
-    """``world`` contiguous [start, stop) slabs of ``range(n_fit)``; interior cuts are multiples of
-    ``align``; sizes differ by at most ``align``; trailing slabs may be empty for tiny inputs."""
+    """``world`` contiguous [start, stop) slabs of ``range(n_fit)``: slab r = [r L, (r+1) L) clipped to n_fit, L =
+    ``slab_length``.  Every slab but the last non-empty one has exactly L voxels, so the concatenation of L-padded slabs is
+    the full vector followed by padding (the all-gather then needs no stitching); sizes differ by less than L only at the
+    tail; trailing slabs may be empty for tiny inputs."""
     if world < 1:
         raise ValueError("world must be >= 1")
-    blocks = -(-n_fit // align)
-    cuts = [min(n_fit, ((blocks * r) // world) * align) for r in range(world + 1)]
-    cuts[-1] = n_fit
-    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+    L = slab_length(n_fit, world, align)
+    return [(min(n_fit, r * L), min(n_fit, (r + 1) * L)) for r in range(world)]
 
 
-def gather_slabs(local, bounds, group=None):
-    """All-gather equally padded slabs of a float32 tensor ``local`` [C, m_r] and stitch them into
-    [C, n_fit] on every rank.  One collective (NCCL for CUDA tensors, gloo for CPU tensors)."""
+def _agree_or_raise(exc, device, group):
+    """Exchange an error flag BEFORE any collective that depends on every rank having fitted its slab: all ranks raise if
+    any rank failed (the reference's pool.map aborts the whole map when one voxel raises)."""
+    import torch
+    import torch.distributed as dist
+    code = 0 if exc is None else (2 if isinstance(exc, ValueError) else 3 if isinstance(exc, IndexError) else 1)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        flag = torch.tensor([code], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        worst = int(flag.item())
+    else:
+        worst = code
+    if exc is not None:
+        raise exc
+    if worst:
+        from .api import BOUNDS_ERROR
+        if worst == 2:
+            raise ValueError(BOUNDS_ERROR)          # what every rank of the reference's map would have seen
+        if worst == 3:
+            raise IndexError("mask_indices out of range (on another rank)")
+        raise ShardError("the fit failed on another rank")
+
+
+def gather_fields(local: dict, n_fit: int, group=None):
+    """All-gather the slab vectors of ``local`` (name -> 1-D tensor of this rank's slab, any dtype) into full vectors on
+    every rank.  One ``all_gather_into_tensor`` per field straight into the final buffer: slab r lands at [r L, (r+1) L),
+    which is its place in the full vector; the result is the first ``n_fit`` elements -- no stitch copies."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    sizes = [b - a for a, b in bounds]
-    mx = max(max(sizes), 1)
-    c = local.shape[0]
-    assert local.shape[1] == sizes[rank], "local slab does not match the partition"
-    pad = torch.zeros((c, mx), dtype=local.dtype, device=local.device)
-    pad[:, :sizes[rank]] = local
-    flat = torch.empty((world * c, mx), dtype=local.dtype, device=local.device)   # concatenation along dim 0
-    dist.all_gather_into_tensor(flat, pad, group=group)
-    out = flat.view(world, c, mx)
-    full = torch.empty((c, bounds[-1][1]), dtype=local.dtype, device=local.device)
-    for r, (a, b) in enumerate(bounds):
-        full[:, a:b] = out[r, :, :b - a]
-    return full
+    L = slab_length(n_fit, world)
+    a, b = slab_bounds(n_fit, world)[rank]
+    out = {}
+    for name, v in local.items():
+        assert v.dim() == 1 and v.shape[0] == b - a, "local slab does not match the partition"
+        full = torch.empty(world * L, dtype=v.dtype, device=v.device)
+        mine = full[rank * L:(rank + 1) * L]
+        mine[:b - a].copy_(v)                      # the one copy: the slab into its place of the final buffer
+        if b - a < L:
+            mine[b - a:].zero_()
+        # NCCL gathers in place (the input is this rank's chunk of the output); gloo (CPU tests) gets its own input buffer
+        dist.all_gather_into_tensor(full, mine if v.is_cuda else mine.clone(), group=group)
+        out[name] = full[:n_fit]
+    return out
+
+
+def gather_slabs(local, bounds, group=None):
+    """All-gather the slabs of a 2-D tensor ``local`` [C, m_r] (one dtype) into [C, n_fit] on every rank (kept for callers
+    that hold their fields stacked; ``gather_fields`` avoids the stacking)."""
+    import torch
+    n_fit = bounds[-1][1]
+    got = gather_fields({str(c): local[c].contiguous() for c in range(local.shape[0])}, n_fit, group)
+    return torch.stack([got[str(c)] for c in range(local.shape[0])])
+
+
+def _as_tensor(x):
+    import torch
+    return x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+
+
+def _finish(r, exc, n_fit, bounds, rank, world, gather, group):
+    import torch
+    device = None
+    if r is not None:
+        device = _as_tensor(r.t2).device
+    elif torch.cuda.is_available() and torch.distributed.is_initialized() and torch.distributed.get_backend(group) == "nccl":
+        device = torch.device("cuda", torch.cuda.current_device())
+    _agree_or_raise(exc, device, group)
+    local = {"t2": _as_tensor(r.t2).float(), "k": _as_tensor(r.k).float(), "sigma": _as_tensor(r.sigma).float(),
+             "res": _as_tensor(r.res).float(), "status": _as_tensor(r.status).to(torch.uint8)}
+    if world == 1 or not gather:
+        out = dict(local) if world == 1 else {"local": local}
+    else:
+        out = gather_fields(local, n_fit, group)
+    out.update(bounds=bounds, rank=rank)
+    return out
+
+
+def fit_slab_sharded(slab_rows, n_fit, TEeffs, fit, fit_params, prior=True, norm=False, *, group=None, fit_fn=None,
+                     gather=True, **kw):
+    """The product's multi-GPU call when every rank holds ONLY ITS OWN SLAB: ``slab_rows`` = the float32 rows ``[m_r, E]`` of
+    the voxels ``slab_bounds(n_fit, world)[rank]`` of the masked list (what a loader hands each GPU).  Fits them and
+    all-gathers (t2, k, sigma, res, status) into full-length vectors on every rank."""
+    import torch.distributed as dist
+    if fit_fn is None:
+        from .api import fit_voxels_batch as fit_fn
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    bounds = slab_bounds(int(n_fit), world)
+    a, b = bounds[rank]
+    r, exc = None, None
+    try:
+        if slab_rows.shape[0] != b - a:
+            raise IndexError(f"rank {rank} holds {slab_rows.shape[0]} rows, its slab has {b - a}")
+        r = fit_fn(slab_rows, None, TEeffs, fit, fit_params, prior, norm, **kw)
+    except Exception as e:                       # noqa: BLE001 -- exchanged with the other ranks, then re-raised
+        exc = e
+    return _finish(r, exc, int(n_fit), bounds, rank, world, gather, group)
 
 
 def fit_voxels_sharded(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prior=True, norm=False, *, group=None,
                        fit_fn=None, gather=True, **kw):
-    """Every rank holds (or can read) ``reshaped_t2w`` / ``mask_indices``; rank r fits slab r of the
-    masked list and the (t2, k, sigma, res, status) vectors are all-gathered.  Returns a dict of
-    full-length arrays on every rank (``gather=False``: the local slab and its bounds only).
+    """The reference-shaped arguments on every rank (``reshaped_t2w`` may be a memory-mapped / host array: only the rows of
+    the rank's own slab are read); rank r fits slab r of the masked list and the (t2, k, sigma, res, status) vectors are
+    all-gathered.  Returns a dict of full-length arrays on every rank (``gather=False``: the local slab and its bounds).
 
     ``fit_fn(reshaped_t2w, mask_indices_slab, TEeffs, fit, fit_params, prior, norm, **kw)`` must return an
-    object with ``t2, k, sigma, res, status`` (default: the CUDA path, ``api.fit_voxels_batch``).
-    """
-    import torch
+    object with ``t2, k, sigma, res, status`` (default: the CUDA path, ``api.fit_voxels_batch``).  If the fit raises on any
+    rank, every rank raises (no rank is left in the collective)."""
     import torch.distributed as dist
     if fit_fn is None:
         from .api import fit_voxels_batch as fit_fn
@@ -70,20 +171,12 @@ def fit_voxels_sharded(reshaped_t2w, mask_indices, TEeffs, fit, fit_params, prio
     n_fit = int(mask_indices.shape[0])
     bounds = slab_bounds(n_fit, world)
     a, b = bounds[rank]
-    r = fit_fn(reshaped_t2w, mask_indices[a:b], TEeffs, fit, fit_params, prior, norm, **kw)
-
-    def as_tensor(x):
-        return x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
-    local = torch.stack([as_tensor(r.t2).float(), as_tensor(r.k).float(), as_tensor(r.sigma).float(),
-                         as_tensor(r.res).float(), as_tensor(r.status).float()])
-    if not gather or world == 1:
-        full = local
-        if world > 1:
-            return {"local": local, "bounds": bounds, "rank": rank}
-    else:
-        full = gather_slabs(local, bounds, group)
-    return {"t2": full[0], "k": full[1], "sigma": full[2], "res": full[3], "status": full[4].to(torch.uint8),
-            "bounds": bounds, "rank": rank}
+    r, exc = None, None
+    try:
+        r = fit_fn(reshaped_t2w, mask_indices[a:b], TEeffs, fit, fit_params, prior, norm, **kw)
+    except Exception as e:                       # noqa: BLE001 -- exchanged with the other ranks, then re-raised
+        exc = e
+    return _finish(r, exc, n_fit, bounds, rank, world, gather, group)
 
 
 class _DeviceBytes:
@@ -97,14 +190,15 @@ def fit_voxels_fused_gather(reshaped_t2w, mask_indices, TEeffs, fit, fit_params,
                             solver="auto"):
     """The fit with the final gather FUSED into the kernels: rank r fits slab r of ``mask_indices`` and its kernel's
     epilogue stores (t2, k, sigma, res, status) straight into the ROOT GPU's full-length buffer over NVLink (peer stores
-    through a CUDA-IPC mapping; no collective launch, the transfer overlaps the fit).  Device tensors in.  Returns the
-    full-length tensors on ``root`` (None on the other ranks) -- the reference's consumer of the maps is one process
-    (NIfTI writers, run_t2mapping.py:471-479)."""
+    through a CUDA-IPC mapping; no collective launch, the transfer overlaps the fit).  Device tensors in (each rank reads
+    only its slab's rows).  Returns the full-length tensors on ``root`` (None on the other ranks) -- the reference's
+    consumer of the maps is one process (NIfTI writers, run_t2mapping.py:471-479).  Raises on every rank what the reference
+    raises (``ValueError`` for the --no_prior bounds, ``IndexError``) if any rank's slab holds such a voxel."""
     import ctypes as C
     import torch
     import torch.distributed as dist
     from . import _abi
-    from .api import fit_voxels_into, init
+    from .api import _device_counts, _raise_for_counts, fit_voxels_into, init
     lib = init()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n_fit = int(mask_indices.shape[0])
@@ -122,12 +216,20 @@ def fit_voxels_fused_gather(reshaped_t2w, mask_indices, TEeffs, fit, fit_params,
         _abi.check(lib, lib.t2fit_shared_open(payload[0], C.byref(ptr)), "t2fit_shared_open")
     base = ptr.value
     try:
-        if b > a:
-            out = {"t2": base + 4 * a, "k": base + 4 * (n_fit + a), "sigma": base + 4 * (2 * n_fit + a),
-                   "res": base + 4 * (3 * n_fit + a), "status": base + 16 * n_fit + a}
-            fit_voxels_into(reshaped_t2w, mask_indices[a:b], TEeffs, fit, fit_params, prior, norm, out, solver=solver)
-        torch.cuda.synchronize()
-        dist.barrier(group=group)                          # every rank's stores have landed in the root's memory
+        exc = None
+        counts = _device_counts(torch, reshaped_t2w.device)
+        try:
+            if b > a:
+                out = {"t2": base + 4 * a, "k": base + 4 * (n_fit + a), "sigma": base + 4 * (2 * n_fit + a),
+                       "res": base + 4 * (3 * n_fit + a), "status": base + 16 * n_fit + a}
+                fit_voxels_into(reshaped_t2w, mask_indices[a:b], TEeffs, fit, fit_params, prior, norm, out, solver=solver,
+                                counts=counts)
+            torch.cuda.synchronize()
+            _raise_for_counts([int(v) for v in counts.cpu()])
+        except Exception as e:                   # noqa: BLE001 -- exchanged with the other ranks, then re-raised
+            exc = e
+        _agree_or_raise(exc, reshaped_t2w.device, group)   # (an all-reduce: also the point where every rank's stores have landed)
+        dist.barrier(group=group)
         result = None
         if rank == root:
             raw = torch.as_tensor(_DeviceBytes(base, max(nbytes, 1)), device=reshaped_t2w.device)

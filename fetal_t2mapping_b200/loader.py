@@ -56,7 +56,8 @@ class _Slot:
         self.h_maps = None         # page-locked result block of the volume in flight; handed to the caller, not reused
         self.h_mask = None
         self.d_status = torch.empty(n_vox, dtype=torch.uint8, device=dev)
-        self.h_cnt = torch.zeros(3, dtype=torch.int64, pin_memory=True)
+        self.h_cnt = torch.zeros(4, dtype=torch.int64, pin_memory=True)
+        self.d_cnt = torch.zeros(4, dtype=torch.int64, device=dev)      # this volume's own status histogram (counts_dev)
         self.copied = torch.cuda.Event()
         self.done = torch.cuda.Event()
         self.shape3 = None
@@ -109,7 +110,7 @@ def t2map_series(volumes, TEeffs, fit, fit_params, prior=True, norm=False, *, fa
     def finish(s):
         s.done.synchronize()
         s.busy = False
-        nonfinite, gave_up, bad_bounds = (int(v) for v in s.h_cnt)
+        _, nonfinite, gave_up, bad_bounds = (int(v) for v in s.h_cnt)
         if bad_bounds > 0:
             raise ValueError(BOUNDS_ERROR)
         maps, mk = s.h_maps.numpy(), s.h_mask.numpy()          # views of the page-locked blocks: no copy; the blocks go
@@ -133,17 +134,19 @@ def t2map_series(volumes, TEeffs, fit, fit_params, prior=True, norm=False, *, fa
                    "t2fit_mask_indices")
         s.n_fit = int(n.value)
         p, o = _abi.Problem(), _abi.Outputs()
-        keep = _fill_problem(p, fit, fit_params, te, prior, norm, 0, 0.0, "loglinear", solver)
+        keep = _fill_problem(p, fit, fit_params, te, prior, norm, 0, 0.0, "auto", solver)
         p.echoes, p.memory, p.layout, p.ld = s.d_planes.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_PLANES, n_vox
         p.mask_idx, p.n_vox, p.n_fit = s.d_idx.data_ptr(), n_vox, s.n_fit
         o.t2, o.k, o.sigma, o.res = (s.d_maps[i].data_ptr() for i in range(4))
         o.dense, o.zero_fill_mask = 1, s.d_mask.data_ptr()
         o.status = s.d_status.data_ptr()
+        with torch.cuda.stream(compute):
+            s.d_cnt.zero_()
+        o.counts_dev = s.d_cnt.data_ptr()
         _run(lib, p, o, cs)
         del keep
         with torch.cuda.stream(compute):
-            st = s.d_status[:s.n_fit]
-            s.h_cnt.copy_(torch.stack([(st == 1).sum(), (st == 2).sum(), (st == 3).sum()]), non_blocking=True)
+            s.h_cnt.copy_(s.d_cnt, non_blocking=True)
             s.h_maps.copy_(s.d_maps, non_blocking=True)
             s.h_mask.copy_(s.d_mask, non_blocking=True)
             s.done.record(compute)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define T2FIT_ABI_VERSION 3
+#define T2FIT_ABI_VERSION 4
 #define T2FIT_MAX_ECHO 32
 
 /* return codes */
@@ -73,6 +73,14 @@ extern "C" {
 /* initial guess of the iteration */
 #define T2FIT_INIT_LOGLINEAR 0 /* weighted log-linear fit of the echoes (default) */
 #define T2FIT_INIT_PRESET 1    /* the preset's initial_guess, clipped, as the reference starts */
+#define T2FIT_INIT_BEST 2      /* 3-parameter FAST solver: multi-start -- log-linear, preset x0, T2 on its lower bound, T2
+                                  mid-box -- and the lowest cost wins (the noise-floor objective has several local minima on
+                                  voxels whose signal has decayed into the floor); the 2-parameter solver treats it as
+                                  T2FIT_INIT_LOGLINEAR (its reduced problem is solved by a bracketing Newton iteration) */
+
+/* element type of t2fit_problem.mask_idx */
+#define T2FIT_IDX_I64 0
+#define T2FIT_IDX_I32 1
 
 /* The fit of one call.  Mirrors fit_voxel's arguments (run_t2mapping.py:120). */
 typedef struct t2fit_problem {
@@ -107,6 +115,9 @@ typedef struct t2fit_problem {
        while the masked rows are gathered into the staging buffers: only the n_fit fitted rows are cast, not all n_vox.
        Device-memory calls take float32 only. */
     int32_t echo_dtype;
+    /* Element type of mask_idx: T2FIT_IDX_I64 (0, np.where's int64) or T2FIT_IDX_I32 (the same indices as int32, n_vox <
+       2^31: half the index bytes over PCIe / from HBM).  mask_idx is then really a const int32_t*. */
+    int32_t idx_dtype;
 } t2fit_problem;
 
 /* Results.  Any pointer may be NULL (that output is skipped).  Parameter maps follow the reference's
@@ -138,6 +149,12 @@ typedef struct t2fit_outputs {
                                     kernel on a side stream concurrent with the fit (forked from / joined into
                                     `stream`; one such call at a time per process, the events are shared).
                                     NULL = caller zero-fills. */
+    uint64_t *counts_dev;        /* T2FIT_MEM_DEVICE calls, optional: [4] DEVICE counters this call ADDS its voxels to
+                                    (slot 0: mask_idx entries outside [0, n_vox), which read / write voxel 0 instead --
+                                    the reference raises IndexError there; slots 1..3: voxels per non-OK status).  The caller
+                                    zeroes and reads them on its own stream: the histogram of exactly this call, whatever
+                                    else runs on other streams.  NULL: the per-process counters behind
+                                    t2fit_status_counts(). */
 } t2fit_outputs;
 
 /* Bind this process to one GPU (one process per GPU; device = LOCAL_RANK) and create its context
@@ -155,8 +172,11 @@ int t2fit_device_info(char *name, int name_len, int *sm_count, int *cc_major, in
  * when the results are in the caller's buffers. */
 int t2fit_run(const t2fit_problem *p, t2fit_outputs *o, void *stream);
 
-/* Status histogram of the device-memory t2fit_run calls enqueued on `stream` since the previous query
- * (synchronises that stream, then resets the counters). */
+/* Status histogram of the device-memory t2fit_run calls WITHOUT counts_dev of their own since the previous query
+ * (synchronises `stream`, then resets the counters): counts[1..3] = voxels per non-OK status, counts[0] = mask_idx entries
+ * that were out of range.  One set of counters per process: a t2fit_run call that finds counts nobody has queried clears
+ * them first, so a call's histogram is its own as long as calls and queries alternate on one stream; concurrent streams
+ * should pass t2fit_outputs.counts_dev instead. */
 int t2fit_status_counts(void *stream, int64_t counts[4]);
 
 /* mask = np.sum(mask4, axis=3) > 0 (:383-384) and mask_indices = np.where(mask.flat) (:412,421):

@@ -151,14 +151,15 @@ def test_residual_and_fun_match_reference_formulas(gpu_lib, name):
 
 @pytest.mark.parametrize("name", ["c3_floor_noprior", "c3_floor_prior", "c5_floor_noprior"])
 def test_floor_model_reaches_a_bounded_minimum(gpu_lib, name):
-    """3-parameter noise-floor fit.  The reference stops at ftol=gtol=1e-2 (run_t2mapping.py:53-54), far
-    from any minimiser (11-37 % of its voxels within 1e-3 of the bounded minimum), so the
-    checks are: (i) failed sets identical, (ii) the CUDA result is never worse than the reference's
-    point in the reference's own objective, (iii) it agrees with the exact bounded LSQ minimiser on the
-    voxels where that minimiser is well determined (signal present, same basin)."""
+    """3-parameter noise-floor fit, FAST solver (multi-start by default).  The reference stops at ftol=gtol=1e-2
+    (run_t2mapping.py:53-54), far from any minimiser, so this solver is NOT the reference's point -- the
+    L-BFGS-B solver is (test_lbfgsb_solver_reproduces_the_reference).  What it must be is the bounded minimiser, on ALL
+    voxels: (i) failed set identical to the reference's, (ii) cost within 1e-4 of the exact minimum on > 99 % (exact =
+    scipy TRF from a grid of starts, tests/golden/make_exact_multistart.py), (iii) T2 within 1e-3 of the exact minimiser on
+    >= 95 % (the rest: flat valleys of voxels decayed into the noise floor), (iv) never above the reference's own cost."""
     g = load_golden(name)
     o = run_rows(gpu_lib, g, True, solver="fast")
-    assert np.array_equal(o["status"] == 0, g["ref_success"]) or (o["status"] != 0).mean() < 0.01
+    assert np.array_equal(o["status"] == 0, g["ref_success"])
     te = g["te"][None, :]
     y = g["rows"].astype(np.float64)
 
@@ -168,13 +169,14 @@ def test_floor_model_reaches_a_bounded_minimum(gpu_lib, name):
     f_mine = mse(o["k"].astype(float), o["t2"].astype(float), o["sigma"].astype(float))
     f_ref = mse(*g["ref_params"].T)
     f_exact = g["exact_fun"]
-    assert (f_mine <= f_ref * (1 + 1e-4) + 1e-6).mean() >= 0.85
-    same_basin = f_mine <= f_exact * (1 + 1e-5) + 1e-9
-    signal = y[:, 0] > 8 * np.median(y[:, -1])            # decaying signal well above the floor
-    sel = same_basin & signal
+    assert (f_mine <= f_exact * (1 + 1e-4) + 1e-9).mean() > 0.99
     rel = np.abs(o["t2"] - g["exact_params"][:, 1]) / g["exact_params"][:, 1]
-    assert sel.sum() > 20
-    assert (rel[sel] <= T2_RTOL).mean() >= 0.97
+    assert (rel <= T2_RTOL).mean() >= 0.95
+    assert (f_mine <= f_ref * (1 + 1e-4) + 1e-6).mean() >= 0.99
+    # the single-start variant stays selectable (speed): a local minimiser only
+    o1 = run_rows(gpu_lib, g, True, solver="fast", init_mode="loglinear")
+    f1 = mse(o1["k"].astype(float), o1["t2"].astype(float), o1["sigma"].astype(float))
+    assert (f_mine <= f1 * (1 + 1e-5) + 1e-9).mean() > 0.995
 
 
 @pytest.mark.parametrize("solver", ["fast", "lbfgsb"])

@@ -36,18 +36,39 @@ def test_preset_start_reaches_same_minimum():
     assert (np.abs(a["t2"] - b["t2"]) / a["t2"]).max() < 1e-4
 
 
-@pytest.mark.parametrize("name", ["c3_floor_noprior", "c3_floor_prior", "c5_floor_noprior"])
-def test_floor3_not_worse_than_reference_point(name):
-    g = load_golden(name)
-    o = run(g)
-    assert (o["status"] != 0).mean() < 0.01
-    te, y = g["te"][None, :], g["rows"].astype(np.float64)
+def _floor_mse(g, k, t2, s):
+    te, y = g["te"][None, :].astype(float), g["rows"].astype(np.float64)
+    return ((y - np.sqrt(k[:, None] ** 2 * np.exp(-2 * te / t2[:, None]) + s[:, None] ** 2)) ** 2).mean(1)
 
-    def mse(k, t2, s):
-        return ((y - np.sqrt(k[:, None] ** 2 * np.exp(-2 * te / t2[:, None]) + s[:, None] ** 2)) ** 2).mean(1)
-    f_m = mse(o["k"].astype(float), o["t2"].astype(float), o["sigma"].astype(float))
-    f_r = mse(*g["ref_params"].T)
-    assert (f_m <= f_r * (1 + 1e-4) + 1e-6).mean() >= 0.85
+
+@pytest.mark.parametrize("name", ["c3_floor_noprior", "c3_floor_prior", "c5_floor_noprior"])
+def test_floor3_multistart_reaches_the_bounded_minimum(name):
+    """3-parameter fast solver with its default multi-start (T2FIT_INIT_BEST) against the exact bounded minimiser
+    (scipy TRF from a grid of starts, tests/golden/make_exact_multistart.py) on ALL voxels of the fixture: failed set
+    identical to the reference's, cost within 1e-4 of the minimum on > 99 %, T2 within 1e-3 of the minimiser on >= 95 %
+    (the rest are flat valleys: voxels decayed into the noise floor, where equal cost leaves T2 undetermined)."""
+    g = load_golden(name)
+    o = run(g, init=2)
+    assert np.array_equal(o["status"] == 0, g["ref_success"])
+    f_m = _floor_mse(g, o["k"].astype(float), o["t2"].astype(float), o["sigma"].astype(float))
+    f_e = g["exact_fun"]
+    assert (f_m <= f_e * (1 + 1e-4) + 1e-9).mean() > 0.99
+    rel = np.abs(o["t2"] - g["exact_params"][:, 1]) / g["exact_params"][:, 1]
+    assert (rel <= T2_RTOL).mean() >= 0.95
+    # never worse than where the reference's loosely converged run stopped
+    f_r = _floor_mse(g, *g["ref_params"].T)
+    assert (f_m <= f_r * (1 + 1e-4) + 1e-6).mean() >= 0.99
+
+
+@pytest.mark.parametrize("name", ["c3_floor_noprior", "c5_floor_noprior"])
+def test_floor3_single_start_is_a_local_minimiser_only(name):
+    """What the multi-start is for: from the log-linear start alone the solver ends in a local minimum with a cost above
+    the global one on ~12 % of the voxels (documented in DESIGN.md; `init_mode='loglinear'` remains selectable for speed)."""
+    g = load_golden(name)
+    o = run(g, init=0)
+    f_m = _floor_mse(g, o["k"].astype(float), o["t2"].astype(float), o["sigma"].astype(float))
+    worse = (f_m > g["exact_fun"] * (1 + 1e-4) + 1e-9).mean()
+    assert 0.03 < worse < 0.2
 
 
 @pytest.mark.parametrize("fit", ["gaussian", "gaussian_rician"])
@@ -83,3 +104,16 @@ def test_noise_free_signals_converge_in_one_or_two_passes():
     rel = np.abs(o["t2"] - t2) / t2
     assert (o["status"] == 0).all() and o["nit"].max() <= 3
     assert rel.max() < 2e-4 and np.median(rel) < 1e-5
+
+
+def test_sigma_box_without_a_lower_bound():
+    """The fast 3-parameter solver works in sigma^2: a negative or absent (-inf, scipy's None) sigma lower bound means
+    sigma >= 0, not an inverted box; a sigma box entirely below zero is rejected."""
+    g = load_golden("c3_floor_prior")
+    rows, b = g["rows"][:200], [tuple(x) for x in g["bounds"]]
+    ref = hostsim.fit(rows, g["te"], g["fit"], g["x0"], [b[0], b[1], (0.0, b[2][1])], True, init=2)
+    for lo in (-np.inf, -5.0):
+        o = hostsim.fit(rows, g["te"], g["fit"], g["x0"], [b[0], b[1], (lo, b[2][1])], True, init=2)
+        assert np.array_equal(o["t2"], ref["t2"]) and np.array_equal(o["sigma"], ref["sigma"]) and (o["sigma"] >= 0).all()
+    with pytest.raises(ValueError, match="sigma upper bound"):
+        hostsim.fit(rows, g["te"], g["fit"], g["x0"], [b[0], b[1], (-9.0, -1.0)], True)
