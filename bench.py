@@ -255,6 +255,9 @@ def gpu_setup(args):
     c.lib = t2.init(c.local)
     c.torch, c.dist, c.t2 = torch, dist, t2
     c.stream = torch.cuda.current_stream(c.dev)
+    # OMP_NUM_THREADS=1 above is for the forked scipy workers of the CPU arm; torch's own host copies (the loader's casts into
+    # page-locked planes) get the cores back
+    torch.set_num_threads(max(1, host_procs() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", c.world)))))
     return c
 
 
@@ -280,7 +283,7 @@ def sum_over_ranks(c, v):
     return int(t[0])
 
 
-def time_steps(c, step, steps, passes):
+def time_steps(c, step, steps, passes, finish=None):
     """K steps of `passes` passes between two CUDA events on the launching stream, barrier + synchronize on both sides;
     returns the max over ranks of the elapsed milliseconds.  No events inside: a pair around every launch was measured to
     stretch a 68 us c2 pass to 125 us."""
@@ -291,22 +294,28 @@ def time_steps(c, step, steps, passes):
     for _ in range(steps):
         for _ in range(passes):
             step()
+    if finish is not None:
+        finish()                                  # e.g. make the stream wait for collectives still in flight
     e1.record(c.stream)
     barrier(c)
     return max_over_ranks(c, e0.elapsed_time(e1))[0]
 
 
-def pick_passes(c, step, steps):
+def pick_passes(c, step, steps, finish=None):
     """passes per step so that the timed region lasts >= MIN_TIMED_S (same on every rank)."""
     torch = c.torch
     for _ in range(3):
         step()
+    if finish is not None:
+        finish()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 5
+    n = 6
     e0.record(c.stream)
     for _ in range(n):
         step()
+    if finish is not None:
+        finish()
     e1.record(c.stream)
     torch.cuda.synchronize()
     per = max_over_ranks(c, e0.elapsed_time(e1) / n)[0] * 1e-3
@@ -355,9 +364,9 @@ def parity_block(c, cfg, rows, te, oracle, solver):
 def cpu_leg(args, cfg):
     """CPU baseline + the oracle fits the parity block needs; BEFORE CUDA is initialised (the oracle forks workers)."""
     procs = host_procs()
-    rows_all, te = cpu_rows_for(args.config, 20000)
+    rows_all, te = cpu_rows_for(args.config, 200000)
     probe = oracle_fit(rows_all[:64 * procs], te, cfg["fit"], procs)
-    n_s = int(os.environ.get("T2FIT_CPU_SAMPLE", "0")) or int(np.clip(15.0 * probe["rate"], 512, 20000))
+    n_s = int(os.environ.get("T2FIT_CPU_SAMPLE", "0")) or int(np.clip(12.0 * probe["rate"], 512, rows_all.shape[0]))
     rows = np.ascontiguousarray(rows_all[:n_s])
     o = oracle_fit(rows, te, cfg["fit"], procs)
     from oracle import fit_oracle as fo
@@ -426,55 +435,88 @@ def bench_volume(args, cfg):
         sizes_l = [int(v) for v in sizes.tolist()]
         L = -(-max(sizes_l) // D.ALIGN) * D.ALIGN                 # one volume-sized slab per rank, padded to a common length
         names = ["t2", "k", "res", "status"] + ([] if mono else ["sigma"])
-        bufs = {n: torch.zeros(c.world * L, dtype=torch.uint8 if n == "status" else torch.float32, device=c.dev) for n in names}
-        mine = {n: bufs[n][c.rank * L:(c.rank + 1) * L] for n in names}
         rows_d = y_d[idx_d].contiguous()                          # what a loader hands this rank: the rows of its slab, nothing else
         scnt = torch.zeros(4, dtype=torch.int64, device=c.dev)
-        # the call fit_slab_sharded / fit_voxels_into makes, with the structs built once (this loop issues a pass every ~50 us)
-        p2, o2 = _abi.Problem(), _abi.Outputs()
-        keep2 = _fill_problem(p2, fit, fp, te, False, False, 0, 0.0, "auto", solver)
-        p2.echoes, p2.memory, p2.layout, p2.mask_idx = rows_d.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_AOS, None
-        p2.n_vox, p2.n_fit = m, m
-        o2.t2, o2.k, o2.res, o2.status = mine["t2"].data_ptr(), mine["k"].data_ptr(), mine["res"].data_ptr(), mine["status"].data_ptr()
-        o2.sigma = None if mono else mine["sigma"].data_ptr()
-        o2.dense, o2.counts_dev = 0, scnt.data_ptr()
+        # TWO buffer sets: the all-gather of pass i (NCCL's stream) overlaps the fit of pass i+1 (compute stream), as
+        # distributed.SlabPipeline does for a stream of jobs; the structs of the fit call are built once per set (this loop
+        # issues a pass every ~50-100 us)
+        sets = []
+        for _ in range(2):
+            bufs = {n: torch.zeros(c.world * L, dtype=torch.uint8 if n == "status" else torch.float32, device=c.dev) for n in names}
+            mine = {n: bufs[n][c.rank * L:(c.rank + 1) * L] for n in names}
+            p2, o2 = _abi.Problem(), _abi.Outputs()
+            k2 = _fill_problem(p2, fit, fp, te, False, False, 0, 0.0, "auto", solver)
+            p2.echoes, p2.memory, p2.layout, p2.mask_idx = rows_d.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_AOS, None
+            p2.n_vox, p2.n_fit = m, m
+            o2.t2, o2.k, o2.res, o2.status = mine["t2"].data_ptr(), mine["k"].data_ptr(), mine["res"].data_ptr(), mine["status"].data_ptr()
+            o2.sigma = None if mono else mine["sigma"].data_ptr()
+            o2.dense, o2.counts_dev = 0, scnt.data_ptr()
+            sets.append({"bufs": bufs, "mine": mine, "p": p2, "o": o2, "keep": k2, "pending": None})
+        bufs, mine = sets[0]["bufs"], sets[0]["mine"]
+        state = {"i": 0}
 
-        def fit_only_pass():
-            rc = lib.t2fit_run(C.byref(p2), C.byref(o2), c.stream.cuda_stream)
+        def fit_set(st):
+            rc = lib.t2fit_run(C.byref(st["p"]), C.byref(st["o"]), c.stream.cuda_stream)
             if rc:
                 raise RuntimeError(lib.t2fit_last_error())
 
-        def gather_fields():
-            for n in names:
-                c.dist.all_gather_into_tensor(bufs[n], mine[n])
-        try:                                                      # one NCCL group launch for the four fields if torch offers it
+        def fit_only_pass():
+            fit_set(sets[0])
+
+        try:                                                      # one NCCL group launch for the fields of a pass if torch offers it
             from torch.distributed import _coalescing_manager
 
-            def gather_coalesced():
-                with _coalescing_manager(device=c.dev):
+            def gather_async(st):
+                with _coalescing_manager(device=c.dev, async_ops=True) as cm:
                     for n in names:
-                        c.dist.all_gather_into_tensor(bufs[n], mine[n])
-            gather_coalesced()
+                        c.dist.all_gather_into_tensor(st["bufs"][n], st["mine"][n])
+                return [cm]
+            for w in gather_async(sets[0]):
+                w.wait()
             torch.cuda.synchronize()
-            gather = gather_coalesced
+            coalesced = True
         except Exception:
-            gather = gather_fields
+            coalesced = False
 
-        def sharded_pass():
-            fit_only_pass()
-            gather()
+            def gather_async(st):
+                return [c.dist.all_gather_into_tensor(st["bufs"][n], st["mine"][n], async_op=True) for n in names]
+
+        def wait_set(st):
+            if st["pending"]:
+                for w in st["pending"]:
+                    w.wait()                                      # the compute stream waits for that set's gathers; the host does not
+                st["pending"] = None
+
+        def sharded_pass():                                       # pipelined: gather(i) || fit(i+1)
+            st = sets[state["i"] & 1]
+            state["i"] += 1
+            wait_set(st)                                          # its buffers are about to be overwritten
+            fit_set(st)
+            st["pending"] = gather_async(st)
+
+        def sharded_finish():
+            for st in sets:
+                wait_set(st)
+
+        def single_job_pass():                                    # one job alone: fit, then its gather, nothing overlapped
+            fit_set(sets[0])
+            for w in gather_async(sets[0]):
+                w.wait()
 
     sampler = ClockSampler(c.local) if c.rank == 0 else None
     if sampler:
         sampler.start()
     main_pass = sharded_pass if c.world > 1 else dense_pass
+    main_finish = sharded_finish if c.world > 1 else None
     for _ in range(max(3, args.warmup)):
         main_pass()
-    passes = pick_passes(c, main_pass, args.steps)
+    passes = pick_passes(c, main_pass, args.steps, main_finish)
     for _ in range(max(3, args.warmup)):                  # W warm-up STEPS of the final shape
         for _ in range(min(passes, 50)):
             main_pass()
-    elapsed_ms = time_steps(c, main_pass, args.steps, passes)
+    if main_finish:
+        main_finish()
+    elapsed_ms = time_steps(c, main_pass, args.steps, passes, main_finish)
     clocks = sampler.stop() if sampler else None
     m_total = sum_over_ranks(c, m)
     value = m_total * args.steps * passes / (elapsed_ms * 1e-3)
@@ -484,7 +526,10 @@ def bench_volume(args, cfg):
     if c.world > 1:
         # the gather delivered, bit for bit, what every owner computed (every rank checks every slab)
         bounds = [(r * L, r * L + sizes_l[r]) for r in range(c.world)]
+        sharded_finish()
         torch.cuda.synchronize()
+        for st in sets[1:]:                               # both buffer sets hold the same job
+            assert all(bool(torch.equal(st["bufs"][n], bufs[n])) for n in names), "buffer sets differ"
         local_tab = slab_hashes(torch, [mine[n] for n in names], [(0, m)])[0]
         tabs = torch.zeros((c.world, len(names)), dtype=torch.int64, device=c.dev)
         c.dist.all_gather_into_tensor(tabs, local_tab)
@@ -500,14 +545,20 @@ def bench_volume(args, cfg):
         assert int(ok_all[0]) == 1, "sharded fit + gather differs from the single-GPU fit"
         p_fit = pick_passes(c, fit_only_pass, args.steps)
         fit_ms = time_steps(c, fit_only_pass, args.steps, p_fit) / (args.steps * p_fit)
+        p_one = pick_passes(c, single_job_pass, args.steps)
+        one_ms = time_steps(c, single_job_pass, args.steps, p_one) / (args.steps * p_one)
         p_rep = pick_passes(c, dense_pass, args.steps)
         rep_ms = time_steps(c, dense_pass, args.steps, p_rep) / (args.steps * p_rep)
         bytes_in = sum((c.world - 1) * L * (1 if n == "status" else 4) for n in names)
         extra["sharded"] = {"op": "fit of the rank's slab (compact results into its chunk of the gather buffers) + in-place NCCL "
-                                  "all_gather_into_tensor per field (" + ", ".join(names) + "; status as uint8)",
-                            "ms_per_pass": pass_ms, "fit_only_ms": fit_ms, "gather_ms": pass_ms - fit_ms,
+                                  "all_gather_into_tensor per field (" + ", ".join(names) + "; status as uint8, "
+                                  + ("one coalesced group launch" if coalesced else "one launch per field") + "); two buffer sets: "
+                                  "the gather of pass i overlaps the fit of pass i+1",
+                            "ms_per_pass": pass_ms, "fit_only_ms": fit_ms, "single_job_ms": one_ms, "single_job_gather_ms": one_ms - fit_ms,
+                            "single_job_value": m_total / (one_ms * 1e-3),
                             "gather_bytes_received_per_rank": int(bytes_in),
-                            "gather_gbs_received_per_rank": bytes_in / max(pass_ms - fit_ms, 1e-9) / 1e6,
+                            "gather_gbs_received_per_rank_single_job": bytes_in / max(one_ms - fit_ms, 1e-9) / 1e6,
+                            "gather_gbs_received_per_rank_pipelined": bytes_in / max(pass_ms, 1e-9) / 1e6,
                             "equals_single_gpu_fit": True, "voxels_per_rank": sizes_l,
                             "note": "every rank ends with the full vectors: it RECEIVES (N-1) slabs per pass, which bounds the pass at "
                                     "(N-1)*L*13 B / NVLink ingest whatever the fit costs (DESIGN.md section 5)"}
@@ -662,7 +713,8 @@ def bench_volume(args, cfg):
                            "l2": "inputs + outputs of a pass (%.0f MB) exceed the 126 MB L2" % ((flat.nbytes + 16.0 * n_vox) / 1e6),
                            "timed_region_s": elapsed_ms * 1e-3,
                            "step": ("%d back-to-back passes; a pass = " % passes) + (
-                               "fit of the rank's slab + in-place all-gather of the result vectors (ONE job of %d slabs)" % c.world if c.world > 1 else
+                               "fit of the rank's slab + in-place all-gather of the result vectors (a job of %d slabs); the gather of pass i "
+                               "overlaps the fit of pass i+1 (two buffer sets) -- `sharded.single_job_ms` is one job alone" % c.world if c.world > 1 else
                                "zero the four dense maps + fit + residuals + scatter of one volume"),
                            "scale": SCALE},
                 "roofline": roofline, "roofline_fp32": roof_fp32, "cpu_baseline": cpu[0] if cpu else None, "parity": parity,
@@ -673,8 +725,6 @@ def bench_volume(args, cfg):
     if c.world > 1:
         c.dist.destroy_process_group()
     del keep
-    if c.world > 1:
-        del keep2
 
 
 def bench_series(args, cfg):

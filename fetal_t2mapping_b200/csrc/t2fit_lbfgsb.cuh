@@ -805,11 +805,9 @@ struct Solver {
         // while formk was skipped (no free variable at the Cauchy point) leaves its row unset, and the Cauchy search
         // returns before clearing c when no variable moves.  Without this the result of a voxel depended on the voxel
         // the thread had fitted before (1 of 1500 voxels of the c3 fixture).
-        T2_ROLLED for (int i = 0; i < M2; ++i) { T2_ROLLED for (int j = 0; j < M2; ++j) { wn1[i][j] = 0.0; wn[i][j] = 0.0; } pc[i] = 0.0; cc[i] = 0.0; }
-        T2_ROLLED for (int i = 0; i < kM; ++i) {
-            T2_ROLLED for (int j = 0; j < kM; ++j) { sy[i][j] = 0.0; ss[i][j] = 0.0; wt[i][j] = 0.0; }
-            T2_ROLLED for (int j = 0; j < N; ++j) { ws[i][j] = 0.0; wy[i][j] = 0.0; }
-        }
+        // (WN1 and the Cauchy vectors are the arrays with such reads; every used entry of WS, WY, S'Y, S'S, WT and WN is
+        // computed during the run before it is read)
+        T2_ROLLED for (int i = 0; i < M2; ++i) { T2_ROLLED for (int j = 0; j <= i; ++j) wn1[i][j] = 0.0; pc[i] = 0.0; cc[i] = 0.0; }
     }
 
     // f, g at the start point have been evaluated

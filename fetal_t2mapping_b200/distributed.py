@@ -16,7 +16,8 @@ volume, so a brain mask does not unbalance the GPUs.
   before the collective: an error flag is all-reduced first and every rank raises, as ``pool.map`` aborts the whole map
   in the reference -- nobody is left waiting in a collective;
 * ``fit_voxels_fused_gather``: no collective at all -- the fit kernels' epilogues store their slab straight into the
-  root GPU's buffer over NVLink (CUDA IPC peer mapping).
+  root GPU's buffer over NVLink (CUDA IPC peer mapping);
+* ``SlabPipeline``: a stream of sharded jobs with the gather of job i overlapping the fit of job i+1 (double-buffered).
 
 Host logic only -- the fit of a slab is ``api.fit_voxels_batch`` (CUDA).  ``fit_fn`` is injectable so the partition /
 gather / error logic is testable with ``gloo`` on CPU.
@@ -26,7 +27,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = ["slab_bounds", "slab_length", "fit_voxels_sharded", "fit_slab_sharded", "gather_slabs", "gather_fields",
-           "fit_voxels_fused_gather", "ShardError"]
+           "fit_voxels_fused_gather", "ShardError", "SlabPipeline"]
 
 ALIGN = 128
 FIELDS = ("t2", "k", "sigma", "res", "status")
@@ -247,3 +248,84 @@ def fit_voxels_fused_gather(reshaped_t2w, mask_indices, TEeffs, fit, fit_params,
             lib.t2fit_shared_free(ptr)
         else:
             lib.t2fit_shared_close(ptr)
+
+
+class SlabPipeline:
+    """A STREAM of sharded jobs of one shape (e.g. the volumes of a series, each cut into ``world`` slabs): the all-gather of
+    job i runs on NCCL's stream while the fit of job i+1 runs on the compute stream (``depth`` buffer sets, default 2).
+
+    One job alone costs fit + gather; a stream of jobs costs max(fit, gather) per job.  Every rank RECEIVES (world - 1) slabs
+    per job, so at 8 GPUs the gather of c2-sized slabs (7 x 21 MB per rank) is the longer of the two whatever the fit costs --
+    overlapping is what is left to do about it.
+
+    ``submit(rows, ...)`` enqueues the fit of this rank's slab (compact results straight into its chunk of the slot's gather
+    buffers) and the asynchronous in-place all-gathers, and returns the slot; ``result(slot)`` makes the current stream wait
+    for that slot's gathers and returns the full vectors (views of the slot's buffers: valid until the slot is reused,
+    ``depth`` submits later).  Status histograms are accumulated per slot (``counts(slot)``)."""
+
+    def __init__(self, n_fit, fit, *, depth=2, fields=None, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_fit, self.fit = int(n_fit), fit
+        self.L = slab_length(self.n_fit, self.world)
+        self.a, self.b = slab_bounds(self.n_fit, self.world)[self.rank]
+        mono = fit == "gaussian"
+        self.fields = tuple(fields) if fields else (("t2", "k", "res", "status") if mono else ("t2", "k", "sigma", "res", "status"))
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.slots = []
+        for _ in range(max(1, depth)):
+            bufs = {n: torch.zeros(self.world * self.L, dtype=torch.uint8 if n == "status" else torch.float32, device=dev)
+                    for n in self.fields}
+            mine = {n: bufs[n][self.rank * self.L:(self.rank + 1) * self.L] for n in self.fields}
+            self.slots.append({"bufs": bufs, "mine": mine, "works": [], "counts": torch.zeros(4, dtype=torch.int64, device=dev)})
+        self.next = 0
+
+    def submit(self, slab_rows, TEeffs, fit_params, prior=True, norm=False, *, solver="auto"):
+        from .api import fit_voxels_into
+        s = self.next
+        self.next = (self.next + 1) % len(self.slots)
+        slot = self.slots[s]
+        for w in slot["works"]:                     # the slot's previous gathers must have finished before the fit overwrites it
+            w.wait()
+        slot["works"] = []
+        if slab_rows.shape[0] != self.b - self.a:
+            raise IndexError(f"rank {self.rank} holds {slab_rows.shape[0]} rows, its slab has {self.b - self.a}")
+        slot["counts"].zero_()
+        out = {n: slot["mine"][n].data_ptr() for n in ("t2", "k", "res")}
+        for n in ("sigma", "status"):
+            if n in slot["mine"]:
+                out[n] = slot["mine"][n].data_ptr()
+        extra = {}
+        if self.fit != "gaussian" and "sigma" not in slot["mine"]:
+            extra["sigma"] = self.torch.empty(max(self.b - self.a, 1), dtype=self.torch.float32, device=slab_rows.device)
+            out["sigma"] = extra["sigma"].data_ptr()
+        if self.b > self.a:
+            fit_voxels_into(slab_rows, None, TEeffs, self.fit, fit_params, prior, norm, out, solver=solver, counts=slot["counts"])
+        slot["keep"] = extra
+        # asynchronous collectives: NCCL's stream waits for the fit just enqueued; the compute stream does NOT wait for them
+        slot["works"] = [self.dist.all_gather_into_tensor(slot["bufs"][n], slot["mine"][n], group=self.group, async_op=True)
+                         for n in self.fields]
+        return s
+
+    def result(self, s, check=False):
+        slot = self.slots[s]
+        for w in slot["works"]:
+            w.wait()                                # the current stream waits for the gathers (no host synchronisation)
+        slot["works"] = []
+        if check:                                   # synchronises: raise what the reference raises, on every rank
+            exc = None
+            try:
+                from .api import _raise_for_counts
+                _raise_for_counts([int(v) for v in slot["counts"].cpu()])
+            except Exception as e:                  # noqa: BLE001
+                exc = e
+            _agree_or_raise(exc, slot["counts"].device, self.group)
+        return {n: slot["bufs"][n][:self.n_fit] for n in self.fields}
+
+    def drain(self):
+        for s in range(len(self.slots)):
+            for w in self.slots[s]["works"]:
+                w.wait()
+            self.slots[s]["works"] = []

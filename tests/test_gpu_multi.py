@@ -34,6 +34,38 @@ def _worker(rank, world, port, tmp, fit):
         for name in ("t2", "k", "sigma", "res"):
             assert torch.equal(fused[name], out[name]), name
         assert torch.equal(fused["status"], out["status"])
+    # every rank holding ONLY the rows of its own slab (what a loader hands each GPU)
+    a, b = D.slab_bounds(idx.numel(), world)[rank]
+    out2 = D.fit_slab_sharded(flat[idx[a:b]].contiguous(), idx.numel(), te, fit, fp, prior=False)
+    for name in ("t2", "k", "sigma", "res", "status"):
+        assert torch.equal(out2[name], out[name]), name
+    assert out["status"].dtype == torch.uint8
+    # one rank's slab holds a voxel scipy rejects (--no_prior, S(TE0) > 10000): EVERY rank raises, nobody hangs in the gather
+    bad = flat.clone()
+    bad[idx[idx.numel() - 3], 0] = 2.0e4                       # lies in the last rank's slab
+    for call in (lambda: D.fit_voxels_sharded(bad, idx, te, fit, fp, prior=False),
+                 lambda: D.fit_voxels_fused_gather(bad, idx, te, fit, fp, prior=False, root=0)):
+        try:
+            call()
+            raised = False
+        except ValueError as e:
+            raised = "upper bound" in str(e)
+        assert raised, f"rank {rank} did not raise"
+    # a stream of jobs through the double-buffered pipeline (gather of job i overlaps the fit of job i+1)
+    pipe = D.SlabPipeline(idx.numel(), fit)
+    rows = flat[idx[a:b]].contiguous()
+    rows2 = (rows * 1.5).contiguous()
+    slots = [pipe.submit(r_, te, fp, prior=False) for r_ in (rows, rows2, rows)]
+    last = pipe.result(slots[2], check=True)
+    torch.cuda.synchronize()
+    for name in ("t2", "k", "res", "status"):
+        assert torch.equal(last[name], out[name]), name
+    mid = pipe.result(slots[1])
+    torch.cuda.synchronize()
+    assert not torch.equal(mid["k"], out["k"]) and torch.allclose(mid["t2"], out["t2"], rtol=2e-3)   # k scales with the signal, T2 does not
+    pipe.drain()
+    again = D.fit_voxels_sharded(flat, idx, te, fit, fp, prior=False)      # and the next clean job is unaffected
+    assert torch.equal(again["t2"], out["t2"])
     np.save(os.path.join(tmp, f"t2_{rank}.npy"), out["t2"].cpu().numpy())
     np.save(os.path.join(tmp, f"st_{rank}.npy"), out["status"].cpu().numpy())
     if rank == 0:

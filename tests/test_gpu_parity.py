@@ -357,7 +357,7 @@ def test_fused_zero_fill_ragged_volumes(gpu_lib, fit, solver, shape, route, dens
     _, fp = gpu_lib.preset(fit, True)
     lib = gpu_lib.init()
     p, o = _abi.Problem(), _abi.Outputs()
-    keep = _fill_problem(p, fit, fp, te, False, False, 0, 0.0, "loglinear", solver)
+    keep = _fill_problem(p, fit, fp, te, False, False, 0, 0.0, "auto", solver)
     yd, idxd, md = torch.from_numpy(y).cuda(), torch.from_numpy(idx).cuda(), torch.from_numpy(mask).cuda()
     maps = torch.full((4, n), float("nan"), device="cuda")
     p.echoes, p.memory, p.layout, p.mask_idx, p.n_vox, p.n_fit = yd.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_AOS, idxd.data_ptr(), n, idx.size
