@@ -433,9 +433,13 @@ def bench_volume(args, cfg):
         sizes[c.rank] = m
         c.dist.all_reduce(sizes)
         sizes_l = [int(v) for v in sizes.tolist()]
-        L = -(-max(sizes_l) // D.ALIGN) * D.ALIGN                 # one volume-sized slab per rank, padded to a common length
+        # ONE job of `world` slabs: rank r's slab = the first m_s masked voxels of its volume, m_s = the common 128-aligned slab
+        # length (distributed.slab_bounds cuts at multiples of 128: at most 127 of a volume's 1.6 M masked voxels are left out)
+        m_s = (min(sizes_l) // D.ALIGN) * D.ALIGN
+        L, n_job = m_s, c.world * m_s
+        assert D.slab_bounds(n_job, c.world)[c.rank] == (c.rank * L, (c.rank + 1) * L)
         names = ["t2", "k", "res", "status"] + ([] if mono else ["sigma"])
-        rows_d = y_d[idx_d].contiguous()                          # what a loader hands this rank: the rows of its slab, nothing else
+        rows_d = y_d[idx_d[:m_s]].contiguous()                    # what a loader hands this rank: the rows of its slab, nothing else
         scnt = torch.zeros(4, dtype=torch.int64, device=c.dev)
         # TWO buffer sets: the all-gather of pass i (NCCL's stream) overlaps the fit of pass i+1 (compute stream), as
         # distributed.SlabPipeline does for a stream of jobs; the structs of the fit call are built once per set (this loop
@@ -447,7 +451,7 @@ def bench_volume(args, cfg):
             p2, o2 = _abi.Problem(), _abi.Outputs()
             k2 = _fill_problem(p2, fit, fp, te, False, False, 0, 0.0, "auto", solver)
             p2.echoes, p2.memory, p2.layout, p2.mask_idx = rows_d.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_AOS, None
-            p2.n_vox, p2.n_fit = m, m
+            p2.n_vox, p2.n_fit = m_s, m_s
             o2.t2, o2.k, o2.res, o2.status = mine["t2"].data_ptr(), mine["k"].data_ptr(), mine["res"].data_ptr(), mine["status"].data_ptr()
             o2.sigma = None if mono else mine["sigma"].data_ptr()
             o2.dense, o2.counts_dev = 0, scnt.data_ptr()
@@ -503,11 +507,27 @@ def bench_volume(args, cfg):
             for w in gather_async(sets[0]):
                 w.wait()
 
+        # the all-gather FUSED into the fit kernels (distributed.FusedAllGather): peer stores from the epilogue + a one-element
+        # all-reduce as the barrier; falls back to the NCCL path on every rank if CUDA IPC is not available
+        fa = None
+        try:
+            fa = D.FusedAllGather(n_job, fit)
+            ok_f = 1
+        except Exception as ex:
+            ok_f, fused_err = 0, repr(ex)
+        okt = torch.tensor([ok_f], device=c.dev, dtype=torch.int32)
+        c.dist.all_reduce(okt, op=c.dist.ReduceOp.MIN)
+        if int(okt[0]) == 0:
+            fa = None
+
+        def fused_pass():
+            fa.submit(rows_d, te, fp, prior=False, norm=False, solver=solver)
+
     sampler = ClockSampler(c.local) if c.rank == 0 else None
     if sampler:
         sampler.start()
-    main_pass = sharded_pass if c.world > 1 else dense_pass
-    main_finish = sharded_finish if c.world > 1 else None
+    main_pass = (fused_pass if fa is not None else sharded_pass) if c.world > 1 else dense_pass
+    main_finish = (None if fa is not None else sharded_finish) if c.world > 1 else None
     for _ in range(max(3, args.warmup)):
         main_pass()
     passes = pick_passes(c, main_pass, args.steps, main_finish)
@@ -518,52 +538,71 @@ def bench_volume(args, cfg):
         main_finish()
     elapsed_ms = time_steps(c, main_pass, args.steps, passes, main_finish)
     clocks = sampler.stop() if sampler else None
-    m_total = sum_over_ranks(c, m)
+    m_total = sum_over_ranks(c, m_s if c.world > 1 else m)
     value = m_total * args.steps * passes / (elapsed_ms * 1e-3)
     pass_ms = elapsed_ms / (args.steps * passes)
 
     extra = {}
     if c.world > 1:
-        # the gather delivered, bit for bit, what every owner computed (every rank checks every slab)
-        bounds = [(r * L, r * L + sizes_l[r]) for r in range(c.world)]
+        # the gather delivered, bit for bit, what every owner computed (every rank checks every slab) -- for both forms
+        bounds = [(r * L, (r + 1) * L) for r in range(c.world)]
+
+        def check_gathered(full, local):
+            local_tab = slab_hashes(torch, [local[n] for n in names], [(0, m_s)])[0]
+            tabs = torch.zeros((c.world, len(names)), dtype=torch.int64, device=c.dev)
+            c.dist.all_gather_into_tensor(tabs, local_tab)
+            return bool(torch.equal(tabs, slab_hashes(torch, [full[n] for n in names], bounds)))
+        for _ in range(4):                                # (the timed loop may have ended on either buffer set)
+            sharded_pass()
         sharded_finish()
         torch.cuda.synchronize()
-        for st in sets[1:]:                               # both buffer sets hold the same job
-            assert all(bool(torch.equal(st["bufs"][n], bufs[n])) for n in names), "buffer sets differ"
-        local_tab = slab_hashes(torch, [mine[n] for n in names], [(0, m)])[0]
-        tabs = torch.zeros((c.world, len(names)), dtype=torch.int64, device=c.dev)
-        c.dist.all_gather_into_tensor(tabs, local_tab)
-        got = slab_hashes(torch, [bufs[n] for n in names], bounds)
-        gather_ok = bool(torch.equal(tabs, got)) and bool(torch.equal(bufs["t2"][c.rank * L:c.rank * L + m], mine["t2"][:m]))
+        ok_g = all(check_gathered(st["bufs"], {n: st["mine"][n] for n in names}) for st in sets)
         # and the slab fit itself equals the single-GPU dense-map fit of the same volume
         dense_pass()
         torch.cuda.synchronize()
-        fit_ok = bool(torch.equal(mine["t2"][:m], maps[0][idx_d])) and bool(torch.equal(mine["res"][:m], maps[3][idx_d])) \
-            and bool(torch.equal(mine["status"][:m], st_d))
-        ok_all = torch.tensor([int(gather_ok and fit_ok)], device=c.dev, dtype=torch.int32)
+        sel = idx_d[:m_s]
+        fit_ok = bool(torch.equal(mine["t2"][:m_s], maps[0][sel])) and bool(torch.equal(mine["res"][:m_s], maps[3][sel])) \
+            and bool(torch.equal(mine["status"][:m_s], st_d[:m_s]))
+        ok_fused = None
+        if fa is not None:
+            s0 = fa.submit(rows_d, te, fp, prior=False, norm=False, solver=solver)
+            rf = fa.result(s0)
+            torch.cuda.synchronize()
+            ok_fused = check_gathered(rf, {n: rf[n][c.rank * L:(c.rank + 1) * L] for n in names}) and \
+                all(bool(torch.equal(rf[n], bufs[n][:n_job])) for n in names)
+        ok_all = torch.tensor([int(ok_g and fit_ok and ok_fused is not False)], device=c.dev, dtype=torch.int32)
         c.dist.all_reduce(ok_all, op=c.dist.ReduceOp.MIN)
         assert int(ok_all[0]) == 1, "sharded fit + gather differs from the single-GPU fit"
         p_fit = pick_passes(c, fit_only_pass, args.steps)
         fit_ms = time_steps(c, fit_only_pass, args.steps, p_fit) / (args.steps * p_fit)
         p_one = pick_passes(c, single_job_pass, args.steps)
         one_ms = time_steps(c, single_job_pass, args.steps, p_one) / (args.steps * p_one)
+        p_pipe = pick_passes(c, sharded_pass, args.steps, sharded_finish)
+        pipe_ms = time_steps(c, sharded_pass, args.steps, p_pipe, sharded_finish) / (args.steps * p_pipe)
         p_rep = pick_passes(c, dense_pass, args.steps)
         rep_ms = time_steps(c, dense_pass, args.steps, p_rep) / (args.steps * p_rep)
         bytes_in = sum((c.world - 1) * L * (1 if n == "status" else 4) for n in names)
-        extra["sharded"] = {"op": "fit of the rank's slab (compact results into its chunk of the gather buffers) + in-place NCCL "
-                                  "all_gather_into_tensor per field (" + ", ".join(names) + "; status as uint8, "
-                                  + ("one coalesced group launch" if coalesced else "one launch per field") + "); two buffer sets: "
-                                  "the gather of pass i overlaps the fit of pass i+1",
-                            "ms_per_pass": pass_ms, "fit_only_ms": fit_ms, "single_job_ms": one_ms, "single_job_gather_ms": one_ms - fit_ms,
-                            "single_job_value": m_total / (one_ms * 1e-3),
-                            "gather_bytes_received_per_rank": int(bytes_in),
-                            "gather_gbs_received_per_rank_single_job": bytes_in / max(one_ms - fit_ms, 1e-9) / 1e6,
-                            "gather_gbs_received_per_rank_pipelined": bytes_in / max(pass_ms, 1e-9) / 1e6,
-                            "equals_single_gpu_fit": True, "voxels_per_rank": sizes_l,
+        extra["sharded"] = {"form": "fused all-gather" if fa is not None else "NCCL all-gather, pipelined",
+                            "op": ("fit of the rank's slab; the kernel epilogue stores the compact results (" + ", ".join(names) + "; status as uint8) into "
+                                   "its own buffer and, over NVLink, into every peer's buffer (CUDA-IPC peer stores); a one-element NCCL all-reduce "
+                                   "ordered after the kernels is the barrier (distributed.FusedAllGather)") if fa is not None else
+                                  "fit + in-place NCCL all_gather_into_tensor per field, two buffer sets (distributed.SlabPipeline)",
+                            "ms_per_pass": pass_ms, "fit_only_ms": fit_ms, "gather_bytes_received_per_rank": int(bytes_in),
+                            "gather_gbs_received_per_rank": bytes_in / max(pass_ms, 1e-9) / 1e6,
+                            "equals_single_gpu_fit": True, "gathered_equals_owner": True, "voxels_per_rank": m_s,
                             "note": "every rank ends with the full vectors: it RECEIVES (N-1) slabs per pass, which bounds the pass at "
-                                    "(N-1)*L*13 B / NVLink ingest whatever the fit costs (DESIGN.md section 5)"}
-        extra["replicas"] = {"value": m_total / (rep_ms * 1e-3), "ms_per_pass": rep_ms,
+                                    "(N-1) * slab * 13 B / NVLink ingest whatever the fit costs (DESIGN.md section 5)"}
+        extra["sharded_nccl"] = {"op": "fit + in-place NCCL all_gather_into_tensor per field (" + ("one coalesced group launch" if coalesced else "one launch per field")
+                                       + "), status as uint8", "pipelined_ms_per_pass": pipe_ms, "pipelined_value": m_total / (pipe_ms * 1e-3),
+                                 "single_job_ms": one_ms, "single_job_gather_ms": one_ms - fit_ms, "single_job_value": m_total / (one_ms * 1e-3),
+                                 "gather_gbs_received_per_rank_single_job": bytes_in / max(one_ms - fit_ms, 1e-9) / 1e6,
+                                 "what": "pipelined: the gather of pass i overlaps the fit of pass i+1; single job: nothing overlapped"}
+        if fa is None:
+            extra["sharded"]["fused_unavailable"] = fused_err if not ok_f else "CUDA IPC failed on another rank"
+        extra["replicas"] = {"value": sum_over_ranks(c, m) / (rep_ms * 1e-3), "ms_per_pass": rep_ms,
                              "what": "N independent dense-map passes (zero-fill + fit + scatter of one volume per rank), no gather -- round 1's value"}
+        if fa is not None:
+            fa.close()
     else:
         fit_ms = None
 
@@ -709,12 +748,11 @@ def bench_volume(args, cfg):
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if solver == "fast" else "f64", "data": "synthetic",
                 "config": {"workload": cfg["workload"], "solver": solver, "passes_per_step": passes, "ms_per_pass": pass_ms,
-                           "masked_voxels_per_gpu": int(m), "failed_voxels": n_failed, "volume_voxels_per_gpu": int(n_vox), "n_echo": int(n_echo),
+                           "masked_voxels_per_gpu": int(m_s if c.world > 1 else m), "failed_voxels": n_failed, "volume_voxels_per_gpu": int(n_vox), "n_echo": int(n_echo),
                            "l2": "inputs + outputs of a pass (%.0f MB) exceed the 126 MB L2" % ((flat.nbytes + 16.0 * n_vox) / 1e6),
                            "timed_region_s": elapsed_ms * 1e-3,
                            "step": ("%d back-to-back passes; a pass = " % passes) + (
-                               "fit of the rank's slab + in-place all-gather of the result vectors (a job of %d slabs); the gather of pass i "
-                               "overlaps the fit of pass i+1 (two buffer sets) -- `sharded.single_job_ms` is one job alone" % c.world if c.world > 1 else
+                               "ONE job of %d slabs: fit of the rank's slab + all-gather of the result vectors to every rank (see `sharded.form`)" % c.world if c.world > 1 else
                                "zero the four dense maps + fit + residuals + scatter of one volume"),
                            "scale": SCALE},
                 "roofline": roofline, "roofline_fp32": roof_fp32, "cpu_baseline": cpu[0] if cpu else None, "parity": parity,

@@ -10,6 +10,7 @@ import os
 
 ABI_VERSION = 4
 MAX_ECHO = 32
+MAX_DUP = 7
 
 MODEL_GAUSSIAN = 0
 MODEL_GAUSSIAN_RICIAN = 1
@@ -86,6 +87,12 @@ class Outputs(C.Structure):
         ("trace_len", C.c_void_p),
         ("trace_cap", C.c_int32),
         ("zero_fill_mask", C.c_void_p),
+        ("n_dup", C.c_int32),
+        ("dup_t2", C.c_void_p * MAX_DUP),
+        ("dup_k", C.c_void_p * MAX_DUP),
+        ("dup_sigma", C.c_void_p * MAX_DUP),
+        ("dup_res", C.c_void_p * MAX_DUP),
+        ("dup_status", C.c_void_p * MAX_DUP),
         ("counts_dev", C.c_void_p),
     ]
 

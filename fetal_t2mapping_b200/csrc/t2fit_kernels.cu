@@ -72,6 +72,8 @@ struct KernelIO {
     int64_t fill_words;          // n_vox / 4 full words; the ragged tail is left to thread 0
     int64_t fill_nvox;
     int fill_wpb;                // mask words per block (host: ceil(fill_words / blocks), rounded up to whole 128-byte lines of the maps)
+    // fused all-gather: compact results are also stored to these peer-GPU destinations (t2fit_outputs::dup_*)
+    struct Dup { int n; float* t2[T2FIT_MAX_DUP]; float* k[T2FIT_MAX_DUP]; float* sigma[T2FIT_MAX_DUP]; float* res[T2FIT_MAX_DUP]; uint8_t* status[T2FIT_MAX_DUP]; } dup;
     // > 0: idx comes unchecked from the caller's host memory -- entries outside [0, n_rows) are counted in counts[0] and
     // read row 0 instead (the host raises IndexError afterwards, as the reference's fancy indexing would)
     int64_t n_rows;
@@ -83,6 +85,16 @@ __device__ __forceinline__ int64_t guarded_row(const KernelIO& io, int64_t row) 
         row = 0;
     }
     return row;
+}
+// the fused all-gather: element i of this launch to the same slot of every peer buffer (NVLink peer stores)
+__device__ __forceinline__ void store_dups(const KernelIO& io, int64_t i, float t2, float k, float sigma, float res, int status) {
+    for (int j = 0; j < io.dup.n; ++j) {
+        if (io.dup.t2[j]) io.dup.t2[j][i] = t2;
+        if (io.dup.k[j]) io.dup.k[j][i] = k;
+        if (io.dup.sigma[j]) io.dup.sigma[j][i] = sigma;
+        if (io.dup.res[j]) io.dup.res[j][i] = res;
+        if (io.dup.status[j]) io.dup.status[j][i] = (uint8_t)status;
+    }
 }
 __device__ __forceinline__ bool has_idx(const KernelIO& io) { return io.idx != nullptr || io.idx32 != nullptr; }
 // mask_indices[i] (int64 or int32 vector), unchecked
@@ -304,6 +316,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
         if (io.fun) io.fun[i] = f.fun;
         if (io.nit) io.nit[i] = f.nit;
         if (io.status) io.status[i] = (uint8_t)f.status;
+        if (io.dup.n) store_dups(io, i, f.t2, f.k, f.sigma, f.res, f.status);
     }
     // warp-aggregated status histogram: one atomic per warp per non-OK status (normally none)
     const int st = valid ? f.status : 0;
@@ -362,6 +375,7 @@ __global__ void __launch_bounds__(kQBlock, queue_min_blocks(E)) floor_queue_kern
                 if (io.fun) io.fun[i] = f.fun;
                 if (io.nit) io.nit[i] = f.nit;
                 if (io.status) io.status[i] = (uint8_t)f.status;
+                if (io.dup.n) store_dups(io, i, f.t2, f.k, f.sigma, f.res, f.status);
                 cnt1 += f.status == 1; cnt2 += f.status == 2; cnt3 += f.status == 3;
                 have = false;
             }
@@ -429,6 +443,7 @@ __device__ __noinline__ void lb_store(const lb::LbConsts& c, const KernelIO& io,
     if (io.nit) io.nit[i] = v.nit;
     if (io.status) io.status[i] = (uint8_t)v.status;
     if (io.trace_len) io.trace_len[i] = v.trace_len;
+    if (io.dup.n) store_dups(io, i, t2f, kf, sf, (float)(acc / (double)E), v.status);
     if (v.status != 0 && io.counts) atomicAdd(io.counts + v.status, 1ull);
 }
 
@@ -559,6 +574,7 @@ __global__ void __launch_bounds__(G == 8 ? 256 : G == 16 ? 512 : 1024, 1) lbfgsb
                 if (io.nit) io.nit[cur] = v.nit;
                 if (io.status) io.status[cur] = (uint8_t)v.status;
                 if (io.trace_len) io.trace_len[cur] = v.trace_len;
+                if (io.dup.n) store_dups(io, cur, t2f, kf, sf, (float)(acc / (double)E), v.status);
                 if (v.status != 0 && io.counts) atomicAdd(io.counts + v.status, 1ull);
             }
             grp.sync();
@@ -1576,6 +1592,13 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     }
     io.vec_ok = (reinterpret_cast<uintptr_t>(p->echoes) % 16) == 0;
     io.layout = p->layout;
+    if (o->n_dup < 0 || o->n_dup > T2FIT_MAX_DUP) return fail(T2FIT_EINVAL, "n_dup out of range");
+    if (o->n_dup > 0 && o->dense) return fail(T2FIT_EINVAL, "the fused all-gather (dup_*) takes compact outputs (dense = 0)");
+    io.dup.n = o->n_dup;
+    for (int j = 0; j < o->n_dup; ++j) {
+        io.dup.t2[j] = o->dup_t2[j]; io.dup.k[j] = o->dup_k[j]; io.dup.res[j] = o->dup_res[j]; io.dup.status[j] = o->dup_status[j];
+        io.dup.sigma[j] = p->model == T2FIT_MODEL_GAUSSIAN ? nullptr : o->dup_sigma[j];
+    }
     if (lbs && o->trace_cap > 0) {
         io.trace_f = o->trace_f; io.trace_step = o->trace_step; io.trace_len = o->trace_len; io.trace_cap = o->trace_cap;
     }

@@ -17,7 +17,9 @@ volume, so a brain mask does not unbalance the GPUs.
   in the reference -- nobody is left waiting in a collective;
 * ``fit_voxels_fused_gather``: no collective at all -- the fit kernels' epilogues store their slab straight into the
   root GPU's buffer over NVLink (CUDA IPC peer mapping);
-* ``SlabPipeline``: a stream of sharded jobs with the gather of job i overlapping the fit of job i+1 (double-buffered).
+* ``SlabPipeline``: a stream of sharded jobs with the (NCCL) gather of job i overlapping the fit of job i+1 (double-buffered);
+* ``FusedAllGather``: the all-gather fused into the kernels -- every rank's epilogue stores its slab into EVERY rank's buffer
+  over NVLink, one tiny all-reduce as the barrier (the fastest form measured: profiles/r02_notes.md).
 
 Host logic only -- the fit of a slab is ``api.fit_voxels_batch`` (CUDA).  ``fit_fn`` is injectable so the partition /
 gather / error logic is testable with ``gloo`` on CPU.
@@ -27,7 +29,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = ["slab_bounds", "slab_length", "fit_voxels_sharded", "fit_slab_sharded", "gather_slabs", "gather_fields",
-           "fit_voxels_fused_gather", "ShardError", "SlabPipeline"]
+           "fit_voxels_fused_gather", "ShardError", "SlabPipeline", "FusedAllGather"]
 
 ALIGN = 128
 FIELDS = ("t2", "k", "sigma", "res", "status")
@@ -329,3 +331,130 @@ class SlabPipeline:
             for w in self.slots[s]["works"]:
                 w.wait()
             self.slots[s]["works"] = []
+
+
+class FusedAllGather:
+    """Sharded jobs of one shape with the all-gather FUSED INTO THE FIT KERNELS: every rank's kernel epilogue stores its slab
+    of (t2, k, [sigma,] res, status) into its own buffer AND, over NVLink, into the same slab of every peer's buffer (CUDA-IPC
+    mappings, ``t2fit_outputs.dup_*``); a one-element NCCL all-reduce, stream-ordered after the kernels, is the cross-rank
+    barrier that completes the gather.  No collective moves data: the transfer overlaps the fit, and a pass costs the fit plus
+    ~15 us at 2 GPUs where NCCL's all-gather of the same 21 MB costs 77 us (profiles/r02_notes.md).  Every rank still
+    RECEIVES (world - 1) slabs per job: at 8 GPUs the NVLink ingest (~150 MB per rank for c2-sized slabs) bounds the pass.
+
+    ``depth`` buffer sets (default 2) let a consumer read job i while job i+1 is being written.  ``submit(rows, ...)`` ->
+    slot; ``result(slot)`` -> full-length tensors (views of this rank's buffer, valid until the slot is reused)."""
+
+    def __init__(self, n_fit, fit, *, depth=2, group=None, device=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _abi
+        from .api import init
+        self.torch, self.dist, self.group, self.C, self._abi = torch, dist, group, C, _abi
+        self.lib = init()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world - 1 > _abi.MAX_DUP:
+            raise ValueError(f"the fused all-gather serves up to {_abi.MAX_DUP + 1} GPUs")
+        self.n_fit, self.fit = int(n_fit), fit
+        self.L = slab_length(self.n_fit, self.world)
+        self.a, self.b = slab_bounds(self.n_fit, self.world)[self.rank]
+        self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        tot = self.world * self.L
+        self.fields = ("t2", "k", "res", "status") if fit == "gaussian" else ("t2", "k", "sigma", "res", "status")
+        self.off, o = {}, 0
+        for n in self.fields:
+            self.off[n] = o
+            o += tot * (1 if n == "status" else 4)
+        self.nbytes = (o + 255) // 256 * 256
+        self.sets = []
+        for _ in range(max(1, depth)):
+            ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+            _abi.check(self.lib, self.lib.t2fit_shared_alloc(self.nbytes, C.byref(ptr), handle), "t2fit_shared_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            peers = {}
+            for r in range(self.world):
+                if r != self.rank:
+                    pp = C.c_void_p()
+                    _abi.check(self.lib, self.lib.t2fit_shared_open(handles[r], C.byref(pp)), "t2fit_shared_open")
+                    peers[r] = pp
+            raw = torch.as_tensor(_DeviceBytes(ptr.value, self.nbytes), device=self.dev)
+            raw.zero_()
+            self.sets.append({"ptr": ptr, "peers": peers, "raw": raw, "counts": torch.zeros(4, dtype=torch.int64, device=self.dev),
+                              "call": None})
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        self.next = 0
+
+    def _build(self, st, slab_rows, TEeffs, fit_params, prior, norm, solver):
+        """The t2fit_run arguments of a slot (built once per slot and input tensor; a pass then is two C calls)."""
+        from .api import _fill_problem, resolve_solver
+        _abi, C = self._abi, self.C
+        p, o = _abi.Problem(), _abi.Outputs()
+        keep = _fill_problem(p, self.fit, fit_params, TEeffs, prior, norm, 0, 0.0, "auto", resolve_solver(self.fit, solver))
+        p.echoes, p.memory, p.layout, p.mask_idx = slab_rows.data_ptr(), _abi.MEM_DEVICE, _abi.LAYOUT_AOS, None
+        p.n_vox = p.n_fit = slab_rows.shape[0]
+
+        def at(base, n):
+            return base + self.off[n] + (1 if n == "status" else 4) * self.rank * self.L
+        base = st["ptr"].value
+        o.t2, o.k, o.res, o.status = at(base, "t2"), at(base, "k"), at(base, "res"), at(base, "status")
+        o.sigma = at(base, "sigma") if "sigma" in self.off else None
+        o.dense, o.counts_dev = 0, st["counts"].data_ptr()
+        o.n_dup = len(st["peers"])
+        for j, r in enumerate(sorted(st["peers"])):
+            pb = st["peers"][r].value
+            o.dup_t2[j], o.dup_k[j], o.dup_res[j], o.dup_status[j] = at(pb, "t2"), at(pb, "k"), at(pb, "res"), at(pb, "status")
+            o.dup_sigma[j] = at(pb, "sigma") if "sigma" in self.off else None
+        return {"p": p, "o": o, "keep": (keep, slab_rows), "key": (slab_rows.data_ptr(), slab_rows.shape[0], id(fit_params), prior, norm, solver)}
+
+    def submit(self, slab_rows, TEeffs, fit_params, prior=True, norm=False, *, solver="auto"):
+        s = self.next
+        self.next = (self.next + 1) % len(self.sets)
+        st = self.sets[s]
+        if slab_rows.shape[0] != self.b - self.a:
+            raise IndexError(f"rank {self.rank} holds {slab_rows.shape[0]} rows, its slab has {self.b - self.a}")
+        key = (slab_rows.data_ptr(), slab_rows.shape[0], id(fit_params), prior, norm, solver)
+        if st["call"] is None or st["call"]["key"] != key:
+            st["call"] = self._build(st, slab_rows, TEeffs, fit_params, prior, norm, solver)
+        st["counts"].zero_()
+        stream = self.torch.cuda.current_stream(self.dev).cuda_stream
+        if self.b > self.a:
+            rc = self.lib.t2fit_run(self.C.byref(st["call"]["p"]), self.C.byref(st["call"]["o"]), stream)
+            if rc:
+                raise self._abi.T2FitError((self.lib.t2fit_last_error() or b"").decode())
+        # cross-rank barrier ordered after the kernels: when it completes here, every rank's kernel (and its peer stores) has
+        self.dist.all_reduce(self.flag, group=self.group)
+        return s
+
+    def result(self, s, check=False):
+        st = self.sets[s]
+        if check:
+            exc = None
+            try:
+                from .api import _raise_for_counts
+                _raise_for_counts([int(v) for v in st["counts"].cpu()])
+            except Exception as e:                  # noqa: BLE001
+                exc = e
+            _agree_or_raise(exc, self.dev, self.group)
+        tot = self.world * self.L
+        out = {}
+        for n in self.fields:
+            if n == "status":
+                out[n] = st["raw"][self.off[n]:self.off[n] + tot][:self.n_fit]
+            else:
+                out[n] = st["raw"][self.off[n]:self.off[n] + 4 * tot].view(self.torch.float32)[:self.n_fit]
+        return out
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)
+        for st in self.sets:
+            for pp in st["peers"].values():
+                self.lib.t2fit_shared_close(pp)
+            st["raw"] = None
+        self.dist.barrier(group=self.group)
+        for st in self.sets:
+            self.lib.t2fit_shared_free(st["ptr"])
+        self.sets = []

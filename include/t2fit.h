@@ -28,6 +28,7 @@ extern "C" {
 
 #define T2FIT_ABI_VERSION 4
 #define T2FIT_MAX_ECHO 32
+#define T2FIT_MAX_DUP 7 /* peer destinations of the fused all-gather: the other GPUs of an 8-GPU node */
 
 /* return codes */
 #define T2FIT_OK 0
@@ -149,6 +150,14 @@ typedef struct t2fit_outputs {
                                     kernel on a side stream concurrent with the fit (forked from / joined into
                                     `stream`; one such call at a time per process, the events are shared).
                                     NULL = caller zero-fills. */
+    /* Fused all-gather (T2FIT_MEM_DEVICE, dense == 0): every compact result of this call is ALSO stored to n_dup further
+       destinations -- the same slab of the peer GPUs' buffers, mapped with t2fit_shared_open -- straight from the kernel
+       epilogue over NVLink (peer stores; no collective, the transfer overlaps the fit).  dup_*[j] may be NULL (skipped);
+       element i of this call goes to dup_*[j][i].  After the call a cross-rank barrier that is ordered after the kernels
+       (e.g. a one-element NCCL all-reduce on the same stream) completes the gather on every rank. */
+    int32_t n_dup;
+    float *dup_t2[T2FIT_MAX_DUP], *dup_k[T2FIT_MAX_DUP], *dup_sigma[T2FIT_MAX_DUP], *dup_res[T2FIT_MAX_DUP];
+    uint8_t *dup_status[T2FIT_MAX_DUP];
     uint64_t *counts_dev;        /* T2FIT_MEM_DEVICE calls, optional: [4] DEVICE counters this call ADDS its voxels to
                                     (slot 0: mask_idx entries outside [0, n_vox), which read / write voxel 0 instead --
                                     the reference raises IndexError there; slots 1..3: voxels per non-OK status).  The caller

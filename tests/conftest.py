@@ -44,19 +44,30 @@ def lbfgsb_parity_report(t2, nit, success, g):
     with np.errstate(all="ignore"):
         rel = np.abs(np.asarray(t2, np.float64) - ref[:, 1]) / np.abs(ref[:, 1])
         relj = np.abs(g["jit_params"][:, 1] - ref[:, 1]) / np.abs(ref[:, 1])
-    return dict(all=float(np.mean(rel <= 1e-3)), jitter_all=float(np.mean(relj <= 1e-3)),
+    conv = g["converged"] if "converged" in g else np.zeros(rel.shape[0], bool)
+    conv_rate = float(np.mean(rel[conv] <= 1e-3)) if conv.sum() >= 20 else None
+    return dict(converged=conv_rate, n_converged=int(conv.sum()), jitter_converged=float(np.mean(relj[conv] <= 1e-3)) if conv.sum() >= 20 else None,
+                all=float(np.mean(rel <= 1e-3)), jitter_all=float(np.mean(relj <= 1e-3)),
                 reproducible=float(np.mean(rel[rp] <= 1e-3)), n_reproducible=int(rp.sum()),
                 nit_eq=float(np.mean(np.asarray(nit) == g["ref_nit"])), jitter_nit_eq=float(np.mean(g["jit_nit"] == g["ref_nit"])),
                 success_eq=bool(np.array_equal(np.asarray(success, bool), g["ref_success"])))
 
 
 def assert_lbfgsb_parity(rep, name):
-    """Tolerances: identical success sets; relative |dT2| <= 1e-3 on >= 98.5 % of the voxels whose reference
+    """Tolerances: identical success sets; relative |dT2| <= 1e-3 on >= 99 % of the CONVERGED voxels and on >= 98.5 % of the voxels whose reference
     result is reproducible under a 1-ulp change of exp (the rest differ between two runs of the reference
     itself; measured 98.97-100 % over the 13 fixtures -- log / i0e also differ in the last ulps, which the
     exp-only jitter does not probe); over ALL voxels no worse than the reference's own jittered rerun by more
     than 1.5 points."""
+    print(f"[lbfgsb parity] {name}: T2 within 1e-3 on converged {rep['converged']} (n={rep['n_converged']}; the reference's own "
+          f"jittered rerun: {rep['jitter_converged']}), reproducible {rep['reproducible']:.4f} (n={rep['n_reproducible']}), "
+          f"all {rep['all']:.4f} (rerun {rep['jitter_all']:.4f}), nit equal {rep['nit_eq']:.4f} (rerun {rep['jitter_nit_eq']:.4f})")
     assert rep["success_eq"], name
+    # north_star's sentence, literally: relative |dT2| <= 1e-3 on CONVERGED voxels (reference success and a tight restart from
+    # its own answer moves T2 by <= 1e-4, SURVEY 7.3; the rician fixtures have no such set: no tight oracle for the NLL).
+    # Measured 99.3-100 % over the ten fixtures that have one; the reference's own jittered rerun reaches 98.0-100 % on it.
+    if rep["converged"] is not None:
+        assert rep["converged"] >= 0.99, (name, rep)
     assert rep["reproducible"] >= 0.985, (name, rep)
     assert rep["all"] >= rep["jitter_all"] - 0.015, (name, rep)
     assert rep["nit_eq"] >= rep["jitter_nit_eq"] - 0.03, (name, rep)

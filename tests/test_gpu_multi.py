@@ -62,8 +62,23 @@ def _worker(rank, world, port, tmp, fit):
         assert torch.equal(last[name], out[name]), name
     mid = pipe.result(slots[1])
     torch.cuda.synchronize()
-    assert not torch.equal(mid["k"], out["k"]) and torch.allclose(mid["t2"], out["t2"], rtol=2e-3)   # k scales with the signal, T2 does not
+    single_mid = t2.fit_voxels_batch((flat * 1.5).contiguous(), idx, te, fit, fp, prior=False)
+    assert torch.equal(mid["t2"], single_mid.t2) and torch.equal(mid["k"], single_mid.k) and not torch.equal(mid["k"], out["k"])
     pipe.drain()
+    # the all-gather fused into the kernels (peer stores into every rank's buffer + a one-element all-reduce as the barrier)
+    fused_ag = D.FusedAllGather(idx.numel(), fit)
+    s0 = fused_ag.submit(rows, te, fp, prior=False)
+    s1 = fused_ag.submit(rows2, te, fp, prior=False)
+    r0, r1 = fused_ag.result(s0, check=True), fused_ag.result(s1)
+    torch.cuda.synchronize()
+    for name in ("t2", "k", "res", "status") + (() if fit == "gaussian" else ("sigma",)):
+        assert torch.equal(r0[name], out[name]), name
+    assert torch.equal(r1["t2"], single_mid.t2) and torch.equal(r1["k"], single_mid.k)
+    s2 = fused_ag.submit(rows, te, fp, prior=False)                    # slot 0 again
+    assert s2 == s0
+    torch.cuda.synchronize()
+    assert torch.equal(fused_ag.result(s2)["res"], out["res"])
+    fused_ag.close()
     again = D.fit_voxels_sharded(flat, idx, te, fit, fp, prior=False)      # and the next clean job is unaffected
     assert torch.equal(again["t2"], out["t2"])
     np.save(os.path.join(tmp, f"t2_{rank}.npy"), out["t2"].cpu().numpy())
