@@ -10,7 +10,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fetal_t2mapping_b200 as t2
 from fetal_t2mapping_b200 import _abi
 from fetal_t2mapping_b200.api import _fill_problem
-from bench import make_workload
+from bench import make_volume_workload
+
+
+def make_workload(rank):
+    return make_volume_workload("c2", rank)
 
 
 def timeit(fn, reps=50):
