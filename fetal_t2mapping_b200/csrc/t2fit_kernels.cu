@@ -77,7 +77,6 @@ struct KernelIO {
     // > 0: idx comes unchecked from the caller's host memory -- entries outside [0, n_rows) are counted in counts[0] and
     // read row 0 instead (the host raises IndexError afterwards, as the reference's fancy indexing would)
     int64_t n_rows;
-    int64_t n_total;             // rows of the AoS echo array (vector fetches must not run past it)
 };
 
 __device__ __forceinline__ int64_t guarded_row(const KernelIO& io, int64_t row) {
@@ -132,32 +131,6 @@ __device__ __forceinline__ void load_aos(const float* __restrict__ base, int64_t
     }
 #pragma unroll
     for (int e = 0; e < E; ++e) y[e] = __ldg(p + e);
-}
-
-// Odd echo counts (E = 5: the c2 configuration) have no per-lane vector load: a lane's row is E scalar loads whose 4-byte
-// pieces interleave with its neighbours' across every sector of the warp's span.  Inside a mask run the rows of a warp are
-// consecutive in memory, so the warp fetches the 32 * E floats as whole 16-byte vectors (an aligned superset, 2-3 LDG.128 per
-// lane) into shared memory and every lane picks its row up from there (stride E floats, odd: no bank conflicts).  Fewer and
-// fuller requests: what matters when the rows live in HOST memory and every request is a PCIe read.  false = not applicable
-// (rows not consecutive, unaligned base, span touching the end of the array): the caller takes the scalar path.
-template <int E>
-__device__ __forceinline__ bool load_aos_warp(const float* __restrict__ base, int64_t row, bool vec_ok, int64_t n_rows_total,
-                                              float* __restrict__ smem_warp, float (&y)[E]) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int64_t row0 = __shfl_sync(full, row, 0);
-    if (!__all_sync(full, vec_ok && row == row0 + lane)) return false;
-    const int64_t f0 = row0 * E;                         // first float of the span
-    const int64_t v0 = f0 >> 2, v1 = (f0 + 32 * E + 3) >> 2;      // 16-byte vectors [v0, v1): aligned superset of the span
-    if (v1 * 4 > n_rows_total * E) return false;         // would read past the array
-    const float4* p4 = reinterpret_cast<const float4*>(base);
-    float4* s4 = reinterpret_cast<float4*>(smem_warp);
-    for (int64_t q = v0 + lane; q < v1; q += 32) s4[q - v0] = __ldg(p4 + q);
-    __syncwarp();
-    const int off = (int)(f0 - v0 * 4) + lane * E;
-#pragma unroll
-    for (int e = 0; e < E; ++e) y[e] = smem_warp[off + e];
-    return true;
 }
 
 template <int E>
@@ -300,14 +273,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
         }
     }
     float y[E];
-    if (LAYOUT == T2FIT_LAYOUT_AOS) {
-        bool got = false;
-        if constexpr (E % 2 == 1) {                        // warp-cooperative vector fetch of a run of rows (see load_aos_warp)
-            __shared__ __align__(16) float rows_smem[kBlock / 32][32 * E + 8];
-            got = load_aos_warp<E>(io.echoes, row, io.vec_ok != 0, io.n_total, rows_smem[threadIdx.x >> 5], y);
-        }
-        if (!got) load_aos<E>(io.echoes, row, io.vec_ok != 0, y);
-    }
+    if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row, io.vec_ok != 0, y);
     else if (LAYOUT == T2FIT_LAYOUT_SOA) load_soa<E>(io.echoes, io.ld, ii, y);
     else load_soa<E>(io.echoes, io.ld, row, y);            // PLANES: per-TE volumes, voxel `row` of every plane
     if (FILL) {                                            // zero stores go out while the echoes are on their way
@@ -1260,7 +1226,7 @@ int run_host_mapped(Context* c, const t2fit_problem& p, t2fit_outputs& o, const 
         CU_TRY(cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(unsigned long long), st));
         c->counts_dirty = false;
     }
-    io.echoes = static_cast<const float*>(d_echo); io.ld = p.ld; io.n_fit = M; io.n_total = p.n_vox;
+    io.echoes = static_cast<const float*>(d_echo); io.ld = p.ld; io.n_fit = M;
     io.counts = c->d_counts; io.dense = 0; io.layout = p.layout;
     io.vec_ok = (reinterpret_cast<uintptr_t>(d_echo) % 16) == 0;
     int rc = lc ? launch_lbfgsb(c, *lc, io, p.model, p.n_echo, st) : launch_fit(c, fc, io, p.model, p.n_echo, p.layout, st);
@@ -1421,7 +1387,7 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
         CU_TRY(cudaMemcpyAsync(s.d_in, s.h_in, sizeof(float) * E * n, cudaMemcpyHostToDevice, s.stream));
         float* df = reinterpret_cast<float*>(s.d_out);
         KernelIO io{};
-        io.echoes = s.d_in; io.idx = nullptr; io.ld = n; io.n_fit = n; io.n_total = n;
+        io.echoes = s.d_in; io.idx = nullptr; io.ld = n; io.n_fit = n;
         io.t2 = df; io.k = df + n; io.sigma = df + 2 * n; io.res = df + 3 * n; io.fun = df + 4 * n;
         io.nit = reinterpret_cast<int32_t*>(s.d_out + (size_t)5 * n * sizeof(float));
         io.status = s.d_out + (size_t)5 * n * sizeof(float) + (size_t)n * sizeof(int32_t);
@@ -1609,7 +1575,7 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
 
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, as in CUDA
     KernelIO io{};
-    io.echoes = p->echoes; io.ld = p->ld; io.n_fit = p->n_fit; io.n_total = p->n_vox;
+    io.echoes = p->echoes; io.ld = p->ld; io.n_fit = p->n_fit;
     if (p->idx_dtype == T2FIT_IDX_I32) io.idx32 = reinterpret_cast<const int32_t*>(p->mask_idx);
     else io.idx = p->mask_idx;
     // a caller-supplied index vector is range-checked by the kernels (entries outside [0, n_vox) are counted in slot 0 of

@@ -166,6 +166,9 @@ def main():
         rows, te, t2, s0 = sample_rows("c2", 1000, 0.25, 103)
         build_case(ref, "c2_gaussian_hf_prior", rows * np.float32(1.6), te, "gaussian", "hf", True, False,
                    a.procs, truth=(t2, s0 * 1.6))
+    if want("c4_gaussian_noprior"):                      # BASELINE config 4: fetal-brain volume, 6 TEs
+        rows, te, t2, s0 = sample_rows("c4", 1500, 0.4, 109)
+        build_case(ref, "c4_gaussian_noprior", rows, te, "gaussian", "lf", False, False, a.procs, truth=(t2, s0))
     if want("c3_floor_noprior"):
         rows, te, t2, s0 = sample_rows("c3", 1500, 0.2, 104)
         build_case(ref, "c3_floor_noprior", rows, te, "gaussian_rician", "lf", False, False, a.procs, truth=(t2, s0))

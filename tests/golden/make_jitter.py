@@ -122,7 +122,7 @@ def main():
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     ref = load_reference()
-    names = ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior", "c2_gaussian_hf_prior", "c3_floor_noprior",
+    names = ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior", "c2_gaussian_hf_prior", "c4_gaussian_noprior", "c3_floor_noprior",
              "c3_floor_prior", "c5_floor_noprior", "c3_rician_prior", "norm_gaussian", "cli3_gaussian_lf_noprior",
              "cli3_floor_hf_prior", "cli3_rician_hf_prior", "cli3_rician_lf_noprior"]
     for n in names:

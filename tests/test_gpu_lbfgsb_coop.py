@@ -46,7 +46,7 @@ def test_coop_kernel_equals_thread_kernel(gpu_lib, name, kernel):
     assert np.array_equal(a["trace_f"][same], b["trace_f"][same], equal_nan=True)
 
 
-@pytest.mark.parametrize("name", ["c1_gaussian_noprior", "c2_gaussian_noprior", "c2_gaussian_hf_prior", "c3_floor_noprior", "c3_floor_prior",
+@pytest.mark.parametrize("name", ["c1_gaussian_noprior", "c2_gaussian_noprior", "c2_gaussian_hf_prior", "c4_gaussian_noprior", "c3_floor_noprior", "c3_floor_prior",
                                   "c5_floor_noprior", "c3_rician_prior", "cli3_gaussian_lf_noprior", "cli3_floor_hf_prior",
                                   "cli3_rician_hf_prior", "cli3_rician_lf_noprior"])
 def test_coop_kernel_reproduces_reference_fixtures(gpu_lib, name):

@@ -31,7 +31,7 @@ def run_rows(t2, g, device, **kw):
     return dict(t2=r.t2, k=r.k, sigma=r.sigma, res=r.res, fun=r.fun, nit=r.nit, status=r.status)
 
 
-LB_CASES = ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior", "c2_gaussian_hf_prior", "c3_floor_noprior",
+LB_CASES = ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior", "c2_gaussian_hf_prior", "c4_gaussian_noprior", "c3_floor_noprior",
             "c3_floor_prior", "c5_floor_noprior", "c3_rician_prior", "norm_gaussian", "cli3_gaussian_lf_noprior",
             "cli3_floor_hf_prior", "cli3_rician_hf_prior", "cli3_rician_lf_noprior"]
 
@@ -113,7 +113,7 @@ def test_rician_failed_set(gpu_lib):
 
 @pytest.mark.parametrize("device", [False, True], ids=["host", "device"])
 @pytest.mark.parametrize("name", ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior",
-                                  "c2_gaussian_hf_prior"])
+                                  "c2_gaussian_hf_prior", "c4_gaussian_noprior"])
 def test_gaussian_matches_reference_on_converged_voxels(gpu_lib, name, device):
     g = load_golden(name)
     o = run_rows(gpu_lib, g, device)

@@ -18,7 +18,7 @@ def run(g, **kw):
 
 
 @pytest.mark.parametrize("use_double", [False, True], ids=["f32", "f64"])
-@pytest.mark.parametrize("name", ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior", "c2_gaussian_hf_prior"])
+@pytest.mark.parametrize("name", ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior", "c2_gaussian_hf_prior", "c4_gaussian_noprior"])
 def test_mono2_reaches_bounded_minimum(name, use_double):
     g = load_golden(name)
     o = run(g, use_double=use_double)

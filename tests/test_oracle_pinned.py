@@ -11,7 +11,7 @@ import scipy
 from tests.conftest import fit_params_of, load_golden
 from oracle import fit_oracle as fo
 
-CASES = ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior", "c2_gaussian_hf_prior",
+CASES = ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior", "c2_gaussian_hf_prior", "c4_gaussian_noprior",
          "c3_floor_noprior", "c3_floor_prior", "c5_floor_noprior", "c3_rician_prior"]
 
 
