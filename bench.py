@@ -637,7 +637,12 @@ def bench_volume(args, cfg):
     roofline = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                 "traffic": traffic.get("step_dram_bytes") if (args.config == "c2" and fill_in_fit) else None, "peak_src": peaks["src"],
                 "kernel": kernel_name, "kernel_ms": dense_ms, "algorithmic_bytes": step_bytes,
-                "bytes_per_fit": per_fit, "dense_map_bytes": step_bytes - float(m) * per_fit}
+                "bytes_per_fit": per_fit, "dense_map_bytes": step_bytes - float(m) * per_fit,
+                # the same launch on SURVEY 8(d)'s per-fit accounting alone (4E + 4(P+1) + 1 bytes per masked voxel, without the
+                # zero-fill of the dense maps and without index / nit / fun): what share of the HBM peak the FITS themselves use
+                "per_fit_accounting": {"bytes_per_fit": 4.0 * n_echo + 4 * (3 if mono else 4) + 1,
+                                       "achieved": float(m) * (4.0 * n_echo + 4 * (3 if mono else 4) + 1) / (dense_ms * 1e-3) / 1e9,
+                                       "frac": float(m) * (4.0 * n_echo + 4 * (3 if mono else 4) + 1) / (dense_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
     if solver == "lbfgsb":
         roofline["note"] = ("the L-BFGS-B kernel is bound by the latency of its own per-thread optimiser state (~7 KB / voxel in local "
                             "memory, DRAM-resident at 896 threads / SM), not by HBM bandwidth or a math pipe: frac is the "
