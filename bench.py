@@ -523,6 +523,21 @@ def bench_volume(args, cfg):
         def fused_pass():
             fa.submit(rows_d, te, fp, prior=False, norm=False, solver=solver)
 
+        fa2 = None                                                # the literal "gather of the parameter maps": T2 and S0 only
+        if fa is not None:
+            try:
+                fa2 = D.FusedAllGather(n_job, fit, gather=("t2", "k"))
+                ok2 = 1
+            except Exception:
+                ok2 = 0
+            okt = torch.tensor([ok2], device=c.dev, dtype=torch.int32)
+            c.dist.all_reduce(okt, op=c.dist.ReduceOp.MIN)
+            if int(okt[0]) == 0:
+                fa2 = None
+
+        def fused_pass_t2s0():
+            fa2.submit(rows_d, te, fp, prior=False, norm=False, solver=solver)
+
     sampler = ClockSampler(c.local) if c.rank == 0 else None
     if sampler:
         sampler.start()
@@ -597,6 +612,21 @@ def bench_volume(args, cfg):
                                  "single_job_ms": one_ms, "single_job_gather_ms": one_ms - fit_ms, "single_job_value": m_total / (one_ms * 1e-3),
                                  "gather_gbs_received_per_rank_single_job": bytes_in / max(one_ms - fit_ms, 1e-9) / 1e6,
                                  "what": "pipelined: the gather of pass i overlaps the fit of pass i+1; single job: nothing overlapped"}
+        if fa2 is not None:
+            s2 = fa2.submit(rows_d, te, fp, prior=False, norm=False, solver=solver)
+            r2 = fa2.result(s2)
+            torch.cuda.synchronize()
+            ok2 = all(bool(torch.equal(r2[n], bufs[n][:n_job])) for n in ("t2", "k"))
+            okt = torch.tensor([int(ok2)], device=c.dev, dtype=torch.int32)
+            c.dist.all_reduce(okt, op=c.dist.ReduceOp.MIN)
+            assert int(okt[0]) == 1, "fused gather of T2 / S0 differs"
+            p2s = pick_passes(c, fused_pass_t2s0, args.steps)
+            t2s0_ms = time_steps(c, fused_pass_t2s0, args.steps, p2s) / (args.steps * p2s)
+            extra["sharded_t2_s0_only"] = {"value": m_total / (t2s0_ms * 1e-3), "ms_per_pass": t2s0_ms,
+                                           "gather_bytes_received_per_rank": int((c.world - 1) * L * 8),
+                                           "what": "the same fused all-gather moving only the PARAMETER maps (T2 and S0, 8 B per voxel: the 'final "
+                                                   "gather of the parameter maps' of BASELINE.json read literally); res and status stay with the slab's owner"}
+            fa2.close()
         if fa is None:
             extra["sharded"]["fused_unavailable"] = fused_err if not ok_f else "CUDA IPC failed on another rank"
         extra["replicas"] = {"value": sum_over_ranks(c, m) / (rep_ms * 1e-3), "ms_per_pass": rep_ms,

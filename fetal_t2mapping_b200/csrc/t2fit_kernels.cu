@@ -1570,6 +1570,7 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
         return fail(T2FIT_EINVAL, "bad echo_dtype");
     if (!f32 && p->memory != T2FIT_MEM_HOST) return fail(T2FIT_EINVAL, "device-memory echoes must be float32");
     CU_TRY(cudaSetDevice(c->device));
+    if (p->memory == T2FIT_MEM_HOST && o->n_dup != 0) return fail(T2FIT_EINVAL, "the fused all-gather (dup_*) is for T2FIT_MEM_DEVICE calls");
     if (p->memory == T2FIT_MEM_HOST) return run_host(c, *p, *o, fc, lbs ? &lc : nullptr);
     if (p->memory != T2FIT_MEM_DEVICE) return fail(T2FIT_EINVAL, "bad memory kind");
 

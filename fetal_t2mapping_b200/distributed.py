@@ -344,13 +344,18 @@ class FusedAllGather:
     ``depth`` buffer sets (default 2) let a consumer read job i while job i+1 is being written.  ``submit(rows, ...)`` ->
     slot; ``result(slot)`` -> full-length tensors (views of this rank's buffer, valid until the slot is reused)."""
 
-    def __init__(self, n_fit, fit, *, depth=2, group=None, device=None):
+    def __init__(self, n_fit, fit, *, depth=2, group=None, device=None, gather=None):
+        """``gather``: the fields every rank receives from every peer (default: all of them).  ``("t2", "k")`` is the
+        literal "final gather of the parameter maps" of BASELINE.json (T2 and S0): res / sigma / status of a slab then stay
+        with its owner (``result()`` returns the owner's slab of those, zeros elsewhere) and 8 instead of 13-17 bytes per
+        voxel cross NVLink."""
         import ctypes as C
         import torch
         import torch.distributed as dist
         from . import _abi
         from .api import init
         self.torch, self.dist, self.group, self.C, self._abi = torch, dist, group, C, _abi
+        self.gather = None if gather is None else tuple(gather)
         self.lib = init()
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world - 1 > _abi.MAX_DUP:
@@ -403,10 +408,11 @@ class FusedAllGather:
         o.sigma = at(base, "sigma") if "sigma" in self.off else None
         o.dense, o.counts_dev = 0, st["counts"].data_ptr()
         o.n_dup = len(st["peers"])
+        sel = self.fields if self.gather is None else self.gather
         for j, r in enumerate(sorted(st["peers"])):
             pb = st["peers"][r].value
-            o.dup_t2[j], o.dup_k[j], o.dup_res[j], o.dup_status[j] = at(pb, "t2"), at(pb, "k"), at(pb, "res"), at(pb, "status")
-            o.dup_sigma[j] = at(pb, "sigma") if "sigma" in self.off else None
+            for n, arr in (("t2", o.dup_t2), ("k", o.dup_k), ("res", o.dup_res), ("status", o.dup_status), ("sigma", o.dup_sigma)):
+                arr[j] = at(pb, n) if (n in self.off and n in sel) else None
         return {"p": p, "o": o, "keep": (keep, slab_rows), "key": (slab_rows.data_ptr(), slab_rows.shape[0], id(fit_params), prior, norm, solver)}
 
     def submit(self, slab_rows, TEeffs, fit_params, prior=True, norm=False, *, solver="auto"):
