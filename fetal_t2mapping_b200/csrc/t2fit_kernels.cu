@@ -232,11 +232,11 @@ constexpr int min_blocks(int model, int e) {
 // coalesced 16-byte store per map and word, fire-and-forget) go out while the thread waits for its echoes.  Every
 // resident warp carries both kinds of work, so the HBM-bound fill rides in the memory stalls of the fit without a
 // second kernel holding SM slots (the side-stream zero_fill_kernel remains for callers this path does not cover).
-template <int MODEL>
+template <int MODEL, bool SIGMA = true>
 __device__ __forceinline__ void fill_word(const KernelIO& io, int64_t w, uint32_t m) {
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t v = w * 4;
-    if (MODEL == kMono2 || m == 0u) *reinterpret_cast<float4*>(io.sigma + v) = z4;   // the 2-parameter fit never writes sigma
+    if (SIGMA && (MODEL == kMono2 || m == 0u)) *reinterpret_cast<float4*>(io.sigma + v) = z4;   // the 2-parameter fit never writes sigma
     if (m == 0u) {
         *reinterpret_cast<float4*>(io.t2 + v) = z4;
         *reinterpret_cast<float4*>(io.k + v) = z4;
@@ -246,16 +246,58 @@ __device__ __forceinline__ void fill_word(const KernelIO& io, int64_t w, uint32_
         for (int q = 0; q < 4; ++q) {
             if (((m >> (8 * q)) & 0xffu) == 0u) {
                 io.t2[v + q] = 0.f; io.k[v + q] = 0.f; io.res[v + q] = 0.f;
-                if (MODEL != kMono2) io.sigma[v + q] = 0.f;
+                if (SIGMA && MODEL != kMono2) io.sigma[v + q] = 0.f;
             }
         }
     }
 }
 
+#ifdef T2_FILL_BULK
+// Experiment (profiles/r02_notes.md section 8): zero runs of the dense maps leave the SM as bulk asynchronous shared -> global copies
+// of a zeroed shared line buffer (one instruction per map and 2 KB chunk, issued by one lane) instead of 16-byte stores through
+// the load/store unit in front of the fit's own dependent loads.
+constexpr int kBulkWords = 128;                            // mask words (x 16 bytes per map) per warp chunk
+__device__ __forceinline__ void bulk_zero(float* dst, const float* zeros_smem, int bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(zeros_smem)), "r"(bytes) : "memory");
+}
+// One warp, one chunk of up to 128 consecutive mask words starting at window word cw0 (n of them inside the window).
+template <int MODEL>
+__device__ __forceinline__ void fill_chunk_bulk(const KernelIO& io, const float* zeros, int64_t w0, int cw0, int n, const uint32_t (&mw)[4]) {
+    const int lane = (int)threadIdx.x & 31;
+    uint32_t any = 0u;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) any |= (g * 32 + lane < n) ? mw[g] : 0u;
+    const bool all_zero = __all_sync(0xffffffffu, any == 0u);
+    const int64_t v = (w0 + cw0) * 4;
+    if (n > 0) {
+        if (MODEL == kMono2 && lane == 3) bulk_zero(io.sigma + v, zeros, n * 16);     // the 2-parameter fit never writes sigma
+        if (all_zero) {
+            if (lane == 0) bulk_zero(io.t2 + v, zeros, n * 16);
+            if (lane == 1) bulk_zero(io.k + v, zeros, n * 16);
+            if (lane == 2) bulk_zero(io.res + v, zeros, n * 16);
+            if (MODEL != kMono2 && lane == 3) bulk_zero(io.sigma + v, zeros, n * 16);
+        } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                if (g * 32 + lane < n) {
+                    if (MODEL == kMono2) fill_word<MODEL, false>(io, w0 + cw0 + g * 32 + lane, mw[g]);
+                    else fill_word<MODEL, true>(io, w0 + cw0 + g * 32 + lane, mw[g]);
+                }
+        }
+    }
+}
+#endif
+
 template <int MODEL, int E, int LAYOUT, bool FILL>
 __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const __grid_constant__ FitConsts c,
                                                      const __grid_constant__ KernelIO io) {
     constexpr int kGroup = 4;                              // mask words in flight per thread
+    // Programmatic dependent launch (launch_fit sets the attribute): the next fit launch of the stream may become resident while
+    // this one drains; it touches no global memory before the wait, which returns once the previous grid has completed and
+    // its stores are visible.  Both are no-ops for a launch without the attribute.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool valid = i < io.n_fit;
     const int64_t ii = valid ? i : io.n_fit - 1;           // whole warps stay in the solver (warp votes)
@@ -264,6 +306,22 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
     // few concurrent write streams); thread t takes words t, t + 256, ... of the window
     const int64_t w0 = (int64_t)blockIdx.x * io.fill_wpb;
     uint32_t mw[kGroup];
+#ifdef T2_FILL_BULK
+    __shared__ __align__(128) float zeros[kBulkWords * 4];
+    const int wlim = FILL ? (int)min((int64_t)io.fill_wpb, io.fill_words - w0) : 0;   // words of this block's window (<= 0: none)
+    const int cbase = ((int)threadIdx.x >> 5) * kBulkWords;   // warp w owns window words [w * 128, w * 128 + 128) (+ 1024 per round)
+    if (FILL) {
+        reinterpret_cast<float2*>(zeros)[threadIdx.x] = make_float2(0.f, 0.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        const uint32_t* pm = reinterpret_cast<const uint32_t*>(io.fill_mask);
+#pragma unroll
+        for (int g = 0; g < kGroup; ++g) {
+            const int lw = cbase + g * 32 + ((int)threadIdx.x & 31);
+            mw[g] = lw < wlim ? __ldg(pm + w0 + lw) : 0u;
+        }
+    }
+#else
     if (FILL) {                                            // this thread's mask words: loads in flight beside the index load
         const uint32_t* pm = reinterpret_cast<const uint32_t*>(io.fill_mask);
 #pragma unroll
@@ -272,11 +330,25 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
             mw[g] = (lw < io.fill_wpb && w0 + lw < io.fill_words) ? __ldg(pm + w0 + lw) : 0x01010101u;
         }
     }
+#endif
     float y[E];
     if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row, io.vec_ok != 0, y);
     else if (LAYOUT == T2FIT_LAYOUT_SOA) load_soa<E>(io.echoes, io.ld, ii, y);
     else load_soa<E>(io.echoes, io.ld, row, y);            // PLANES: per-TE volumes, voxel `row` of every plane
     if (FILL) {                                            // zero stores go out while the echoes are on their way
+#ifdef T2_FILL_BULK
+        fill_chunk_bulk<MODEL>(io, zeros, w0, cbase, max(0, min(kBulkWords, wlim - cbase)), mw);
+#pragma unroll 1
+        for (int r0 = (kBlock / 32) * kBulkWords; r0 < wlim; r0 += (kBlock / 32) * kBulkWords) {   // sparse masks: further rounds
+            const uint32_t* pm = reinterpret_cast<const uint32_t*>(io.fill_mask);
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g) {
+                const int lw = r0 + cbase + g * 32 + ((int)threadIdx.x & 31);
+                mw[g] = lw < wlim ? __ldg(pm + w0 + lw) : 0u;
+            }
+            fill_chunk_bulk<MODEL>(io, zeros, w0, r0 + cbase, max(0, min(kBulkWords, wlim - r0 - cbase)), mw);
+        }
+#else
 #pragma unroll
         for (int g = 0; g < kGroup; ++g) {
             const int lw = (int)threadIdx.x + g * kBlock;
@@ -296,6 +368,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
                 if (lw < io.fill_wpb && w0 + lw < io.fill_words) fill_word<MODEL>(io, w0 + lw, mw[g]);
             }
         }
+#endif
         if (i == 0) {                                               // ragged tail of the volume (n_vox % 4 voxels)
             for (int64_t v = io.fill_words * 4; v < io.fill_nvox; ++v) {
                 const bool unmasked = io.fill_mask[v] == 0;
@@ -328,6 +401,12 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
             if (m && (threadIdx.x & 31) == 0) atomicAdd(io.counts + s, (unsigned long long)__popc(m));
         }
     }
+#ifdef T2_FILL_BULK
+    if (FILL) {                                            // the zero line buffer must outlive the bulk copies that read it
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -450,8 +529,13 @@ __device__ __noinline__ void lb_store(const lb::LbConsts& c, const KernelIO& io,
 // Persistent grid; every LANE pulls its next voxel from a global queue as soon as its current one has
 // terminated (warp-aggregated atomicAdd), so lanes whose optimiser stopped early do not idle until the
 // slowest voxel of the warp is done (iteration counts vary 3..40 between neighbouring voxels).
+// 8 blocks x 128 threads per SM = at most 64 registers: the kernel waits on its own local-memory state, so resident warps pay
+// more than registers do (profiles/r02_notes.md section 7: 5 / 7 / 8 / 10 / 12 blocks per SM measured).
+#ifndef T2_LB_MIN_BLOCKS
+#define T2_LB_MIN_BLOCKS 8
+#endif
 template <int OBJ>
-__global__ void __launch_bounds__(kLbBlock) lbfgsb_kernel(const __grid_constant__ lb::LbConsts c,
+__global__ void __launch_bounds__(kLbBlock, T2_LB_MIN_BLOCKS) lbfgsb_kernel(const __grid_constant__ lb::LbConsts c,
                                                           const __grid_constant__ KernelIO io,
                                                           unsigned long long* __restrict__ queue) {
     const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
@@ -1025,7 +1109,16 @@ int launch_fit(Context* c, const FitConsts& fc, KernelIO io, int model, int n_ec
     }
     FitFn fn = pick_kernel(model, n_echo, layout, fa != nullptr);
     if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
-    fn<<<(unsigned)blocks, kBlock, 0, st>>>(fc, io);
+    // T2FIT_PDL=0: plain stream order (the default lets back-to-back fit launches overlap launch latency and ramp-up with the
+    // previous launch's tail; the kernel waits for the previous grid before its first global access)
+    static const bool pdl = [] { const char* e = getenv("T2FIT_PDL"); return !(e && !strcmp(e, "0")); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    CU_TRY(cudaLaunchKernelEx(&cfg, fn, fc, io));
     CU_TRY(cudaGetLastError());
     return T2FIT_OK;
 }

@@ -34,9 +34,26 @@
 #if T2_DEVICE_BUILD
 #define T2_NI __device__ __noinline__
 #define T2_ROLLED _Pragma("unroll 1")      // keep the optimiser core compact: it must stay resident in the instruction cache
-#define T2_INNER _Pragma("unroll 4")       // innermost dot products: a few independent loads in flight (the kernel is latency-bound)
+// innermost dot products (trip count = number of stored pairs, <= 10): rolled for the 3-parameter fits, unrolled x2 for the
+// 2-parameter fit.  Measured (profiles/r02_notes.md section 7): the loose 3-parameter presets stop after ~10 iterations, so most
+// of these loops run 1-5 times and an unrolled body plus its remainder loop executes MORE instructions than the rolled loop
+// (c3 +11 %, c5 +16 % rolled); the 2-parameter fit runs mostly at 10 pairs (c2 +3 % at x2; x4 was round 1's setting, x8 -16 %).
+// N is the parameter count of the enclosing Solver<N> / CoopSolver<N, G>.
+#ifdef T2_INNER_UNROLL
+#define T2_PRAGMA_STR(x) _Pragma(#x)
+#define T2_PRAGMA_UNROLL(n) T2_PRAGMA_STR(unroll n)
+#define T2_INNER T2_PRAGMA_UNROLL(T2_INNER_UNROLL)
+#else
+#define T2_INNER _Pragma("unroll (N == 2 ? 2 : 1)")
+#endif
+#ifndef T2_LINPACK_INLINE
+#define T2_LP T2_NI                        // the small LINPACK kernels (dpofa / dtrsl) as calls: less code (+3-6 %)
+#else
+#define T2_LP T2_HD
+#endif
 #else
 #define T2_NI inline
+#define T2_LP inline
 #define T2_ROLLED
 #define T2_INNER
 #endif
@@ -241,7 +258,7 @@ struct Solver {
     // ---- LINPACK-style kernels on the small dense matrices ----------------------------------
     // Cholesky A = R'R of the leading nn x nn block starting at (o, o), upper triangle in place; false = not SPD
     template <int LD>
-    T2_HD static bool dpofa(double (&a)[LD][LD], int o, int nn) {
+    T2_LP static bool dpofa(double (&a)[LD][LD], int o, int nn) {
         T2_ROLLED for (int j = 0; j < nn; ++j) {
             double s = 0.0;
             T2_ROLLED for (int k = 0; k < j; ++k) {
@@ -259,7 +276,7 @@ struct Solver {
     }
     // solve T' x = b (job 11) / T x = b (job 01), T = upper triangle of the leading nn x nn block; false = zero pivot
     template <int LD>
-    T2_HD static bool dtrsl_t(const double (&a)[LD][LD], int nn, double* b) {
+    T2_LP static bool dtrsl_t(const double (&a)[LD][LD], int nn, double* b) {
         T2_ROLLED for (int j = 0; j < nn; ++j) if (a[j][j] == 0.0) return false;
         T2_ROLLED for (int j = 0; j < nn; ++j) {
             double s = b[j];
@@ -269,7 +286,7 @@ struct Solver {
         return true;
     }
     template <int LD>
-    T2_HD static bool dtrsl_n(const double (&a)[LD][LD], int nn, double* b) {
+    T2_LP static bool dtrsl_n(const double (&a)[LD][LD], int nn, double* b) {
         T2_ROLLED for (int j = 0; j < nn; ++j) if (a[j][j] == 0.0) return false;
         T2_ROLLED for (int j = nn - 1; j >= 0; --j) {
             double s = b[j];
