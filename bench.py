@@ -823,7 +823,7 @@ def bench_series(args, cfg):
 
     def one_pass():
         acc = 0.0
-        for mp in t2.t2map_series(vols, te, "gaussian", fp, prior=False, depth=3):
+        for mp in t2.t2map_series(vols, te, "gaussian", fp, prior=False, depth=3, route=os.environ.get("T2FIT_BENCH_C4_ROUTE", "auto")):
             acc += float(mp.t2[mp.t2.shape[0] // 2, 0, 0])       # consume the maps as process_t2maps does, then drop them
         return acc
     sampler = ClockSampler(c.local) if c.rank == 0 else None

@@ -109,6 +109,10 @@ SYMBOLS = [
     ("t2fit_mask_indices", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     ("t2fit_mask_union", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                                    C.c_void_p]),
+    ("t2fit_host_mask_union_indices", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int64,
+                                                C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
+    ("t2fit_host_gather_planes", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                           C.c_void_p, C.c_int64]),
     ("t2fit_roi_stats", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_double),
                                   C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_void_p]),
     ("t2fit_shared_alloc", C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),

@@ -34,6 +34,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "t2fit_consts.h"
@@ -77,6 +78,9 @@ struct KernelIO {
     // > 0: idx comes unchecked from the caller's host memory -- entries outside [0, n_rows) are counted in counts[0] and
     // read row 0 instead (the host raises IndexError afterwards, as the reference's fancy indexing would)
     int64_t n_rows;
+    // fit_kernel, device-resident inputs: > 0 = this block also pulls the index entries, echo rows and fill-mask words of the
+    // block `ahead` blocks further on into L2, so that block's two dependent DRAM round trips (index -> row) become L2 hits
+    int ahead;
 };
 
 __device__ __forceinline__ int64_t guarded_row(const KernelIO& io, int64_t row) {
@@ -143,6 +147,7 @@ __device__ __forceinline__ void load_soa(const float* __restrict__ base, int64_t
 // the fit kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kQueueRefill = 8;      // floor_queue_kernel: waiting lanes per warp that trigger epilogue + refill
+constexpr int kPrefetchAheadWaves = 0;  // fit_kernel: L2 prefetch distance in waves of resident blocks (KernelIO::ahead); 0 = off
 constexpr int kFusedFillMaxWpt = 16; // fused fill only while a fit thread gets at most this many mask words
 constexpr int kFillChunk = 512;    // dense voxels zero-filled by one warp per round (32 lanes x 4 words x 4 voxels)
 
@@ -227,11 +232,12 @@ constexpr int min_blocks(int model, int e) {
 }
 
 // Fused zero-fill (FILL): the np.zeros_like x4 of the dense maps (run_t2mapping.py:415-418) is spread over the fit
-// threads themselves.  Thread t of the launch owns the 4-voxel mask words t, t + T, t + 2T, ... (T = launched threads,
-// fill_wpt of them): their loads are issued together with the thread's own index load, and the zero stores (one
-// coalesced 16-byte store per map and word, fire-and-forget) go out while the thread waits for its echoes.  Every
-// resident warp carries both kinds of work, so the HBM-bound fill rides in the memory stalls of the fit without a
-// second kernel holding SM slots (the side-stream zero_fill_kernel remains for callers this path does not cover).
+// blocks themselves.  Block b owns ONE contiguous window of fill_wpb 4-voxel mask words, each of its warps a 128-word
+// chunk of it: the mask words are loaded beside the thread's own index load; a chunk without a masked voxel goes out as one
+// bulk shared -> global copy per map (fill_chunk_bulk), a chunk that meets the mask as 16-byte / 4-byte stores to the unmasked
+// slots only (fill_word; the fit writes the masked ones, so no slot is written twice).  Every resident block carries both
+// kinds of work, so the HBM-bound fill rides in the memory stalls of the fit without a second kernel holding SM slots (the
+// side-stream zero_fill_kernel remains for callers this path does not cover).
 template <int MODEL, bool SIGMA = true>
 __device__ __forceinline__ void fill_word(const KernelIO& io, int64_t w, uint32_t m) {
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -252,10 +258,9 @@ __device__ __forceinline__ void fill_word(const KernelIO& io, int64_t w, uint32_
     }
 }
 
-#ifdef T2_FILL_BULK
-// Experiment (profiles/r02_notes.md section 8): zero runs of the dense maps leave the SM as bulk asynchronous shared -> global copies
-// of a zeroed shared line buffer (one instruction per map and 2 KB chunk, issued by one lane) instead of 16-byte stores through
-// the load/store unit in front of the fit's own dependent loads.
+// Zero runs of the dense maps leave the SM as bulk asynchronous shared -> global copies (cp.async.bulk, the TMA unit) of a zeroed
+// shared line buffer: one instruction per map and 2 KB chunk, issued by one lane, instead of 16-byte stores queued in the
+// load/store unit in front of the fit's own dependent loads (profiles/r02_notes.md section 8: c2 step 66.5 -> 65.7 us).
 constexpr int kBulkWords = 128;                            // mask words (x 16 bytes per map) per warp chunk
 __device__ __forceinline__ void bulk_zero(float* dst, const float* zeros_smem, int bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -287,12 +292,17 @@ __device__ __forceinline__ void fill_chunk_bulk(const KernelIO& io, const float*
         }
     }
 }
-#endif
 
 template <int MODEL, int E, int LAYOUT, bool FILL>
 __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const __grid_constant__ FitConsts c,
                                                      const __grid_constant__ KernelIO io) {
     constexpr int kGroup = 4;                              // mask words in flight per thread
+    __shared__ __align__(128) float zeros[FILL ? kBulkWords * 4 : 4];   // FILL: the line of zeros the bulk copies read
+    if (FILL) {
+        reinterpret_cast<float2*>(zeros)[threadIdx.x] = make_float2(0.f, 0.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
     // Programmatic dependent launch (launch_fit sets the attribute): the next fit launch of the stream may become resident while
     // this one drains; it touches no global memory before the wait, which returns once the previous grid has completed and
     // its stores are visible.  Both are no-ops for a launch without the attribute.
@@ -302,18 +312,19 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
     const bool valid = i < io.n_fit;
     const int64_t ii = valid ? i : io.n_fit - 1;           // whole warps stay in the solver (warp votes)
     const int64_t row = has_idx(io) ? guarded_row(io, raw_row(io, ii)) : ii;
+    int64_t row_ahead = -1;                                // the index entry of the thread `ahead` blocks on (an ordinary load)
+    if (io.ahead > 0 && LAYOUT == T2FIT_LAYOUT_AOS && has_idx(io)) {
+        const int64_t ia = i + (int64_t)io.ahead * kBlock;
+        if (ia < io.n_fit) row_ahead = raw_row(io, ia);
+    }
     // FILL: block b owns the contiguous window of fill_wpb mask words starting at b * fill_wpb (one window per map and block:
-    // few concurrent write streams); thread t takes words t, t + 256, ... of the window
+    // few concurrent write streams); warp w of the block owns window words [w * 128, w * 128 + 128) (+ 1024 per further
+    // round), 2 KB of every map
     const int64_t w0 = (int64_t)blockIdx.x * io.fill_wpb;
     uint32_t mw[kGroup];
-#ifdef T2_FILL_BULK
-    __shared__ __align__(128) float zeros[kBulkWords * 4];
     const int wlim = FILL ? (int)min((int64_t)io.fill_wpb, io.fill_words - w0) : 0;   // words of this block's window (<= 0: none)
-    const int cbase = ((int)threadIdx.x >> 5) * kBulkWords;   // warp w owns window words [w * 128, w * 128 + 128) (+ 1024 per round)
-    if (FILL) {
-        reinterpret_cast<float2*>(zeros)[threadIdx.x] = make_float2(0.f, 0.f);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
+    const int cbase = ((int)threadIdx.x >> 5) * kBulkWords;
+    if (FILL) {                                            // this warp's mask words: loads in flight beside the index load
         const uint32_t* pm = reinterpret_cast<const uint32_t*>(io.fill_mask);
 #pragma unroll
         for (int g = 0; g < kGroup; ++g) {
@@ -321,22 +332,11 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
             mw[g] = lw < wlim ? __ldg(pm + w0 + lw) : 0u;
         }
     }
-#else
-    if (FILL) {                                            // this thread's mask words: loads in flight beside the index load
-        const uint32_t* pm = reinterpret_cast<const uint32_t*>(io.fill_mask);
-#pragma unroll
-        for (int g = 0; g < kGroup; ++g) {
-            const int lw = (int)threadIdx.x + g * kBlock;
-            mw[g] = (lw < io.fill_wpb && w0 + lw < io.fill_words) ? __ldg(pm + w0 + lw) : 0x01010101u;
-        }
-    }
-#endif
     float y[E];
     if (LAYOUT == T2FIT_LAYOUT_AOS) load_aos<E>(io.echoes, row, io.vec_ok != 0, y);
     else if (LAYOUT == T2FIT_LAYOUT_SOA) load_soa<E>(io.echoes, io.ld, ii, y);
     else load_soa<E>(io.echoes, io.ld, row, y);            // PLANES: per-TE volumes, voxel `row` of every plane
     if (FILL) {                                            // zero stores go out while the echoes are on their way
-#ifdef T2_FILL_BULK
         fill_chunk_bulk<MODEL>(io, zeros, w0, cbase, max(0, min(kBulkWords, wlim - cbase)), mw);
 #pragma unroll 1
         for (int r0 = (kBlock / 32) * kBulkWords; r0 < wlim; r0 += (kBlock / 32) * kBulkWords) {   // sparse masks: further rounds
@@ -348,27 +348,11 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
             }
             fill_chunk_bulk<MODEL>(io, zeros, w0, r0 + cbase, max(0, min(kBulkWords, wlim - r0 - cbase)), mw);
         }
-#else
-#pragma unroll
-        for (int g = 0; g < kGroup; ++g) {
-            const int lw = (int)threadIdx.x + g * kBlock;
-            if (lw < io.fill_wpb && w0 + lw < io.fill_words) fill_word<MODEL>(io, w0 + lw, mw[g]);
+        if (io.ahead > 0 && threadIdx.x < 32) {            // mask words of the window `ahead` blocks on: one 128-byte line per lane
+            const int64_t wa = w0 + (int64_t)io.ahead * io.fill_wpb + (int64_t)threadIdx.x * 32;
+            if (threadIdx.x * 32 < io.fill_wpb && wa < io.fill_words)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const uint32_t*>(io.fill_mask) + wa));
         }
-#pragma unroll 1
-        for (int g0 = kGroup; g0 * kBlock < io.fill_wpb; g0 += kGroup) {     // sparse masks: more words than one group per thread
-            const uint32_t* pm = reinterpret_cast<const uint32_t*>(io.fill_mask);
-#pragma unroll
-            for (int g = 0; g < kGroup; ++g) {
-                const int lw = (int)threadIdx.x + (g0 + g) * kBlock;
-                mw[g] = (lw < io.fill_wpb && w0 + lw < io.fill_words) ? __ldg(pm + w0 + lw) : 0x01010101u;
-            }
-#pragma unroll
-            for (int g = 0; g < kGroup; ++g) {
-                const int lw = (int)threadIdx.x + (g0 + g) * kBlock;
-                if (lw < io.fill_wpb && w0 + lw < io.fill_words) fill_word<MODEL>(io, w0 + lw, mw[g]);
-            }
-        }
-#endif
         if (i == 0) {                                               // ragged tail of the volume (n_vox % 4 voxels)
             for (int64_t v = io.fill_words * 4; v < io.fill_nvox; ++v) {
                 const bool unmasked = io.fill_mask[v] == 0;
@@ -377,6 +361,9 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
             }
         }
     }
+
+    if (row_ahead >= 0 && (io.n_rows <= 0 || row_ahead < io.n_rows))       // its echo row (20 bytes for E = 5: lanes share lines)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(io.echoes + row_ahead * E));
 
     const VoxelFit f = fit_voxel<float, MODEL, E>(y, c, valid);
 
@@ -401,12 +388,10 @@ __global__ void __launch_bounds__(kBlock, min_blocks(MODEL, E)) fit_kernel(const
             if (m && (threadIdx.x & 31) == 0) atomicAdd(io.counts + s, (unsigned long long)__popc(m));
         }
     }
-#ifdef T2_FILL_BULK
     if (FILL) {                                            // the zero line buffer must outlive the bulk copies that read it
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1554,6 +1539,91 @@ int run_host(Context* c, const t2fit_problem& p, t2fit_outputs& o, const FitCons
 // ================================================================================================
 // C ABI
 // ================================================================================================
+// ------------------------------------------------------------------------------------------------
+// Host-side front of the loader for sparse masks: the union / label masking / np.where of run_t2mapping.py:383-384,393-400,421
+// and the gather + float32 cast of the masked voxels (:411-412 restricted to the rows the fit reads), on the library's own
+// worker threads.  No GPU involved: with a brain mask covering ~10 % of the volume the loader then ships [E, M] floats and
+// one mask plane over PCIe instead of E volumes and E masks.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+std::mutex g_host_mu;                       // one host-side call at a time (Workers::run has one caller)
+Workers* g_host_workers = nullptr;
+
+Workers& host_workers() {                   // g_host_mu held
+    if (!g_host_workers) {
+        unsigned hw = std::thread::hardware_concurrency();
+        const char* env = getenv("T2FIT_HOST_THREADS");
+        g_host_workers = new Workers(env ? atoi(env) : (int)std::min(16u, hw ? hw : 4u));
+    }
+    return *g_host_workers;
+}
+
+constexpr int kHostTile = 512;              // voxels per inner tile (accumulators stay in L1)
+
+template <typename T>
+void union_range(const void* const* planes, int n_planes, int64_t a, int64_t b, uint8_t* __restrict__ out) {
+    // np.sum(mask, axis=3) > 0 per voxel.  Unsigned masks: the sum is positive iff any plane is non-zero (bitwise OR, no
+    // widening); signed integers sum exactly in int64; floating-point masks sum in float64 in plane order as numpy does.
+    using Acc = std::conditional_t<std::is_unsigned<T>::value, T, std::conditional_t<std::is_integral<T>::value, int64_t, double>>;
+    Acc acc[kHostTile];
+    for (int64_t v0 = a; v0 < b; v0 += kHostTile) {
+        const int n = (int)std::min<int64_t>(kHostTile, b - v0);
+        for (int j = 0; j < n; ++j) acc[j] = Acc(0);
+        for (int p = 0; p < n_planes; ++p) {
+            const T* __restrict__ src = static_cast<const T*>(planes[p]) + v0;
+            if constexpr (std::is_unsigned<T>::value) { for (int j = 0; j < n; ++j) acc[j] = (Acc)(acc[j] | src[j]); }
+            else { for (int j = 0; j < n; ++j) acc[j] += (Acc)src[j]; }
+        }
+        for (int j = 0; j < n; ++j) out[v0 + j] = acc[j] > Acc(0) ? 1 : 0;
+    }
+}
+
+template <typename T>
+void label_range(const void* label, int64_t a, int64_t b, uint8_t* __restrict__ out) {      // mask[label == 0] = 0
+    const T* __restrict__ l = static_cast<const T*>(label);
+    for (int64_t v = a; v < b; ++v) out[v] = (l[v] == T(0)) ? 0 : out[v];
+}
+
+// the 0/1 mask of [a, b), eight voxels per step (a is a multiple of 64; whole-zero words -- most of a brain volume -- are skipped)
+int64_t count_ones(const uint8_t* __restrict__ mask, int64_t a, int64_t b) {
+    int64_t n = 0, v = a;
+    for (; v + 8 <= b; v += 8) {
+        uint64_t w;
+        memcpy(&w, mask + v, 8);
+        n += (int64_t)((w * 0x0101010101010101ull) >> 56);                     // bytes are 0 or 1: their sum lands in the top byte
+    }
+    for (; v < b; ++v) n += mask[v];
+    return n;
+}
+
+void write_indices(const uint8_t* __restrict__ mask, int64_t a, int64_t b, int64_t* __restrict__ out) {
+    int64_t v = a;
+    for (; v + 8 <= b; v += 8) {
+        uint64_t w;
+        memcpy(&w, mask + v, 8);
+        if (w == 0) continue;
+        if (w == 0x0101010101010101ull) { for (int j = 0; j < 8; ++j) out[j] = v + j; out += 8; continue; }
+        for (int j = 0; j < 8; ++j) if (mask[v + j]) *out++ = v + j;
+    }
+    for (; v < b; ++v) if (mask[v]) *out++ = v;
+}
+
+template <typename F>
+bool by_dtype(int dtype, F&& f) {
+    switch (dtype) {
+        case T2FIT_DT_U8: f(uint8_t{}); return true;
+        case T2FIT_DT_I16: f(int16_t{}); return true;
+        case T2FIT_DT_U16: f(uint16_t{}); return true;
+        case T2FIT_DT_I32: f(int32_t{}); return true;
+        case T2FIT_DT_F32: f(float{}); return true;
+        case T2FIT_DT_F64: f(double{}); return true;
+        default: return false;
+    }
+}
+
+}  // namespace
+
 extern "C" {
 
 int t2fit_abi_version(void) { return T2FIT_ABI_VERSION; }
@@ -1686,6 +1756,10 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     }
     io.vec_ok = (reinterpret_cast<uintptr_t>(p->echoes) % 16) == 0;
     io.layout = p->layout;
+    {   // T2FIT_PREFETCH_AHEAD: distance of the L2 prefetch in blocks (0 = off); default = two waves of resident blocks
+        static const int env_ahead = [] { const char* e = getenv("T2FIT_PREFETCH_AHEAD"); return e ? atoi(e) : -1; }();
+        io.ahead = env_ahead >= 0 ? env_ahead : kPrefetchAheadWaves * c->prop.multiProcessorCount * 5;
+    }
     if (o->n_dup < 0 || o->n_dup > T2FIT_MAX_DUP) return fail(T2FIT_EINVAL, "n_dup out of range");
     if (o->n_dup > 0 && o->dense) return fail(T2FIT_EINVAL, "the fused all-gather (dup_*) takes compact outputs (dense = 0)");
     io.dup.n = o->n_dup;
@@ -1778,6 +1852,76 @@ int t2fit_mask_union(const void* const* planes, int32_t n_planes, int32_t dtype,
     const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)c->prop.multiProcessorCount * 16);
     mask_union_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, mask_out);
     CU_TRY(cudaGetLastError());
+    return T2FIT_OK;
+}
+
+int t2fit_host_mask_union_indices(const void* const* masks, int32_t n_masks, int32_t mask_dtype, const void* label,
+                                  int32_t label_dtype, int64_t n_vox, uint8_t* mask_out, int64_t* idx_out, int64_t* n_out) {
+    if (!masks || n_masks < 1 || n_masks > kMaxEcho || !mask_out || !idx_out || !n_out || n_vox < 0)
+        return fail(T2FIT_EINVAL, "bad host_mask_union_indices arguments");
+    if (mask_dtype < T2FIT_DT_U8 || mask_dtype > T2FIT_DT_F64 || (label && (label_dtype < T2FIT_DT_U8 || label_dtype > T2FIT_DT_F64)))
+        return fail(T2FIT_EINVAL, "bad dtype code");
+    for (int p = 0; p < n_masks; ++p) if (!masks[p]) return fail(T2FIT_EINVAL, "NULL mask plane");
+    *n_out = 0;
+    if (n_vox == 0) return T2FIT_OK;
+    std::lock_guard<std::mutex> g(g_host_mu);
+    Workers& w = host_workers();
+    const int parts = w.size();
+    std::vector<int64_t> count(parts + 1, 0);
+    const int64_t per = ((n_vox + parts - 1) / parts + 63) & ~(int64_t)63;
+    const bool prof = getenv("T2FIT_HOST_PROFILE") != nullptr;
+    const double t0 = prof ? now_ms() : 0.0;
+    w.run([&](int part, int) {                                                 // union (+ label) and the count of every range
+        const int64_t a = std::min<int64_t>(n_vox, part * per), b = std::min<int64_t>(n_vox, a + per);
+        if (a >= b) return;
+        by_dtype(mask_dtype, [&](auto t) { union_range<decltype(t)>(masks, n_masks, a, b, mask_out); });
+        if (label) by_dtype(label_dtype, [&](auto t) { label_range<decltype(t)>(label, a, b, mask_out); });
+        count[part + 1] = count_ones(mask_out, a, b);
+    });
+    for (int q = 0; q < parts; ++q) count[q + 1] += count[q];
+    const double t1 = prof ? now_ms() : 0.0;
+    w.run([&](int part, int) {                                                 // np.where(mask.flatten())[0], ascending
+        const int64_t a = std::min<int64_t>(n_vox, part * per), b = std::min<int64_t>(n_vox, a + per);
+        if (a < b) write_indices(mask_out, a, b, idx_out + count[part]);
+    });
+    *n_out = count[parts];
+    if (prof) fprintf(stderr, "[t2fit] host_mask_union_indices: %d threads, union + count %.3f ms, indices %.3f ms\n", parts, t1 - t0, now_ms() - t1);
+    return T2FIT_OK;
+}
+
+int t2fit_host_gather_planes(const void* const* planes, int32_t n_planes, int32_t dtype, const int64_t* idx, int64_t n_fit,
+                             int64_t n_vox, float* soa_out, int64_t ld) {
+    if (!planes || n_planes < 1 || n_planes > kMaxEcho || n_fit < 0 || n_vox < 0 || (n_fit > 0 && (!idx || !soa_out)) || ld < n_fit)
+        return fail(T2FIT_EINVAL, "bad host_gather_planes arguments");
+    if (dtype < T2FIT_DT_U8 || dtype > T2FIT_DT_F64) return fail(T2FIT_EINVAL, "bad dtype code");
+    for (int p = 0; p < n_planes; ++p) if (!planes[p]) return fail(T2FIT_EINVAL, "NULL plane");
+    if (n_fit == 0) return T2FIT_OK;
+    std::lock_guard<std::mutex> g(g_host_mu);
+    Workers& w = host_workers();
+    const int parts = w.size();
+    const int64_t per = ((n_fit + parts - 1) / parts + 63) & ~(int64_t)63;
+    std::atomic<int> bad{0};
+    w.run([&](int part, int) {
+        const int64_t a = std::min<int64_t>(n_fit, part * per), b = std::min<int64_t>(n_fit, a + per);
+        for (int64_t j = a; j < b; ++j) if (idx[j] < 0 || idx[j] >= n_vox) { bad.store(1); return; }
+        by_dtype(dtype, [&](auto t) {
+            using T = decltype(t);
+            const int64_t* __restrict__ ix = idx;
+            for (int p = 0; p < n_planes; ++p) {                               // .astype(np.float32) of the rows the fit reads
+                const T* __restrict__ src = static_cast<const T*>(planes[p]);
+                float* __restrict__ dst = soa_out + (int64_t)p * ld;
+                int64_t j = a;
+                for (; j + 8 <= b; j += 8) {                                   // masked voxels come in runs along x: 8 in a row
+                    const int64_t v = ix[j];
+                    __builtin_prefetch(src + ix[std::min<int64_t>(j + 256, b - 1)]);       // the next runs' first lines
+                    if (ix[j + 7] - v == 7) { for (int q = 0; q < 8; ++q) dst[j + q] = (float)src[v + q]; }
+                    else { for (int q = 0; q < 8; ++q) dst[j + q] = (float)src[ix[j + q]]; }
+                }
+                for (; j < b; ++j) dst[j] = (float)src[ix[j]];
+            }
+        });
+    });
+    if (bad.load()) return fail(T2FIT_EINVAL, "host_gather_planes: index outside [0, n_vox)");
     return T2FIT_OK;
 }
 

@@ -207,6 +207,19 @@ int t2fit_mask_indices(const uint8_t *masks, int64_t n_vox, int32_t n_masks, int
 int t2fit_mask_union(const void *const *planes, int32_t n_planes, int32_t dtype, const void *label, int32_t label_dtype,
                      int64_t n_vox, uint8_t *mask_out, void *stream);
 
+/* Host-side variant for sparse masks (pure host code on the library's worker threads; no GPU, no t2fit_init needed): the
+ * same union + label masking from HOST mask volumes, plus np.where(mask.flatten())[0] (:421) in one call:
+ * mask_out[v] as above (host uint8 [n_vox]), idx_out[0 .. *n_out) = ascending flat indices of the union (host int64,
+ * room for n_vox entries). */
+int t2fit_host_mask_union_indices(const void *const *masks, int32_t n_masks, int32_t mask_dtype, const void *label,
+                                  int32_t label_dtype, int64_t n_vox, uint8_t *mask_out, int64_t *idx_out, int64_t *n_out);
+
+/* ... and the gather of the masked voxels of every per-TE HOST volume with the float32 cast of :411-412, packed
+ * echo-major: soa_out[p * ld + i] = (float)planes[p][idx[i]] (T2FIT_LAYOUT_SOA with this ld; ld >= n_fit).  planes: n_planes
+ * host pointers to [n_vox] arrays of element type `dtype` (T2FIT_DT_*).  EINVAL if an index lies outside [0, n_vox). */
+int t2fit_host_gather_planes(const void *const *planes, int32_t n_planes, int32_t dtype, const int64_t *idx, int64_t n_fit,
+                             int64_t n_vox, float *soa_out, int64_t ld);
+
 /* Phantom ROI statistics (save_phantom_csv, utils/t2map_utils.py:30-59): for every label value 1..n_roi the
  * NaN-skipping mean and population standard deviation (np.nanmean / np.nanstd) of each of n_maps float32 maps
  * over the voxels with label == value.  maps: HOST array of n_maps DEVICE pointers to [n_vox] float32; label:

@@ -1,5 +1,6 @@
 """Rows (f3)/(f4) of the scope table on the GPU: the batched per-TE loader (mask union, --in_vitro_fast label masking,
-PLANES layout, overlapped staging) against the one-volume path, and the phantom ROI statistics against numpy."""
+PLANES layout, overlapped staging; route="auto" = mask part on the host + masked voxels only over PCIe for sparse masks,
+route="device" = everything on the GPU) against the one-volume path, and the phantom ROI statistics against numpy."""
 import numpy as np
 import pytest
 
@@ -8,14 +9,14 @@ from fetal_t2mapping_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def _volume(shape, te, seed, mask_dtype=np.uint8):
+def _volume(shape, te, seed, mask_dtype=np.uint8, dense=False):
     rng = np.random.default_rng(seed)
     n = int(np.prod(shape))
     t2 = rng.uniform(60, 300, n)
     s0 = rng.uniform(300, 900, n)
     y = (s0[:, None] * np.exp(-te[None, :] / t2[:, None]) + rng.normal(0, 6, (n, te.size))).astype(np.float32)
     t2w = [np.ascontiguousarray(y[:, e].reshape(shape)) for e in range(te.size)]      # per-TE volumes, as read from disk
-    base = synth.ellipsoid_mask(shape, [0.45 * s for s in shape])
+    base = synth.ellipsoid_mask(shape, [(0.7 if dense else 0.45) * s for s in shape])     # dense: > half of the volume
     masks = []
     for e in range(te.size):                                                          # per-TE masks differ slightly
         m = base.copy()
@@ -26,16 +27,21 @@ def _volume(shape, te, seed, mask_dtype=np.uint8):
     return t2w, masks, label
 
 
+@pytest.mark.parametrize("route", ["auto", "device"])
 @pytest.mark.parametrize("fit", ["gaussian", "gaussian_rician"])
-def test_series_loader_matches_single_volume_path(gpu_lib, fit):
+def test_series_loader_matches_single_volume_path(gpu_lib, fit, route):
     te = np.array([114.0, 150.0, 202.0, 299.0])
     _, fp = gpu_lib.preset(fit, True)
-    shapes = [(12, 14, 10), (20, 18, 16), (12, 14, 10), (9, 7, 11), (20, 18, 16)]
-    vols = [_volume(s, te, 10 + i, np.uint8 if i % 2 == 0 else np.float32) for i, s in enumerate(shapes)]
-    out = list(gpu_lib.t2map_series(((v[0], v[1]) for v in vols), te, fit, fp, prior=False, solver="fast", depth=2))
+    shapes = [(12, 14, 10), (20, 18, 16), (12, 14, 10), (9, 7, 11), (20, 18, 16), (12, 14, 10), (11, 13, 9)]
+    mask_dt = [np.uint8, np.float32, np.bool_, np.float64, np.int16, np.uint8, np.int32]
+    vols = [_volume(s, te, 10 + i, mask_dt[i], dense=i in (2, 5)) for i, s in enumerate(shapes)]
+    vols[3] = ([a.astype(np.float64) for a in vols[3][0]], vols[3][1], vols[3][2])    # float64 volumes, as nibabel's get_fdata gives
+    vols[4][1][0][...] = -1                                                           # a signed mask plane: the SUM decides (:384)
+    assert any(2 * int((np.sum(np.stack(v[1], -1), axis=3) > 0).sum()) > v[1][0].size for v in vols)      # both host routes run
+    out = list(gpu_lib.t2map_series(((v[0], v[1]) for v in vols), te, fit, fp, prior=False, solver="fast", depth=2, route=route))
     assert len(out) == len(vols)
     for (t2w, masks, _), r in zip(vols, out):
-        stack = np.stack(t2w, axis=-1)                                                # :385
+        stack = np.stack(t2w, axis=-1).astype(np.float32)                             # :385, :411
         mask4 = np.stack(masks, axis=-1)                                              # :383
         ref = gpu_lib.t2map_volume(stack, mask4, te, fit, fp, prior=False, solver="fast")
         union = np.sum(mask4, axis=3) > 0                                             # :384
@@ -62,22 +68,24 @@ def test_series_loader_default_solver_is_the_faithful_one_for_three_parameter_fi
             assert (r.sigma[r.mask] >= 2.0).all()          # the 3-parameter fits fill the sigma map
 
 
-def test_series_loader_in_vitro_fast_label_masking(gpu_lib):
+@pytest.mark.parametrize("route", ["auto", "device"])
+def test_series_loader_in_vitro_fast_label_masking(gpu_lib, route):
     te = np.array([114.0, 202.0, 299.0])
     _, fp = gpu_lib.preset("gaussian", True)
     vols = [_volume((16, 12, 14), te, 40 + i) for i in range(3)]
-    out = list(gpu_lib.t2map_series(vols, te, "gaussian", fp, prior=True, fast=True))
+    out = list(gpu_lib.t2map_series(vols, te, "gaussian", fp, prior=True, fast=True, route=route))
     for (t2w, masks, label), r in zip(vols, out):
         m = np.sum(np.stack(masks, -1), axis=3) > 0
         m[label == 0] = 0                                                             # :393-400
         assert np.array_equal(r.mask, m)
         assert (r.t2[~m] == 0).all() and (r.t2[m] > 0).all()
     # without `fast` the label is ignored
-    out2 = list(gpu_lib.t2map_series(vols, te, "gaussian", fp, prior=True, fast=False))
+    out2 = list(gpu_lib.t2map_series(vols, te, "gaussian", fp, prior=True, fast=False, route=route))
     assert out2[0].n_fit > out[0].n_fit
 
 
-def test_series_loader_bounds_error_aborts_like_the_reference(gpu_lib):
+@pytest.mark.parametrize("route", ["auto", "device"])
+def test_series_loader_bounds_error_aborts_like_the_reference(gpu_lib, route):
     te = np.array([114.0, 202.0, 299.0])
     _, fp = gpu_lib.preset("gaussian", True)
     t2w, masks, _ = _volume((8, 8, 8), te, 3)
@@ -85,7 +93,7 @@ def test_series_loader_bounds_error_aborts_like_the_reference(gpu_lib):
     for m in masks:
         m[4, 4, 4] = 1
     with pytest.raises(ValueError):
-        list(gpu_lib.t2map_series([(t2w, masks)], te, "gaussian", fp, prior=False))
+        list(gpu_lib.t2map_series([(t2w, masks)], te, "gaussian", fp, prior=False, route=route))
 
 
 def test_planes_layout_host_and_device_equal_aos(gpu_lib):
