@@ -147,7 +147,6 @@ __device__ __forceinline__ void load_soa(const float* __restrict__ base, int64_t
 // the fit kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kQueueRefill = 8;      // floor_queue_kernel: waiting lanes per warp that trigger epilogue + refill
-constexpr int kPrefetchAheadWaves = 0;  // fit_kernel: L2 prefetch distance in waves of resident blocks (KernelIO::ahead); 0 = off
 constexpr int kFusedFillMaxWpt = 16; // fused fill only while a fit thread gets at most this many mask words
 constexpr int kFillChunk = 512;    // dense voxels zero-filled by one warp per round (32 lanes x 4 words x 4 voxels)
 
@@ -1756,9 +1755,12 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     }
     io.vec_ok = (reinterpret_cast<uintptr_t>(p->echoes) % 16) == 0;
     io.layout = p->layout;
-    {   // T2FIT_PREFETCH_AHEAD: distance of the L2 prefetch in blocks (0 = off); default = two waves of resident blocks
+    {   // T2FIT_PREFETCH_AHEAD: distance of the L2 prefetch in blocks (0 = off).  Default: 3/4 of the resident blocks -- c2 on
+        // 148 SMs x 5 blocks: 63.4 us per pass without, 62.9 / 62.2 / 61.9 / 61.9 / 62.0 / 62.4 / 63.2 / 63.9 at 148 / 296 / 444 /
+        // 592 / 740 / 888 / 1036 / 1184 blocks (profiles/r02_notes.md section 8)
         static const int env_ahead = [] { const char* e = getenv("T2FIT_PREFETCH_AHEAD"); return e ? atoi(e) : -1; }();
-        io.ahead = env_ahead >= 0 ? env_ahead : kPrefetchAheadWaves * c->prop.multiProcessorCount * 5;
+        const int resident = c->prop.multiProcessorCount * min_blocks(p->model == T2FIT_MODEL_GAUSSIAN ? kMono2 : kFloor3, p->n_echo);
+        io.ahead = env_ahead >= 0 ? env_ahead : (3 * resident) / 4;
     }
     if (o->n_dup < 0 || o->n_dup > T2FIT_MAX_DUP) return fail(T2FIT_EINVAL, "n_dup out of range");
     if (o->n_dup > 0 && o->dense) return fail(T2FIT_EINVAL, "the fused all-gather (dup_*) takes compact outputs (dense = 0)");
