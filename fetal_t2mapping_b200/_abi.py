@@ -16,8 +16,8 @@ MODEL_GAUSSIAN = 0
 MODEL_GAUSSIAN_RICIAN = 1
 MODEL_RICIAN = 2
 MODELS = {"gaussian": MODEL_GAUSSIAN, "gaussian_rician": MODEL_GAUSSIAN_RICIAN, "rician": MODEL_RICIAN}
-SOLVER_FAST, SOLVER_LBFGSB = 0, 1
-SOLVERS = {"fast": SOLVER_FAST, "lbfgsb": SOLVER_LBFGSB}
+SOLVER_FAST, SOLVER_LBFGSB, SOLVER_LBFGSB_DENSE = 0, 1, 2
+SOLVERS = {"fast": SOLVER_FAST, "lbfgsb": SOLVER_LBFGSB, "lbfgsb_dense": SOLVER_LBFGSB_DENSE}
 
 LAYOUT_AOS = 0
 LAYOUT_SOA = 1

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, os.environ.get("T2FIT_LIB_NAME", "libt2fit.so"))   # T2FIT_LIB_NAME: variant builds for A/B runs
 SOURCES = ["t2fit_kernels.cu"]
-HEADERS = ["t2fit_core.cuh", "t2fit_lbfgsb.cuh", "t2fit_lbfgsb_coop.cuh", "t2fit_i0e_coeffs.h", "t2fit_consts.h", "t2fit_workers.h", os.path.join("..", "..", "include", "t2fit.h")]
+HEADERS = ["t2fit_core.cuh", "t2fit_lbfgsb.cuh", "t2fit_lbfgsb_coop.cuh", "t2fit_lbfgsb_dense.cuh", "t2fit_i0e_coeffs.h", "t2fit_consts.h", "t2fit_workers.h", os.path.join("..", "..", "include", "t2fit.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "--split-compile", "0"] + \

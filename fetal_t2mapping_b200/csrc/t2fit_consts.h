@@ -64,6 +64,7 @@ inline int make_lb_consts(const t2fit_problem& p, lb::LbConsts& c, std::string& 
     c.no_prior = p.no_prior ? 1 : 0;
     c.norm = p.norm ? 1 : 0;
     c.objective = p.model;
+    c.dense = p.solver == T2FIT_SOLVER_LBFGSB_DENSE ? 1 : 0;
     return T2FIT_OK;
 }
 

@@ -39,6 +39,7 @@
 
 #include "t2fit_consts.h"
 #include "t2fit_lbfgsb_coop.cuh"
+#include "t2fit_lbfgsb_dense.cuh"
 #include "t2fit_workers.h"
 
 using namespace t2fit;
@@ -486,8 +487,7 @@ __global__ void __launch_bounds__(kQBlock, queue_min_blocks(E)) floor_queue_kern
 constexpr int kLbBlock = 128;
 
 template <int OBJ>
-__device__ __noinline__ void lb_store(const lb::LbConsts& c, const KernelIO& io, const lb::VoxelRun<OBJ>& run, int64_t i, int64_t row) {
-    const lb::LbVoxel v = run.finish();
+__device__ __noinline__ void lb_store(const lb::LbConsts& c, const KernelIO& io, const lb::LbVoxel& v, const float* y, int64_t i, int64_t row) {
     const int E = c.n_echo;
     const float kf = (float)v.x[0], t2f = (float)v.x[1], sf = (OBJ == 0) ? 0.f : (float)v.x[2];
     // residual epilogue on the stored float32 values; run.y is the signal as the fit saw it (normalised if norm)
@@ -495,7 +495,7 @@ __device__ __noinline__ void lb_store(const lb::LbConsts& c, const KernelIO& io,
     for (int e = 0; e < E; ++e) {
         double pred = (double)kf * exp(-c.te[e] / (double)t2f);
         if (OBJ != 0) pred = sqrt(pred * pred + (double)sf * (double)sf);
-        acc += (double)run.y[e] - (double)(float)pred;
+        acc += (double)y[e] - (double)(float)pred;
     }
     const int64_t o = io.dense ? row : i;
     if (io.t2) io.t2[o] = t2f;
@@ -518,13 +518,11 @@ __device__ __noinline__ void lb_store(const lb::LbConsts& c, const KernelIO& io,
 #ifndef T2_LB_MIN_BLOCKS
 #define T2_LB_MIN_BLOCKS 8
 #endif
-template <int OBJ>
-__global__ void __launch_bounds__(kLbBlock, T2_LB_MIN_BLOCKS) lbfgsb_kernel(const __grid_constant__ lb::LbConsts c,
-                                                          const __grid_constant__ KernelIO io,
-                                                          unsigned long long* __restrict__ queue) {
+template <int OBJ, class Run>
+__device__ __forceinline__ void lb_queue_loop(const lb::LbConsts& c, const KernelIO& io, unsigned long long* __restrict__ queue) {
     const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
     const int E = c.n_echo;
-    lb::VoxelRun<OBJ> run;
+    Run run;
     run.active = false;
     int64_t cur = -1, row = 0;
     bool exhausted = false;
@@ -550,7 +548,7 @@ __global__ void __launch_bounds__(kLbBlock, T2_LB_MIN_BLOCKS) lbfgsb_kernel(cons
                     const bool tr = io.trace_cap > 0;
                     run.start(yraw, c, (tr && io.trace_f) ? io.trace_f + i * io.trace_cap : nullptr,
                               (tr && io.trace_step) ? io.trace_step + i * io.trace_cap : nullptr, tr ? io.trace_cap : 0);
-                    if (!run.active) lb_store<OBJ>(c, io, run, cur, row);      // non-finite input / bad bounds: no optimiser run
+                    if (!run.active) lb_store<OBJ>(c, io, run.finish(), run.y, cur, row);      // non-finite input / bad bounds: no optimiser run
                 } else {
                     exhausted = true;
                 }
@@ -562,9 +560,34 @@ __global__ void __launch_bounds__(kLbBlock, T2_LB_MIN_BLOCKS) lbfgsb_kernel(cons
         }
         if (run.active) {
             run.pass(c);
-            if (!run.active) lb_store<OBJ>(c, io, run, cur, row);
+            if (!run.active) lb_store<OBJ>(c, io, run.finish(), run.y, cur, row);
         }
     }
+}
+
+
+template <int OBJ>
+__global__ void __launch_bounds__(kLbBlock, T2_LB_MIN_BLOCKS) lbfgsb_kernel(const __grid_constant__ lb::LbConsts c,
+                                                          const __grid_constant__ KernelIO io,
+                                                          unsigned long long* __restrict__ queue) {
+    lb_queue_loop<OBJ, lb::VoxelRun<OBJ>>(c, io, queue);
+}
+
+// ------------------------------------------------------------------------------------------------
+// lbfgsb_dense_kernel: the same optimiser with the limited-memory matrix as a dense n x n matrix (t2fit_lbfgsb_dense.cuh),
+// one voxel per thread, FP64, same lane queue.  The state of a voxel is the <= 10 correction pairs (480 B of local memory,
+// L1-resident) plus ~50 doubles the compiler keeps in registers, and the optimiser core is a few hundred flops per
+// iteration: the kernel is bound by the FP64 pipe evaluating the objective (N + 1 values per gradient, 2 exponentials per
+// echo), not by memory.
+// ------------------------------------------------------------------------------------------------
+#ifndef T2_LBD_MIN_BLOCKS
+#define T2_LBD_MIN_BLOCKS 4
+#endif
+template <int OBJ>
+__global__ void __launch_bounds__(kLbBlock, T2_LBD_MIN_BLOCKS) lbfgsb_dense_kernel(const __grid_constant__ lb::LbConsts c,
+                                                                const __grid_constant__ KernelIO io,
+                                                                unsigned long long* __restrict__ queue) {
+    lb_queue_loop<OBJ, lb::DenseRun<OBJ>>(c, io, queue);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -927,8 +950,13 @@ QueueFn pick_queue_kernel(int n_echo, int layout) {
 
 using LbFn = void (*)(const lb::LbConsts, const KernelIO, unsigned long long*);
 
-LbFn pick_lb_kernel(int model, int n_echo) {
+LbFn pick_lb_kernel(int model, int n_echo, bool dense) {
     if (n_echo < 2 || n_echo > kMaxEcho) return nullptr;
+    if (dense) {
+        if (model == T2FIT_MODEL_GAUSSIAN) return lbfgsb_dense_kernel<0>;
+        if (model == T2FIT_MODEL_GAUSSIAN_RICIAN) return lbfgsb_dense_kernel<1>;
+        return lbfgsb_dense_kernel<2>;
+    }
     if (model == T2FIT_MODEL_GAUSSIAN) return lbfgsb_kernel<0>;
     if (model == T2FIT_MODEL_GAUSSIAN_RICIAN) return lbfgsb_kernel<1>;
     return lbfgsb_kernel<2>;
@@ -1117,12 +1145,13 @@ int launch_lbfgsb(Context* c, const lb::LbConsts& lc, KernelIO io, int model, in
     // profiles/r02_notes.md -- kept as the cross-check of the thread kernel).  Read per call: tests and A/B runs switch it.
     const char* ek = getenv("T2FIT_LB_KERNEL");
     const int lanes = !ek ? 0 : !strcmp(ek, "coop8") ? 8 : !strcmp(ek, "coop16") ? 16 : !strcmp(ek, "coop32") ? 32 : 0;
-    if (lanes) return launch_lbfgsb_coop(c, lc, io, model, lanes, st);
-    LbFn fn = pick_lb_kernel(model, n_echo);
+    if (lanes && !lc.dense) return launch_lbfgsb_coop(c, lc, io, model, lanes, st);
+    LbFn fn = pick_lb_kernel(model, n_echo, lc.dense != 0);
     if (!fn) return fail(T2FIT_EINVAL, "no kernel for this n_echo");
     // persistent grid sized to what is resident at once; voxels are handed out through a queue counter
     static const int env_per_sm = [] { const char* e = getenv("T2FIT_LB_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
-    int per_sm = env_per_sm;
+    static const int env_per_sm_dense = [] { const char* e = getenv("T2FIT_LBD_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
+    int per_sm = lc.dense ? env_per_sm_dense : env_per_sm;
     if (per_sm <= 0) {
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kLbBlock, 0));
         if (per_sm <= 0) per_sm = 1;
@@ -1712,8 +1741,9 @@ int t2fit_run(const t2fit_problem* p, t2fit_outputs* o, void* stream) {
     memset(&fc, 0, sizeof(fc));
     memset(&lc, 0, sizeof(lc));
     std::string err;
-    if (p->solver != T2FIT_SOLVER_FAST && p->solver != T2FIT_SOLVER_LBFGSB) return fail(T2FIT_EINVAL, "unknown solver");
-    const bool lbs = p->solver == T2FIT_SOLVER_LBFGSB;
+    if (p->solver != T2FIT_SOLVER_FAST && p->solver != T2FIT_SOLVER_LBFGSB && p->solver != T2FIT_SOLVER_LBFGSB_DENSE)
+        return fail(T2FIT_EINVAL, "unknown solver");
+    const bool lbs = p->solver != T2FIT_SOLVER_FAST;
     if (!lbs && p->model == T2FIT_MODEL_RICIAN)
         return fail(T2FIT_EINVAL, "fit 'rician' (negative log-likelihood) needs solver T2FIT_SOLVER_LBFGSB");
     int rc = lbs ? make_lb_consts(*p, lc, err) : make_consts(*p, fc, err);

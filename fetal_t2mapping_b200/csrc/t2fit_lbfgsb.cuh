@@ -79,6 +79,7 @@ struct LbConsts {
     int no_prior;
     int norm;
     int objective;            // 0 gaussian, 1 gaussian_rician, 2 rician
+    int dense;                // T2FIT_SOLVER_LBFGSB_DENSE: the dense-matrix form (t2fit_lbfgsb_dense.cuh)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -157,22 +158,29 @@ T2_NI double i0e(double x) {
 // One echo's term of the objective at parameters p (shared by the thread-per-voxel and the cooperative kernels, which
 // evaluate the echoes of one objective call on different lanes: the per-call quantities k^2, sigma^2, log(sigma^2) are
 // recomputed per echo, deterministically the same values).
+// the exponential of one echo's term: the only part that depends on T2 (p[1]) alone
 template <int OBJ>
-T2_HD double objective_term(const double* p, float y, double te) {
+T2_HD double objective_expo(double t2, double te) {
+    if constexpr (OBJ == 1) return exp(mul(-2.0, te) / t2);     // np.exp(-2 * t / t2)
+    else return exp((-te) / t2);                                // np.exp(-t / t2)
+}
+
+// the term given that exponential (u): the forward differences in k and sigma reuse the exponentials of the base point
+template <int OBJ>
+T2_HD double objective_term_u(const double* p, float y, double u) {
     if constexpr (OBJ == 0) {                                   // gauss_obj :141-147
-        const double k = p[0], t2 = p[1];
-        const double m = mul(k, exp((-te) / t2));                    // k * np.exp(-t / t2)
+        const double m = mul(p[0], u);                               // k * np.exp(-t / t2)
         const double r = sub((double)y, m);
         return mul(r, r);
     } else if constexpr (OBJ == 1) {                            // gauss_rician_obj :149-155
-        const double k2 = mul(p[0], p[0]), t2 = p[1], s2 = mul(p[2], p[2]);
-        const double m = sqrt(add(mul(k2, exp(mul(-2.0, te) / t2)), s2));
+        const double k2 = mul(p[0], p[0]), s2 = mul(p[2], p[2]);
+        const double m = sqrt(add(mul(k2, u), s2));
         const double r = sub((double)y, m);
         return mul(r, r);
     } else {                                                    // rician_obj :157-177 (negative log-likelihood)
-        const double k = p[0], t2 = p[1], s2 = mul(p[2], p[2]);
+        const double k = p[0], s2 = mul(p[2], p[2]);
         const double ls2 = log(s2), ts2 = mul(2.0, s2);
-        const double m = mul(k, exp((-te) / t2));
+        const double m = mul(k, u);
         const double x = mul(m, (double)y) / s2;
         const float lg = logf(y);                                   // np.log(float32) stays float32
         const float y2 = mulf(y, y);                                // signal**2 stays float32
@@ -181,6 +189,11 @@ T2_HD double objective_term(const double* p, float y, double te) {
         const double cc = add(fabs(x), log(i0e(x)));
         return add(sub(a, b), cc);
     }
+}
+
+template <int OBJ>
+T2_HD double objective_term(const double* p, float y, double te) {
+    return objective_term_u<OBJ>(p, y, objective_expo<OBJ>(p[1], te));
 }
 
 // np.sum of the E terms and the final scaling (mean for the two least-squares objectives, negated sum for the NLL)
@@ -197,6 +210,78 @@ T2_NI double objective(const double* p, const float* y32, const LbConsts& c) {
     for (int e = 0; e < E; ++e) v[e] = objective_term<OBJ>(p, y32[e], c.te[e]);
     return objective_reduce<OBJ>(v, E);
 }
+
+// ---------------------------------------------------------------------------------------------
+// More'-Thuente safeguarded step (MINPACK-2 dcstep)
+// ---------------------------------------------------------------------------------------------
+T2_HD void dcstep_body(double& stx_, double& fx_, double& dx_, double& sty_, double& fy_, double& dy_, double& stp_,
+                         double fp, double dp, bool& brackt_, double stpmin, double stpmax) {
+    const double sgnd = dp * ddiv(dx_, fabs(dx_));
+    double stpf;
+    if (fp > fx_) {
+        const double th = ddiv(3.0 * (fx_ - fp), stp_ - stx_) + dx_ + dp;
+        const double s = rmax(fabs(th), rmax(fabs(dx_), fabs(dp)));
+        const double ths = ddiv(th, s);
+        double gamma = s * dsqrt(ths * ths - ddiv(dx_, s) * ddiv(dp, s));
+        if (stp_ < stx_) gamma = -gamma;
+        const double p = (gamma - dx_) + th, q = ((gamma - dx_) + gamma) + dp, rr = ddiv(p, q);
+        const double stpc = stx_ + rr * (stp_ - stx_);
+        const double stpq = stx_ + (ddiv(dx_, ddiv(fx_ - fp, stp_ - stx_) + dx_) * 0.5) * (stp_ - stx_);
+        stpf = (fabs(stpc - stx_) < fabs(stpq - stx_)) ? stpc : stpc + (stpq - stpc) * 0.5;
+        brackt_ = true;
+    } else if (sgnd < 0.0) {
+        const double th = ddiv(3.0 * (fx_ - fp), stp_ - stx_) + dx_ + dp;
+        const double s = rmax(fabs(th), rmax(fabs(dx_), fabs(dp)));
+        const double ths = ddiv(th, s);
+        double gamma = s * dsqrt(ths * ths - ddiv(dx_, s) * ddiv(dp, s));
+        if (stp_ > stx_) gamma = -gamma;
+        const double p = (gamma - dp) + th, q = ((gamma - dp) + gamma) + dx_, rr = ddiv(p, q);
+        const double stpc = stp_ + rr * (stx_ - stp_);
+        const double stpq = stp_ + ddiv(dp, dp - dx_) * (stx_ - stp_);
+        stpf = (fabs(stpc - stp_) > fabs(stpq - stp_)) ? stpc : stpq;
+        brackt_ = true;
+    } else if (fabs(dp) < fabs(dx_)) {
+        const double th = ddiv(3.0 * (fx_ - fp), stp_ - stx_) + dx_ + dp;
+        const double s = rmax(fabs(th), rmax(fabs(dx_), fabs(dp)));
+        const double ths = ddiv(th, s);
+        double gamma = s * dsqrt(rmax(0.0, ths * ths - ddiv(dx_, s) * ddiv(dp, s)));
+        if (stp_ > stx_) gamma = -gamma;
+        const double p = (gamma - dp) + th, q = (gamma + (dx_ - dp)) + gamma, rr = ddiv(p, q);
+        double stpc;
+        if (rr < 0.0 && gamma != 0.0) stpc = stp_ + rr * (stx_ - stp_);
+        else if (stp_ > stx_) stpc = stpmax;
+        else stpc = stpmin;
+        const double stpq = stp_ + ddiv(dp, dp - dx_) * (stx_ - stp_);
+        if (brackt_) {
+            stpf = (fabs(stpc - stp_) < fabs(stpq - stp_)) ? stpc : stpq;
+            if (stp_ > stx_) stpf = rmin(stp_ + 0.66 * (sty_ - stp_), stpf);
+            else stpf = rmax(stp_ + 0.66 * (sty_ - stp_), stpf);
+        } else {
+            stpf = (fabs(stpc - stp_) > fabs(stpq - stp_)) ? stpc : stpq;
+            stpf = rmin(stpmax, stpf);
+            stpf = rmax(stpmin, stpf);
+        }
+    } else {
+        if (brackt_) {
+            const double th = ddiv(3.0 * (fp - fy_), sty_ - stp_) + dy_ + dp;
+            const double s = rmax(fabs(th), rmax(fabs(dy_), fabs(dp)));
+            const double ths = ddiv(th, s);
+            double gamma = s * dsqrt(ths * ths - ddiv(dy_, s) * ddiv(dp, s));
+            if (stp_ > sty_) gamma = -gamma;
+            const double p = (gamma - dp) + th, q = ((gamma - dp) + gamma) + dy_, rr = ddiv(p, q);
+            stpf = stp_ + rr * (sty_ - stp_);
+        } else if (stp_ > stx_) stpf = stpmax;
+        else stpf = stpmin;
+    }
+    if (fp > fx_) {
+        sty_ = stp_; fy_ = fp; dy_ = dp;
+    } else {
+        if (sgnd < 0.0) { sty_ = stx_; fy_ = fx_; dy_ = dx_; }
+        stx_ = stp_; fx_ = fp; dx_ = dp;
+    }
+    stp_ = stpf;
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // the optimiser state of one voxel
@@ -253,7 +338,18 @@ struct Solver {
     }
 
     // "refresh the lbfgs memory and restart the iteration"
+#ifdef T2FIT_HOSTSIM
+    void reset_memory() { col = 0; head = 0; theta = 1.0; iupdat = 0; updatd = false; stale_rows = 0; }
+#else
     T2_HD void reset_memory() { col = 0; head = 0; theta = 1.0; iupdat = 0; updatd = false; }
+#endif
+#ifdef T2FIT_HOSTSIM
+    int brk_mask = 0, brk_iter = -1, brk_col = -1;            // test instrumentation: which factorization broke down first, where
+    int stale_rows = 0;
+    void note_break(int bit) { if (!brk_mask) { brk_iter = iter; brk_col = col; } brk_mask |= bit; }
+#else
+    T2_HD void note_break(int) {}
+#endif
 
     // ---- LINPACK-style kernels on the small dense matrices ----------------------------------
     // Cholesky A = R'R of the leading nn x nn block starting at (o, o), upper triangle in place; false = not SPD
@@ -689,73 +785,10 @@ struct Solver {
         return dpofa<kM>(wt, 0, col);
     }
 
-    // ---- More'-Thuente safeguarded step (MINPACK-2 dcstep) -------------------------------
+    // ---- More'-Thuente safeguarded step (dcstep_body above), one out-of-line copy per parameter count ----
     T2_NI static void dcstep(double& stx_, double& fx_, double& dx_, double& sty_, double& fy_, double& dy_, double& stp_,
                              double fp, double dp, bool& brackt_, double stpmin, double stpmax) {
-        const double sgnd = dp * ddiv(dx_, fabs(dx_));
-        double stpf;
-        if (fp > fx_) {
-            const double th = ddiv(3.0 * (fx_ - fp), stp_ - stx_) + dx_ + dp;
-            const double s = rmax(fabs(th), rmax(fabs(dx_), fabs(dp)));
-            const double ths = ddiv(th, s);
-            double gamma = s * dsqrt(ths * ths - ddiv(dx_, s) * ddiv(dp, s));
-            if (stp_ < stx_) gamma = -gamma;
-            const double p = (gamma - dx_) + th, q = ((gamma - dx_) + gamma) + dp, rr = ddiv(p, q);
-            const double stpc = stx_ + rr * (stp_ - stx_);
-            const double stpq = stx_ + (ddiv(dx_, ddiv(fx_ - fp, stp_ - stx_) + dx_) * 0.5) * (stp_ - stx_);
-            stpf = (fabs(stpc - stx_) < fabs(stpq - stx_)) ? stpc : stpc + (stpq - stpc) * 0.5;
-            brackt_ = true;
-        } else if (sgnd < 0.0) {
-            const double th = ddiv(3.0 * (fx_ - fp), stp_ - stx_) + dx_ + dp;
-            const double s = rmax(fabs(th), rmax(fabs(dx_), fabs(dp)));
-            const double ths = ddiv(th, s);
-            double gamma = s * dsqrt(ths * ths - ddiv(dx_, s) * ddiv(dp, s));
-            if (stp_ > stx_) gamma = -gamma;
-            const double p = (gamma - dp) + th, q = ((gamma - dp) + gamma) + dx_, rr = ddiv(p, q);
-            const double stpc = stp_ + rr * (stx_ - stp_);
-            const double stpq = stp_ + ddiv(dp, dp - dx_) * (stx_ - stp_);
-            stpf = (fabs(stpc - stp_) > fabs(stpq - stp_)) ? stpc : stpq;
-            brackt_ = true;
-        } else if (fabs(dp) < fabs(dx_)) {
-            const double th = ddiv(3.0 * (fx_ - fp), stp_ - stx_) + dx_ + dp;
-            const double s = rmax(fabs(th), rmax(fabs(dx_), fabs(dp)));
-            const double ths = ddiv(th, s);
-            double gamma = s * dsqrt(rmax(0.0, ths * ths - ddiv(dx_, s) * ddiv(dp, s)));
-            if (stp_ > stx_) gamma = -gamma;
-            const double p = (gamma - dp) + th, q = (gamma + (dx_ - dp)) + gamma, rr = ddiv(p, q);
-            double stpc;
-            if (rr < 0.0 && gamma != 0.0) stpc = stp_ + rr * (stx_ - stp_);
-            else if (stp_ > stx_) stpc = stpmax;
-            else stpc = stpmin;
-            const double stpq = stp_ + ddiv(dp, dp - dx_) * (stx_ - stp_);
-            if (brackt_) {
-                stpf = (fabs(stpc - stp_) < fabs(stpq - stp_)) ? stpc : stpq;
-                if (stp_ > stx_) stpf = rmin(stp_ + 0.66 * (sty_ - stp_), stpf);
-                else stpf = rmax(stp_ + 0.66 * (sty_ - stp_), stpf);
-            } else {
-                stpf = (fabs(stpc - stp_) > fabs(stpq - stp_)) ? stpc : stpq;
-                stpf = rmin(stpmax, stpf);
-                stpf = rmax(stpmin, stpf);
-            }
-        } else {
-            if (brackt_) {
-                const double th = ddiv(3.0 * (fp - fy_), sty_ - stp_) + dy_ + dp;
-                const double s = rmax(fabs(th), rmax(fabs(dy_), fabs(dp)));
-                const double ths = ddiv(th, s);
-                double gamma = s * dsqrt(ths * ths - ddiv(dy_, s) * ddiv(dp, s));
-                if (stp_ > sty_) gamma = -gamma;
-                const double p = (gamma - dp) + th, q = ((gamma - dp) + gamma) + dy_, rr = ddiv(p, q);
-                stpf = stp_ + rr * (sty_ - stp_);
-            } else if (stp_ > stx_) stpf = stpmax;
-            else stpf = stpmin;
-        }
-        if (fp > fx_) {
-            sty_ = stp_; fy_ = fp; dy_ = dp;
-        } else {
-            if (sgnd < 0.0) { sty_ = stx_; fy_ = fx_; dy_ = dx_; }
-            stx_ = stp_; fx_ = fp; dx_ = dp;
-        }
-        stp_ = stpf;
+        dcstep_body(stx_, fx_, dx_, sty_, fy_, dy_, stp_, fp, dp, brackt_, stpmin, stpmax);
     }
 
     // dcsrch after the first call: 0 = evaluate at the new stp, 1 = line search finished (CONVERGENCE or WARNING)
@@ -812,6 +845,9 @@ struct Solver {
             else { cnstnd = true; iwhere[i] = (nbd[i] == 2 && u[i] - l[i] <= 0.0) ? 3 : 0; }
         }
         reset_memory();
+#ifdef T2FIT_HOSTSIM
+        brk_mask = 0; brk_iter = -1; brk_col = -1; stale_rows = 0;
+#endif
         itail = 0; nfree = N; nenter = 0; ileave = N;
         T2_ROLLED for (int i = 0; i < N; ++i) { index[i] = i; indx2[i] = i; }
         fold = dnorm = dtd = gd = gdold = stp = stpmx = sbgnrm = 0.0;
@@ -845,12 +881,15 @@ struct Solver {
                 T2_ROLLED for (int i = 0; i < N; ++i) z[i] = x[i];
                 wrk = updatd;
             } else {
-                if (!cauchy()) { reset_memory(); continue; }
+                if (!cauchy()) { note_break(1); reset_memory(); continue; }
                 wrk = freev();
             }
+#ifdef T2FIT_HOSTSIM
+            if (nfree == 0 && col != 0 && updatd) ++stale_rows;
+#endif
             if (nfree != 0 && col != 0) {
-                if (wrk && !formk()) { reset_memory(); continue; }
-                if (!subsm()) { reset_memory(); continue; }
+                if (wrk && !formk()) { note_break(2); reset_memory(); continue; }
+                if (!subsm()) { note_break(4); reset_memory(); continue; }
             }
             T2_ROLLED for (int i = 0; i < N; ++i) d[i] = z[i] - x[i];
             // lnsrlb, first entry
@@ -885,6 +924,7 @@ struct Solver {
             gdold = gd;
             if (gd >= 0.0) {                                  // not a descent direction
                 if (col == 0) { result = kAbnormal; return; }
+                note_break(16);
                 reset_memory();
                 continue;
             }
@@ -920,6 +960,7 @@ struct Solver {
                 T2_ROLLED for (int i = 0; i < N; ++i) { x[i] = t[i]; g[i] = r[i]; }
                 f = fold;
                 if (col == 0) { result = kAbnormal; return false; }
+                note_break(32);
                 reset_memory();
                 start_iteration();
                 return false;
@@ -949,6 +990,7 @@ struct Solver {
         if (dr <= kEpsMch * ddum) {
             updatd = false;                                   // skip the update (curvature condition fails)
         } else if (!update_pairs(rr, dr)) {
+            note_break(8);
             reset_memory();                                   // T not positive definite: refresh the memory
         }
         start_iteration();

@@ -1,0 +1,682 @@
+// L-BFGS-B for n <= 3 with the limited-memory matrix held as a DENSE n x n matrix: the same algorithm as t2fit_lbfgsb.cuh
+// (scipy.optimize.minimize(method="L-BFGS-B") as fit_voxel calls it, run_t2mapping.py:260-286), the same objectives in numpy
+// operation order, the same forward differences, line search and stopping tests -- but every product with
+//
+//     B = theta I - W M W'                      (W = [Y, theta S], M the 2m x 2m middle matrix of Byrd, Lu, Nocedal, Zhu 1995)
+//
+// is taken with the n x n matrix itself.  Byrd, Nocedal & Schnabel (1994, theorem 2.3) show that the compact form above IS
+// the result of the BFGS updates with the stored pairs (oldest first) applied to theta I, so with n <= 3:
+//
+//   * B is rebuilt from the <= 10 stored pairs after every accepted pair (theta changes with every pair): <= 10 rank-2
+//     updates of a 3 x 3 matrix, ~ 400 flops instead of the Cholesky factorizations of a 10 x 10 and a 20 x 20 matrix;
+//   * generalized Cauchy point: f' = (g + B (z - x))' d and f'' = d' B d on every segment of the projected path, directly;
+//   * subspace minimisation: B_FF d_F = -(g + B (xcp - x))_F over the free set F, a <= 3 x 3 Cholesky solve, then the
+//     v3.0 projection / backtracking step unchanged.
+//
+// State per voxel: the pairs (480 B) + ~40 scalars, against 10.9 KB of compact matrices; per iteration the optimiser core
+// costs a few hundred flops, so the run time is the objective evaluations (4 per gradient).
+//
+// What it is NOT: bit-for-bit the trajectory of scipy's arithmetic.  In exact arithmetic both forms walk the same path; in
+// floating point the compact matrices of an n <= 3 problem become numerically singular once more than n pairs are stored,
+// scipy's Cholesky factorizations then break down now and then and the memory is refreshed (a steepest-descent restart),
+// and with the reference's loose presets (ftol = gtol = 1e-2) the stopping point depends on the path.  The dense matrix
+// never breaks down.  Parity figures of both forms: DESIGN.md section 3b, tests/test_hostsim_dense.py.
+//
+// Plain C++ when T2FIT_HOSTSIM is defined (tests/hostsim).
+#pragma once
+#include "t2fit_lbfgsb.cuh"
+
+namespace t2fit {
+namespace lb {
+
+template <int N>
+struct DenseSolver {
+    // problem
+    double l[N], u[N];
+    int nbd[N];                 // 0 unbounded, 1 lower, 2 both, 3 upper
+    double ftol, pgtol;
+    int maxls;
+    bool cnstnd, boxed;
+    // iterate
+    double x[N], g[N], f;
+    double t[N], r[N], d[N], z[N];
+    int iwhere[N];
+    // limited memory: the pairs (circular, `head` = oldest) and the matrix they define
+    double ws[kM][N], wy[kM][N];
+    double B[N][N];
+    double theta;
+    int col, head, itail, iupdat;
+    bool want_dir;              // the driver calls start_iteration() (ONE call site: the routine is inlined)
+    bool updatd, stale;         // a pair was stored after the last direction; a stored pair never reached the K matrix (below)
+    // line search / bookkeeping
+    double fold, dnorm, dtd, gd, gdold, stp, stpmx, sbgnrm;
+    int iter, ifun, iback, nfgv;
+    bool brackt;
+    int stage;
+    double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
+    int result;
+
+    T2_HD void projgr() {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double gi = g[i];
+            if (nbd[i] != 0) {
+                if (gi < 0.0) { if (nbd[i] >= 2) gi = rmax(x[i] - u[i], gi); }
+                else { if (nbd[i] <= 2) gi = rmin(x[i] - l[i], gi); }
+            }
+            s = rmax(s, fabs(gi));
+        }
+        sbgnrm = s;
+    }
+
+    T2_HD void reset_memory() {
+        col = 0; head = 0; theta = 1.0; iupdat = 0; updatd = false; stale = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) B[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+
+#ifdef T2FIT_HOSTSIM
+    int brk_mask = 0, brk_iter = -1, brk_col = -1;            // test instrumentation (as in Solver)
+    void note_break(int bit) { if (!brk_mask) { brk_iter = iter; brk_col = col; } brk_mask |= bit; }
+#else
+    T2_HD void note_break(int) {}
+#endif
+
+    // B = theta I, then the BFGS update of every stored pair, oldest first
+    T2_HD void rebuild() {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) B[i][j] = (i == j) ? theta : 0.0;
+        T2_ROLLED for (int q = 0; q < col; ++q) {
+            const int pt = (head + q) % kM;
+            double s[N], y[N], bs[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) { s[i] = ws[pt][i]; y[i] = wy[pt][i]; }
+            double sbs = 0.0, ys = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double a = 0.0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) a += B[i][j] * s[j];
+                bs[i] = a; sbs += a * s[i]; ys += y[i] * s[i];
+            }
+            const double isbs = 1.0 / sbs, iys = 1.0 / ys;
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int j = i; j < N; ++j) {
+                    const double v = B[i][j] - bs[i] * bs[j] * isbs + y[i] * y[j] * iys;
+                    B[i][j] = v; B[j][i] = v;
+                }
+        }
+    }
+
+    // ---- generalized Cauchy point: z (= xcp), iwhere ------------------------------------------------------------
+    T2_HD void cauchy() {
+#pragma unroll
+        for (int i = 0; i < N; ++i) z[i] = x[i];
+        if (sbgnrm <= 0.0) return;
+        bool bnded = true, any_unbounded = false;
+        int nbreak = 0;
+        double dd[N], tt[N], zx[N];                               // search direction, breakpoints, z - x of the fixed variables
+        bool pending[N];
+        double f1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double neggi = -g[i];
+            double tl = 0.0, tu = 0.0;
+            pending[i] = false; tt[i] = 0.0; zx[i] = 0.0;
+            if (iwhere[i] != 3 && iwhere[i] != -1) {
+                if (nbd[i] <= 2) tl = x[i] - l[i];
+                if (nbd[i] >= 2) tu = u[i] - x[i];
+                const bool xlower = nbd[i] <= 2 && tl <= 0.0;
+                const bool xupper = nbd[i] >= 2 && tu <= 0.0;
+                iwhere[i] = 0;
+                if (xlower) { if (neggi <= 0.0) iwhere[i] = 1; }
+                else if (xupper) { if (neggi >= 0.0) iwhere[i] = 2; }
+                else if (fabs(neggi) <= 0.0) iwhere[i] = -3;
+            }
+            if (iwhere[i] != 0 && iwhere[i] != -1) {
+                dd[i] = 0.0;
+            } else {
+                dd[i] = neggi;
+                f1 -= neggi * neggi;
+                if (nbd[i] <= 2 && nbd[i] != 0 && neggi < 0.0) { tt[i] = ddiv(tl, -neggi); pending[i] = true; ++nbreak; }
+                else if (nbd[i] >= 2 && neggi > 0.0) { tt[i] = ddiv(tu, neggi); pending[i] = true; ++nbreak; }
+                else { any_unbounded = true; if (fabs(neggi) > 0.0) bnded = false; }
+            }
+        }
+        if (nbreak == 0 && !any_unbounded) return;              // d is the zero vector
+        const double f2_org = -theta * f1;
+        double f2 = quad(dd);
+        double dtm = ddiv(-f1, f2), tsum = 0.0, tj = 0.0;
+        bool all_fixed = false;
+        int nleft = nbreak;
+        while (nleft > 0) {
+            int ibp = -1;                                         // least of the remaining breakpoints (first one on ties)
+            double tbest = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) if (pending[i] && (ibp < 0 || tt[i] < tbest)) { ibp = i; tbest = tt[i]; }
+            const double tj0 = tj;
+            tj = tbest;
+            const double dt = tj - tj0;
+            if (dtm < dt) break;                                  // the minimiser lies within this segment
+            tsum += dt; --nleft;
+#pragma unroll
+            for (int i = 0; i < N; ++i) if (i == ibp) {           // (static indices: the state stays in registers)
+                pending[i] = false;
+                const double dibp = dd[i];
+                dd[i] = 0.0;
+                if (dibp > 0.0) { zx[i] = u[i] - x[i]; z[i] = u[i]; iwhere[i] = 2; }
+                else { zx[i] = l[i] - x[i]; z[i] = l[i]; iwhere[i] = 1; }
+            }
+            if (nleft == 0 && nbreak == N) { dtm = dt; all_fixed = true; break; }
+            // f' and f'' of the quadratic model on the next segment: (g + B (z - x))' d and d' B d
+            double zc[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) zc[i] = zx[i] + tsum * dd[i];
+            f1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double a = g[i];
+#pragma unroll
+                for (int j = 0; j < N; ++j) a += B[i][j] * zc[j];
+                f1 += a * dd[i];
+            }
+            f2 = rmax(kEpsMch * f2_org, quad(dd));
+            if (nleft > 0) { dtm = ddiv(-f1, f2); continue; }
+            if (bnded) { f1 = 0.0; f2 = 0.0; dtm = 0.0; }
+            else dtm = ddiv(-f1, f2);
+            break;
+        }
+        if (!all_fixed) {
+            if (dtm <= 0.0) dtm = 0.0;
+            tsum += dtm;
+#pragma unroll
+            for (int i = 0; i < N; ++i) z[i] += tsum * dd[i];
+        }
+    }
+
+    T2_HD double quad(const double* v) const {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) a += B[i][j] * v[j];
+            s += a * v[i];
+        }
+        return s;
+    }
+
+    // ---- subspace minimisation over the free variables at the Cauchy point; false = B_FF not positive definite ----
+    T2_HD bool subsm() {
+        // The free set F is NOT compacted: rows / columns of the other variables are replaced by those of the identity and
+        // their right-hand side by 0.  Every operation that touches them is x - 0 * y, x / 1 or sqrt(1), exact, so the
+        // factorization and the solves produce bit for bit what the compacted |F| x |F| system gives, with indices known at
+        // compile time (the state stays in registers).
+        bool fr[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) fr[i] = iwhere[i] <= 0;
+        // reduced gradient r = -Z'(g + B (xcp - x)) and the reduced matrix Z'BZ
+        double rr_[N], A[N][N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double sgn = g[i];
+#pragma unroll
+            for (int j = 0; j < N; ++j) sgn += B[i][j] * (z[j] - x[j]);
+            rr_[i] = fr[i] ? -sgn : 0.0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) A[i][j] = (fr[i] && fr[j]) ? B[i][j] : (i == j ? 1.0 : 0.0);
+        }
+        // Cholesky A = R'R (upper triangle), R'R d = r
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double sq = 0.0;
+#pragma unroll
+            for (int k = 0; k < j; ++k) {
+                double tt = A[k][j];
+#pragma unroll
+                for (int q = 0; q < k; ++q) tt -= A[q][k] * A[q][j];
+                tt = ddiv(tt, A[k][k]);
+                A[k][j] = tt;
+                sq += tt * tt;
+            }
+            sq = A[j][j] - sq;
+            if (!(sq > 0.0)) return false;
+            A[j][j] = dsqrt(sq);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double sq = rr_[j];
+#pragma unroll
+            for (int q = 0; q < j; ++q) sq -= A[q][j] * rr_[q];
+            rr_[j] = ddiv(sq, A[j][j]);
+        }
+#pragma unroll
+        for (int j = N - 1; j >= 0; --j) {
+            double sq = rr_[j];
+#pragma unroll
+            for (int q = j + 1; q < N; ++q) sq -= A[j][q] * rr_[q];
+            rr_[j] = ddiv(sq, A[j][j]);
+        }
+        // projection of the Newton point onto the box (v3.0), else backtrack along the Newton direction
+        double xp[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) xp[i] = z[i];
+        bool iword = false;
+#pragma unroll
+        for (int k = 0; k < N; ++k) if (fr[k]) {
+            const double dk = rr_[k], xk = z[k];
+            if (nbd[k] == 0) z[k] = xk + dk;
+            else if (nbd[k] == 1) { z[k] = rmax(l[k], xk + dk); if (z[k] == l[k]) iword = true; }
+            else if (nbd[k] == 2) { z[k] = rmin(u[k], rmax(l[k], xk + dk)); if (z[k] == l[k] || z[k] == u[k]) iword = true; }
+            else { z[k] = rmin(u[k], xk + dk); if (z[k] == u[k]) iword = true; }
+        }
+        if (!iword) return true;
+        double dd_p = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) dd_p += (z[i] - x[i]) * g[i];
+        if (dd_p > 0.0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) z[i] = xp[i];
+            double alpha = 1.0, temp1 = 1.0;
+            int ibd = -1;
+#pragma unroll
+            for (int k = 0; k < N; ++k) if (fr[k]) {
+                const double dk = rr_[k];
+                if (nbd[k] != 0) {
+                    if (dk < 0.0 && nbd[k] <= 2) {
+                        const double temp2 = l[k] - z[k];
+                        if (temp2 >= 0.0) temp1 = 0.0;
+                        else if (dk * alpha < temp2) temp1 = ddiv(temp2, dk);
+                    } else if (dk > 0.0 && nbd[k] >= 2) {
+                        const double temp2 = u[k] - z[k];
+                        if (temp2 <= 0.0) temp1 = 0.0;
+                        else if (dk * alpha > temp2) temp1 = ddiv(temp2, dk);
+                    }
+                    if (temp1 < alpha) { alpha = temp1; ibd = k; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < N; ++k) if (alpha < 1.0 && k == ibd) {
+                const double dk = rr_[k];
+                if (dk > 0.0) { z[k] = u[k]; rr_[k] = 0.0; }
+                else if (dk < 0.0) { z[k] = l[k]; rr_[k] = 0.0; }
+            }
+#pragma unroll
+            for (int k = 0; k < N; ++k) if (fr[k]) z[k] += alpha * rr_[k];
+        }
+        return true;
+    }
+
+    // ---- new correction pair (matupd), theta, and the matrix they define ----
+    T2_HD void update_pairs(double rr, double dr) {
+        updatd = true;
+        ++iupdat;
+        if (iupdat <= kM) { col = iupdat; itail = (head + iupdat - 1) % kM; }
+        else { itail = (itail + 1) % kM; head = (head + 1) % kM; }
+#pragma unroll
+        for (int i = 0; i < N; ++i) { ws[itail][i] = d[i]; wy[itail][i] = r[i]; }
+        theta = ddiv(rr, dr);
+        rebuild();
+    }
+
+    // dcsrch after the first call: 0 = evaluate at the new stp, 1 = line search finished (CONVERGENCE or WARNING)
+    T2_HD int dcsrch_next(double fv, double gv) {
+        const double ls_gtol = 0.9, ls_xtol = 0.1, stpmin = 0.0, stpmax = stpmx;
+        const double ftest = finit + stp * gtest;
+        if (stage == 1 && fv <= ftest && gv >= 0.0) stage = 2;
+        bool fin = false;
+        if (brackt && (stp <= stmin || stp >= stmax)) fin = true;                 // rounding errors prevent progress
+        if (brackt && stmax - stmin <= ls_xtol * stmax) fin = true;               // xtol test satisfied
+        if (stp == stpmax && fv <= ftest && gv <= gtest) fin = true;              // stp = stpmax
+        if (stp == stpmin && (fv > ftest || gv >= gtest)) fin = true;             // stp = stpmin
+        if (fv <= ftest && fabs(gv) <= ls_gtol * (-ginit)) fin = true;            // strong Wolfe conditions hold
+        if (fin) return 1;
+        // the modified function of stage 1 (psi = f - gtest stp) or f itself: ONE call of the safeguarded step
+        const bool mod = stage == 1 && fv <= fx && fv > ftest;
+        const double sh = mod ? gtest : 0.0;
+        double fxm = mod ? fx - stx * gtest : fx, fym = mod ? fy - sty * gtest : fy;
+        double gxm = gx - sh, gym = gy - sh;
+        const double fm = mod ? fv - stp * gtest : fv, gm = gv - sh;
+        dcstep_body(stx, fxm, gxm, sty, fym, gym, stp, fm, gm, brackt, stmin, stmax);
+        fx = mod ? fxm + stx * gtest : fxm; fy = mod ? fym + sty * gtest : fym;
+        gx = gxm + sh; gy = gym + sh;
+        if (brackt) {
+            if (fabs(sty - stx) >= 0.66 * width1) stp = stx + 0.5 * (sty - stx);
+            width1 = width;
+            width = fabs(sty - stx);
+        }
+        if (brackt) { stmin = rmin(stx, sty); stmax = rmax(stx, sty); }
+        else { stmin = stp + 1.1 * (stp - stx); stmax = stp + 4.0 * (stp - stx); }
+        stp = rmax(stp, stpmin);
+        stp = rmin(stp, stpmax);
+        if ((brackt && (stp <= stmin || stp >= stmax)) || (brackt && stmax - stmin <= ls_xtol * stmax)) stp = stx;
+        return 0;
+    }
+
+    T2_HD void setup(const double* x0, const double* lo, const double* hi, double ftol_, double pgtol_, int maxls_) {
+        ftol = ftol_; pgtol = pgtol_; maxls = maxls_;
+        cnstnd = false; boxed = true;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool hl = lo[i] > -INFINITY, hu = hi[i] < INFINITY;
+            nbd[i] = hl ? (hu ? 2 : 1) : (hu ? 3 : 0);
+            l[i] = hl ? lo[i] : 0.0; u[i] = hu ? hi[i] : 0.0;
+            double xi = x0[i];
+            if (hl) xi = rmax(xi, l[i]);                              // x0 = np.clip(x0, lb, ub)
+            if (hu) xi = rmin(xi, u[i]);
+            x[i] = xi;
+            if (nbd[i] != 2) boxed = false;
+            if (nbd[i] == 0) iwhere[i] = -1;
+            else { cnstnd = true; iwhere[i] = (nbd[i] == 2 && u[i] - l[i] <= 0.0) ? 3 : 0; }
+        }
+        reset_memory();
+#ifdef T2FIT_HOSTSIM
+        brk_mask = 0; brk_iter = -1; brk_col = -1;
+#endif
+        itail = 0;
+        fold = dnorm = dtd = gd = gdold = stp = stpmx = sbgnrm = 0.0;
+        iter = ifun = iback = nfgv = 0;
+        result = kRunning; want_dir = false;
+    }
+
+    T2_HD void begin(double f0, const double* g0) {
+        f = f0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) g[i] = g0[i];
+        nfgv = 1;
+        projgr();
+        if (sbgnrm <= pgtol) { result = kConvPg; return; }
+        want_dir = true;
+    }
+
+    // new search direction and the first trial point of its line search
+    T2_HD void start_iteration() {
+        for (;;) {
+            bool any_free = true;
+            if (!cnstnd && col > 0) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) z[i] = x[i];
+            } else {
+                cauchy();
+                any_free = false;
+#pragma unroll
+                for (int i = 0; i < N; ++i) any_free = any_free || (iwhere[i] <= 0);
+            }
+            // The one breakdown of the published code that is structural, not rounding: formk adds only the NEWEST pair's row
+            // to its incrementally kept K matrix, and it is skipped while no variable is free at the Cauchy point.  A pair
+            // stored during such an iteration never reaches K; when variables become free again the factorization of the
+            // incomplete matrix fails and the memory is refreshed (a steepest-descent restart).  89 of 89 such events on the
+            // golden fixtures end that way in scipy, and they are ALL the breakdowns seen there, so this form restarts too.
+            if (!any_free && col != 0 && updatd) stale = true;
+            if (any_free && col != 0) {
+                if (stale) { note_break(2); reset_memory(); continue; }
+                if (!subsm()) { note_break(4); reset_memory(); continue; }
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) d[i] = z[i] - x[i];
+            dtd = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) dtd += d[i] * d[i];
+            dnorm = dsqrt(dtd);
+            stpmx = 1e10;
+            if (cnstnd) {
+                if (iter == 0) stpmx = 1.0;
+                else {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const double a1 = d[i];
+                        if (nbd[i] != 0) {
+                            if (a1 < 0.0 && nbd[i] <= 2) {
+                                const double a2 = l[i] - x[i];
+                                if (a2 >= 0.0) stpmx = 0.0;
+                                else if (a1 * stpmx < a2) stpmx = ddiv(a2, a1);
+                            } else if (a1 > 0.0 && nbd[i] >= 2) {
+                                const double a2 = u[i] - x[i];
+                                if (a2 <= 0.0) stpmx = 0.0;
+                                else if (a1 * stpmx > a2) stpmx = ddiv(a2, a1);
+                            }
+                        }
+                    }
+                }
+            }
+            stp = (iter == 0 && !boxed) ? rmin(ddiv(1.0, dnorm), stpmx) : 1.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { t[i] = x[i]; r[i] = g[i]; }
+            fold = f; ifun = 0; iback = 0;
+            gd = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) gd += g[i] * d[i];
+            gdold = gd;
+            if (gd >= 0.0) {                                  // not a descent direction
+                if (col == 0) { result = kAbnormal; return; }
+                note_break(16);
+                reset_memory();
+                continue;
+            }
+            brackt = false; stage = 1; finit = f; ginit = gd; gtest = 1e-3 * ginit;
+            width = stpmx - 0.0; width1 = width * 2.0;
+            stx = 0.0; fx = finit; gx = ginit; sty = 0.0; fy = finit; gy = ginit;
+            stmin = 0.0; stmax = stp + 4.0 * stp;
+            ifun = 1; ++nfgv; iback = 0;
+            trial_point();
+            return;
+        }
+    }
+
+    T2_HD void trial_point() {
+        if (stp == 1.0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) x[i] = z[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) x[i] = stp * d[i] + t[i];
+        }
+    }
+
+    // f, g at the trial point x have been evaluated.  Returns true when a NEW ITERATE was accepted.
+    T2_HD bool advance(double fv, const double* gv) {
+        f = fv;
+        gd = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { g[i] = gv[i]; gd += g[i] * d[i]; }
+        if (dcsrch_next(f, gd) == 0) {
+            ++ifun; ++nfgv; iback = ifun - 1;
+            if (iback >= maxls) {                             // line search gave up: back to the start of it
+#pragma unroll
+                for (int i = 0; i < N; ++i) { x[i] = t[i]; g[i] = r[i]; }
+                f = fold;
+                if (col == 0) { result = kAbnormal; return false; }
+                note_break(32);
+                reset_memory();
+                want_dir = true;
+                return false;
+            }
+            trial_point();
+            return false;
+        }
+        ++iter;
+        projgr();
+        return true;
+    }
+
+    T2_HD void continue_after_iterate() {
+        if (sbgnrm <= pgtol) { result = kConvPg; return; }
+        const double ddum0 = rmax(fabs(fold), rmax(fabs(f), 1.0));
+        if ((fold - f) <= ftol * ddum0) { result = kConvF; return; }
+        double rr = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { r[i] = g[i] - r[i]; rr += r[i] * r[i]; }
+        double dr, ddum;
+        if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; }
+        else {
+            dr = (gd - gdold) * stp;
+#pragma unroll
+            for (int i = 0; i < N; ++i) d[i] *= stp;
+            ddum = -gdold * stp;
+        }
+        if (dr <= kEpsMch * ddum) updatd = false;             // skip the update (curvature condition fails)
+        else update_pairs(rr, dr);
+        want_dir = true;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// One voxel through the dense form: fit_voxel's preamble (run_t2mapping.py:237-245), scipy's fun_and_grad per pass, what
+// fit_voxel returns -- the same contract as VoxelRun (t2fit_lbfgsb.cuh), force-inlined so that the state stays in registers.
+// Every larger routine of the solver has exactly one call site in pass().
+// ---------------------------------------------------------------------------------------------
+template <int OBJ>
+struct DenseRun {
+    static constexpr int N = (OBJ == 0) ? 2 : 3;
+    DenseSolver<N> s;
+    float y[kMaxEcho];
+    double xprev[N];
+    float* trace_f;
+    float* trace_step;
+    int trace_cap, tl;
+    int nit, nfev, status;
+    bool have_prev, started, active;
+
+    T2_HD void start(const float* yraw, const LbConsts& c, float* tf, float* ts, int tcap) {
+        const int E = c.n_echo;
+        bool finite = true;
+        float ymax = yraw[0];
+        T2_ROLLED for (int e = 0; e < E; ++e) {
+            y[e] = yraw[e];
+            finite = finite && ((yraw[e] - yraw[e]) == 0.0f);
+            ymax = yraw[e] > ymax ? yraw[e] : ymax;
+        }
+        if (c.norm) {                                         // float32 / float32 (:237-238)
+            T2_ROLLED for (int e = 0; e < E; ++e) { y[e] = yraw[e] / ymax; finite = finite && ((y[e] - y[e]) == 0.0f); }
+        }
+        double lo[3], hi[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { lo[i] = c.lb[i]; hi[i] = c.ub[i]; }
+        if (c.no_prior) lo[0] = (double)yraw[0];              // :243-245 (upper bound and T2 box are in c)
+        status = kOk;
+        if (c.no_prior && (yraw[0] > (float)hi[0])) status = kBadBounds;   // scipy: "An upper bound is less than ..."
+        else if (!finite) status = kNonFinite;
+        if (OBJ == 2 && status == kOk) {                      // rician: log(signal) needs signal > 0
+            T2_ROLLED for (int e = 0; e < E; ++e) if (!(y[e] > 0.0f)) status = kNonFinite;
+        }
+        s.setup(c.x0, lo, hi, c.ftol, c.pgtol, c.maxls);
+        nit = 0; nfev = 0; tl = 0;
+        have_prev = false; started = false;
+        trace_f = tf; trace_step = ts; trace_cap = tcap;
+        active = status == kOk;
+    }
+
+    // scipy's approx_derivative step for variable i (absolute step, sign flip at a bound); the box as the solver holds it
+    T2_HD double fd_h(int i, double h) const {
+        const double lo = (s.nbd[i] == 1 || s.nbd[i] == 2) ? s.l[i] : -INFINITY, hi = s.nbd[i] >= 2 ? s.u[i] : INFINITY;
+        const double lower = s.x[i] - lo, upper = hi - s.x[i];
+        const double xt = s.x[i] + h;
+        const bool violated = (xt < lo) || (xt > hi);
+        const bool fitting = fabs(h) <= rmax(lower, upper);
+        if (violated && fitting) h = -h;
+        if (!fitting) h = (upper >= lower) ? upper : -lower;
+        return h;
+    }
+
+    T2_HD void pass(const LbConsts& c) {
+        const int E = c.n_echo;
+        double fv, gv[N];
+#ifdef T2FIT_HOSTSIM
+        if (c.fd_step < 0.0) {                                // test hook: analytic gradient (as VoxelRun)
+            fv = objective<OBJ>(s.x, y, c);
+            for (int i = 0; i < N; ++i) gv[i] = 0.0;
+            for (int e = 0; e < E; ++e) {
+                if (OBJ == 0) {
+                    const double u = exp(-c.te[e] / s.x[1]), m = s.x[0] * u, rr = (double)y[e] - m;
+                    gv[0] += -2.0 * rr * u / E;
+                    gv[1] += -2.0 * rr * m * c.te[e] / (s.x[1] * s.x[1]) / E;
+                } else if (OBJ == 1) {
+                    const double u2 = exp(-2.0 * c.te[e] / s.x[1]), m = sqrt(s.x[0] * s.x[0] * u2 + s.x[2 % N] * s.x[2 % N]);
+                    const double rr = (double)y[e] - m;
+                    gv[0] += -2.0 * rr * (s.x[0] * u2 / m) / E;
+                    gv[1] += -2.0 * rr * (s.x[0] * s.x[0] * u2 * c.te[e] / (s.x[1] * s.x[1]) / m) / E;
+                    gv[2 % N] += -2.0 * rr * (s.x[2 % N] / m) / E;
+                }
+            }
+        } else
+#endif
+        {
+            // f(x) and the N forward differences: the points x + h e_k and x + h e_sigma have the exponentials of x (same
+            // T2), so 2 exponentials per echo instead of N + 1; every value is bit for bit what objective<OBJ>() returns there
+            double u[kMaxEcho], v[kMaxEcho], xt[N];
+            T2_ROLLED for (int e = 0; e < E; ++e) { u[e] = objective_expo<OBJ>(s.x[1], c.te[e]); v[e] = objective_term_u<OBJ>(s.x, y[e], u[e]); }
+            fv = objective_reduce<OBJ>(v, E);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) xt[j] = s.x[j];
+                xt[i] = s.x[i] + fd_h(i, c.fd_step);
+                if (i == 1) { T2_ROLLED for (int e = 0; e < E; ++e) v[e] = objective_term_u<OBJ>(xt, y[e], objective_expo<OBJ>(xt[1], c.te[e])); }
+                else { T2_ROLLED for (int e = 0; e < E; ++e) v[e] = objective_term_u<OBJ>(xt, y[e], u[e]); }
+                gv[i] = ddiv(objective_reduce<OBJ>(v, E) - fv, xt[i] - s.x[i]);
+            }
+        }
+        nfev += N + 1;
+        if (!started) {
+            if (!(fv - fv == 0.0)) {                          // objective not finite at the start point: scipy ends ABNORMAL there
+                s.f = fv; s.result = kAbnormal; active = false;
+                return;
+            }
+            started = true;
+            s.begin(fv, gv);
+        } else if (s.advance(fv, gv)) {
+            ++nit;                                            // scipy: n_iterations += 1; callback(x)
+            if (tl < trace_cap) {
+                double st = NAN;
+                if (have_prev) {
+                    st = 0.0;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) st += (s.x[i] - xprev[i]) * (s.x[i] - xprev[i]);
+                    st = sqrt(st);
+                }
+                if (trace_f) trace_f[tl] = (float)s.f;
+                if (trace_step) trace_step[tl] = (float)st;
+            }
+            ++tl;
+#pragma unroll
+            for (int i = 0; i < N; ++i) xprev[i] = s.x[i];
+            have_prev = true;
+            if (nit >= c.maxiter) s.result = kMaxIter;
+            else if (nfev > c.maxfun) s.result = kMaxFun;
+            else s.continue_after_iterate();
+        }
+        if (s.result == kRunning && s.want_dir) { s.want_dir = false; s.start_iteration(); }
+        if (s.result != kRunning) active = false;
+    }
+
+    T2_HD LbVoxel finish() const {
+        LbVoxel out;
+#pragma unroll
+        for (int i = 0; i < N; ++i) out.x[i] = s.x[i];
+        if (N < 3) out.x[2] = 0.0;
+        out.fun = s.f;
+        out.nit = nit;
+        out.nfev = nfev;
+        out.result = s.result;
+        out.trace_len = tl < trace_cap ? tl : trace_cap;
+        int st = status;
+        if (st == kOk) {
+            if (s.result == kAbnormal || s.result == kMaxIter || s.result == kMaxFun) st = kNotConverged;
+        } else {
+            out.fun = NAN; out.nit = 0;
+            if (st == kBadBounds) { out.x[0] = out.x[1] = out.x[2] = NAN; }
+        }
+        out.status = st;
+        return out;
+    }
+};
+
+}  // namespace lb
+}  // namespace t2fit

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libt2fit_hostsim.so")
 SRC = os.path.join(HERE, "hostsim.cpp")
 DEPS = [SRC] + [os.path.join(HERE, "..", "..", "fetal_t2mapping_b200", "csrc", f)
-                for f in ("t2fit_core.cuh", "t2fit_consts.h", "t2fit_lbfgsb.cuh", "t2fit_lbfgsb_coop.cuh", "t2fit_i0e_coeffs.h")] + \
+                for f in ("t2fit_core.cuh", "t2fit_consts.h", "t2fit_lbfgsb.cuh", "t2fit_lbfgsb_coop.cuh", "t2fit_lbfgsb_dense.cuh", "t2fit_i0e_coeffs.h")] + \
     [os.path.join(HERE, "lane_emu.h")] + [os.path.join(HERE, "..", "..", "include", "t2fit.h")]
 
 
@@ -42,6 +42,7 @@ def lib(strict=False):
         l.hostsim_last_error.restype = C.c_char_p
         l.hostsim_lbfgsb.restype = C.c_int
         l.hostsim_lbfgsb_coop.restype = C.c_int
+        l.hostsim_lbfgsb_dense.restype = C.c_int
         l.hostsim_i0e.restype = C.c_double
         l.hostsim_i0e.argtypes = [C.c_double]
         _libs[strict] = l
@@ -94,7 +95,7 @@ def fit(rows, te, fit, x0, bounds, prior, norm=False, use_double=False, **kw):
 
 
 def lbfgsb(rows, te, fit, x0, bounds, prior, norm=False, options=None, trace_cap=0, tol=0.0, strict=False, coop_lanes=0,
-           reverse=False):
+           reverse=False, dense=False):
     """The reference-faithful solver compiled for the host: the serial form (csrc/t2fit_lbfgsb.cuh) or, with
     ``coop_lanes`` = 4 / 8 / 16 / 32, the cooperative form (csrc/t2fit_lbfgsb_coop.cuh) on the lane emulator."""
     p, keep = make_problem(rows, te, fit, x0, bounds, prior, norm, options=options or {}, tol=tol)
@@ -108,7 +109,9 @@ def lbfgsb(rows, te, fit, x0, bounds, prior, norm=False, options=None, trace_cap
     args = (vp(out["x"]), vp(out["fun"]), vp(out["nit"]), vp(out["nfev"]), vp(out["status"]), vp(out["result"]),
             vp(tf) if trace_cap else None, vp(ts) if trace_cap else None, vp(tl), C.c_int(trace_cap))
     L = lib(strict)
-    if coop_lanes:
+    if dense:
+        rc = L.hostsim_lbfgsb_dense(C.byref(p), *args)
+    elif coop_lanes:
         rc = L.hostsim_lbfgsb_coop(C.byref(p), C.c_int(coop_lanes), C.c_int(int(reverse)), *args)
     else:
         rc = L.hostsim_lbfgsb(C.byref(p), *args)

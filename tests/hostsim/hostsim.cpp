@@ -8,6 +8,7 @@
 #define T2FIT_HOSTSIM 1
 #include "../../fetal_t2mapping_b200/csrc/t2fit_consts.h"
 #include "../../fetal_t2mapping_b200/csrc/t2fit_lbfgsb_coop.cuh"
+#include "../../fetal_t2mapping_b200/csrc/t2fit_lbfgsb_dense.cuh"
 
 #include <string.h>
 #include <stdio.h>
@@ -63,19 +64,23 @@ extern "C" int hostsim_fit(const t2fit_problem* p, int use_double, float* k, flo
 // ------------------------------------------------------------------------------------------------
 // reference-faithful solver (t2fit_lbfgsb.cuh) on the host: checked against scipy's L-BFGS-B itself
 // ------------------------------------------------------------------------------------------------
-template <int OBJ>
+template <int OBJ, class Run = lb::VoxelRun<OBJ>>
 static int dispatch_lb(int n_echo, const float* rows, int64_t m, const lb::LbConsts& c, double* x, double* fun, int32_t* nit,
                        int32_t* nfev, uint8_t* status, int32_t* result, float* trace_f, float* trace_step, int32_t* trace_len,
                        int trace_cap) {
     for (int64_t i = 0; i < m; ++i) {
-        lb::VoxelRun<OBJ> run;
+        Run run;
         memset((void*)&run, 0xA5, sizeof(run));            // stale memory of the previous voxel: nothing may depend on it
         run.start(rows + i * n_echo, c, trace_f ? trace_f + i * trace_cap : nullptr,
                   trace_step ? trace_step + i * trace_cap : nullptr, (trace_f || trace_step) ? trace_cap : 0);
         while (run.active) run.pass(c);
         const lb::LbVoxel v = run.finish();
         x[3 * i] = v.x[0]; x[3 * i + 1] = v.x[1]; x[3 * i + 2] = v.x[2];
-        fun[i] = v.fun; nit[i] = v.nit; nfev[i] = v.nfev; status[i] = (uint8_t)v.status; result[i] = v.result;
+        fun[i] = v.fun; nit[i] = v.nit; nfev[i] = v.nfev; status[i] = (uint8_t)v.status;
+        // result code in the low byte; instrumentation above it: first breakdown (mask << 8, iteration << 16, pairs << 24)
+        // (HOSTSIM_BRK=1 only)
+        result[i] = v.result;
+        if (getenv("HOSTSIM_BRK")) result[i] |= (run.s.brk_mask << 8) | ((run.s.brk_iter & 0xff) << 16) | ((run.s.brk_col & 0x7f) << 24);
         if (trace_len) trace_len[i] = v.trace_len;
     }
     return 0;
@@ -91,6 +96,20 @@ extern "C" int hostsim_lbfgsb(const t2fit_problem* p, double* x, double* fun, in
         case T2FIT_MODEL_GAUSSIAN: return dispatch_lb<0>(p->n_echo, p->echoes, p->n_fit, c, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
         case T2FIT_MODEL_GAUSSIAN_RICIAN: return dispatch_lb<1>(p->n_echo, p->echoes, p->n_fit, c, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
         default: return dispatch_lb<2>(p->n_echo, p->echoes, p->n_fit, c, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+    }
+}
+
+// the dense-matrix form of the same optimiser (csrc/t2fit_lbfgsb_dense.cuh)
+extern "C" int hostsim_lbfgsb_dense(const t2fit_problem* p, double* x, double* fun, int32_t* nit, int32_t* nfev, uint8_t* status,
+                                    int32_t* result, float* trace_f, float* trace_step, int32_t* trace_len, int trace_cap) {
+    lb::LbConsts c;
+    memset(&c, 0, sizeof(c));
+    int rc = make_lb_consts(*p, c, g_err);
+    if (rc) return rc;
+    switch (p->model) {
+        case T2FIT_MODEL_GAUSSIAN: return dispatch_lb<0, lb::DenseRun<0>>(p->n_echo, p->echoes, p->n_fit, c, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+        case T2FIT_MODEL_GAUSSIAN_RICIAN: return dispatch_lb<1, lb::DenseRun<1>>(p->n_echo, p->echoes, p->n_fit, c, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
+        default: return dispatch_lb<2, lb::DenseRun<2>>(p->n_echo, p->echoes, p->n_fit, c, x, fun, nit, nfev, status, result, trace_f, trace_step, trace_len, trace_cap);
     }
 }
 

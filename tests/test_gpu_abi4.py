@@ -39,7 +39,7 @@ def test_status_counts_do_not_leak_between_calls(gpu_lib):
     assert maps[0].shape == mask.shape
 
 
-@pytest.mark.parametrize("solver", ["fast", "lbfgsb"])
+@pytest.mark.parametrize("solver", ["fast", "lbfgsb", "lbfgsb_dense"])
 def test_device_index_vector_is_range_checked(gpu_lib, solver):
     """A caller-supplied device index tensor with entries outside [0, n_vox): IndexError, as numpy's fancy indexing in the
     reference (:237), instead of out-of-bounds reads / writes."""
@@ -56,7 +56,7 @@ def test_device_index_vector_is_range_checked(gpu_lib, solver):
     assert int((r.status != 0).sum()) == 0
 
 
-@pytest.mark.parametrize("fit,solver", [("gaussian", "fast"), ("gaussian_rician", "fast"), ("gaussian_rician", "lbfgsb")])
+@pytest.mark.parametrize("fit,solver", [("gaussian", "fast"), ("gaussian_rician", "fast"), ("gaussian_rician", "lbfgsb"), ("gaussian_rician", "lbfgsb_dense")])
 def test_int32_mask_indices_equal_int64(gpu_lib, fit, solver):
     """mask_indices as int32 (half the index bytes over PCIe): device tensors, pageable numpy (staged) and page-locked
     numpy (the kernel reads the index vector in place) give exactly what int64 gives."""

@@ -1,0 +1,106 @@
+"""The dense-matrix form of the reference's optimiser (csrc/t2fit_lbfgsb_dense.cuh: L-BFGS-B with the limited-memory matrix
+held as an n x n matrix, n <= 3) compiled for the host and held to the SAME parity thresholds as the compact form
+(tests/test_hostsim_lbfgsb.py): the golden fixtures of the unmodified reference, judged against the reference's own
+reproducibility floor (tests/golden/make_jitter.py)."""
+import warnings
+
+import numpy as np
+import pytest
+from scipy.optimize import minimize
+
+from tests import hostsim
+from tests.conftest import assert_lbfgsb_parity, fit_params_of, lbfgsb_parity_report, load_golden
+from tests.test_hostsim_lbfgsb import _fg_floor, _fg_mono
+
+FIXTURES = ["c1_gaussian_noprior", "c1_gaussian_prior", "c2_gaussian_noprior", "c2_gaussian_hf_prior", "c4_gaussian_noprior",
+            "c3_floor_noprior", "c3_floor_prior", "c5_floor_noprior", "c3_rician_prior", "norm_gaussian",
+            "cli3_gaussian_lf_noprior", "cli3_floor_hf_prior", "cli3_rician_hf_prior", "cli3_rician_lf_noprior"]
+
+
+def _run(g, dense, **kw):
+    fp = fit_params_of(g)
+    return hostsim.lbfgsb(g["rows"], g["te"], g["fit"], g["x0"], g["bounds"], g["prior"], g["norm"], options=fp["options"],
+                          dense=dense, **kw)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_dense_form_reproduces_reference_fixtures(name):
+    g = load_golden(name)
+    o = _run(g, True, trace_cap=64)
+    rep = lbfgsb_parity_report(o["x"][:, 1], o["nit"], o["status"] == 0, g)
+    assert_lbfgsb_parity(rep, name + " (dense)")
+    nt = g["trace_len"].shape[0]
+    for i in range(nt):                                                  # callback traces, as for the compact form
+        if o["nit"][i] != g["ref_nit"][i] or not g["reproducible"][i]:
+            continue
+        n = int(g["trace_len"][i])
+        assert o["trace_len"][i] == n
+        assert np.allclose(o["trace_f"][i, :min(n, 3)], g["trace_f"][i, :min(n, 3)], rtol=5e-3)
+        assert np.allclose(o["trace_f"][i, n - 1], g["trace_f"][i, n - 1], rtol=1e-2)
+
+
+@pytest.mark.parametrize("name", ["c3_floor_noprior", "c5_floor_noprior", "c3_floor_prior"])
+def test_dense_form_restarts_where_the_compact_form_breaks_down(name, monkeypatch):
+    """Every factorization breakdown of the compact form on the fixtures is the structural one (a pair stored while no
+    variable was free never reaches the K matrix); the dense form refreshes its memory at the same event.  The two runs
+    differ in rounding, so a handful of voxels may reach the event in one run only."""
+    g = load_golden(name)
+    monkeypatch.setenv("HOSTSIM_BRK", "1")        # the host build reports the first breakdown above the result code
+    oc, od = _run(g, False), _run(g, True)
+    bc, bd = ((oc["result"] >> 8) & 0xff), ((od["result"] >> 8) & 0xff)
+    assert not np.any(bc & ~2 & 0x0f), "compact form: a breakdown that is not formk's"
+    assert not np.any(bd & ~2 & 0x0f)
+    bc, bd = (bc & 2) > 0, (bd & 2) > 0
+    if name == "c3_floor_prior":
+        assert bc.sum() == 0 and bd.sum() == 0
+    else:
+        assert bc.sum() >= 30
+        assert (bc & bd).sum() >= 0.9 * max(bc.sum(), bd.sum())
+    assert np.mean((oc["result"] & 0xff) == (od["result"] & 0xff)) >= 0.98      # same stopping test fired
+
+
+@pytest.mark.parametrize("name,m", [("c2_gaussian_noprior", 150), ("c3_floor_prior", 100)])
+def test_dense_core_follows_scipy_with_an_analytic_gradient(name, m):
+    """No finite-difference noise: the dense form must walk scipy's path up to rounding in the quasi-Newton products
+    (looser than the compact form's 1e-8, which repeats scipy's operations)."""
+    g = load_golden(name)
+    fp = fit_params_of(g)
+    fg = _fg_mono if g["fit"] == "gaussian" else _fg_floor
+    rows, te = g["rows"][:m], g["te"].astype(float)
+    sx, snit = [], []
+    for i in range(m):
+        bounds = list(fp["param_bounds"])
+        if not g["prior"]:
+            bounds[0] = (float(rows[i, 0]), 10000.0); bounds[1] = (10.0, 2000.0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r = minimize(fg, fp["initial_guess"], args=(te, rows[i].astype(float)), method="L-BFGS-B", bounds=bounds,
+                         options={k: v for k, v in fp["options"].items() if k != "disp"}, jac=True)
+        sx.append(r.x); snit.append(r.nit)
+    sx, snit = np.array(sx), np.array(snit)
+    o = hostsim.lbfgsb(rows, te, g["fit"], fp["initial_guess"], fp["param_bounds"], g["prior"], options=fp["options"], tol=-1.0,
+                       dense=True)
+    n = sx.shape[1]
+    rel = np.abs(o["x"][:, :n] - sx).max(axis=1) / np.abs(sx).max(axis=1)
+    print(name, "nit equal", np.mean(o["nit"] == snit), "within 1e-6", np.mean(rel <= 1e-6), "median", np.median(rel))
+    assert np.mean(o["nit"] == snit) >= 0.95
+    assert np.mean(rel <= 1e-6) >= 0.95
+    assert np.median(rel) <= 1e-9
+
+
+@pytest.mark.parametrize("fit", ["gaussian", "gaussian_rician"])
+@pytest.mark.parametrize("prior", [True, False], ids=["prior", "noprior"])
+def test_dense_edge_cases(fit, prior):
+    g = load_golden(f"edge_{fit}_{'prior' if prior else 'noprior'}")
+    o = _run(g, True)
+    raises = np.array([len(str(e)) > 0 for e in g["ref_error"]])
+    assert np.array_equal(o["status"] == 3, raises)                      # scipy's ValueError rows
+    keep = ~raises
+    assert np.array_equal((o["status"] == 0)[keep], g["ref_success"][keep])
+    failed = keep & ~g["ref_success"]
+    n = g["ref_params"].shape[1]
+    assert np.allclose(o["x"][failed, :n], g["ref_params"][failed])      # clipped x0
+    oc = _run(g, False)                                                  # and the compact form's answers on the rest
+    ok = keep & g["ref_success"] & g["converged"] & (g["ref_params"][:, 1] > 10.0)
+    rel = np.abs(o["x"][ok, 1] - oc["x"][ok, 1]) / oc["x"][ok, 1]
+    assert np.mean(rel <= 1e-3) >= 0.75 and rel.max() <= 5e-2

@@ -1,5 +1,5 @@
 """A/B of the reference-faithful (L-BFGS-B) kernels, device-resident: thread-per-voxel vs cooperative (8 / 16 / 32 lanes per
-voxel).  python tools/lb_bench.py [c2] [c3] [c3r] [c5] [--kernels thread,coop8,...] [--scale S]"""
+voxel) vs the dense-matrix form (dense).  python tools/lb_bench.py [c2] [c3] [c3r] [c5] [--kernels thread,coop8,...] [--scale S]"""
 import os
 import sys
 import time
@@ -53,19 +53,22 @@ def main():
         m = y.shape[0] if idx is None else idx.numel()
         ref = None
         for k in kernels:
-            os.environ["T2FIT_LB_KERNEL"] = k
+            os.environ["T2FIT_LB_KERNEL"] = k if k != "dense" else "thread"
+            solver = "lbfgsb_dense" if k == "dense" else "lbfgsb"
             best = 1e30
             for _ in range(2):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                r = t2.fit_voxels_batch(y, idx, te, fit, fp, False, False, solver="lbfgsb", check_bounds=False)
+                r = t2.fit_voxels_batch(y, idx, te, fit, fp, False, False, solver=solver, check_bounds=False)
                 torch.cuda.synchronize()
                 best = min(best, time.perf_counter() - t0)
             same = ""
             if ref is None:
                 ref = r
             else:
-                same = f", identical to {kernels[0]}: {float(((r.t2 == ref.t2) & (r.nit == ref.nit)).float().mean()):.5f}"
+                rel = ((r.t2 - ref.t2).abs() / ref.t2.abs())
+                same = (f", identical to {kernels[0]}: {float(((r.t2 == ref.t2) & (r.nit == ref.nit)).float().mean()):.5f}, T2 within 1e-3: "
+                        f"{float((rel <= 1e-3).float().mean()):.5f}, nit equal {float((r.nit == ref.nit).float().mean()):.5f}")
             print(f"{name} scale {sc} M={m} E={len(te)} {fit} kernel={k}: {best*1e3:.1f} ms -> {m/best:.3e} fits/s, mean nit "
                   f"{r.nit.float().mean().item():.2f}, failed {(r.status != 0).sum().item()}{same}", flush=True)
         os.environ.pop("T2FIT_LB_KERNEL", None)

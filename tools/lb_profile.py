@@ -1,4 +1,4 @@
-"""One launch of the L-BFGS-B kernel for ncu:  python tools/lb_profile.py [cfg] [scale] [fit]"""
+"""One launch of the L-BFGS-B kernel for ncu:  python tools/lb_profile.py [cfg] [scale] [fit] [solver]"""
 import os
 import sys
 
@@ -14,6 +14,7 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "c2"
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
 c = synth.CONFIGS[cfg]
 fit = sys.argv[3] if len(sys.argv) > 3 else c["fit"]
+solver = sys.argv[4] if len(sys.argv) > 4 else "lbfgsb"
 y, mask, te, _ = synth.make_volume(cfg, scale=scale)
 _, fp = presets.preset(fit, c["field"] == "lf")
 t2.init(0)
@@ -21,6 +22,6 @@ dev = torch.device("cuda", 0)
 yt = torch.from_numpy(y.reshape(-1, y.shape[-1])).to(dev)
 idx = torch.from_numpy(np.flatnonzero(mask.reshape(-1))).to(dev)
 for _ in range(2):
-    r = t2.fit_voxels_batch(yt, idx, te, fit, fp, c["prior"], False, solver="lbfgsb")
+    r = t2.fit_voxels_batch(yt, idx, te, fit, fp, c["prior"], False, solver=solver)
 torch.cuda.synchronize()
 print(cfg, scale, fit, idx.numel(), "mean nit", r.nit.float().mean().item())
