@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(kQBlock, queue_min_blocks(E)) floor_queue_kern
 // ------------------------------------------------------------------------------------------------
 constexpr int kLbBlock = 128;
 
-template <int OBJ>
+template <int OBJ, int YS = 1>           // YS: stride of the signal row y (1 = contiguous; kLbBlock = a column of shared memory)
 __device__ __noinline__ void lb_store(const lb::LbConsts& c, const KernelIO& io, const lb::LbVoxel& v, const float* y, int64_t i, int64_t row) {
     const int E = c.n_echo;
     const float kf = (float)v.x[0], t2f = (float)v.x[1], sf = (OBJ == 0) ? 0.f : (float)v.x[2];
@@ -495,7 +495,7 @@ __device__ __noinline__ void lb_store(const lb::LbConsts& c, const KernelIO& io,
     for (int e = 0; e < E; ++e) {
         double pred = (double)kf * exp(-c.te[e] / (double)t2f);
         if (OBJ != 0) pred = sqrt(pred * pred + (double)sf * (double)sf);
-        acc += (double)y[e] - (double)(float)pred;
+        acc += (double)y[e * YS] - (double)(float)pred;
     }
     const int64_t o = io.dense ? row : i;
     if (io.t2) io.t2[o] = t2f;
@@ -575,19 +575,118 @@ __global__ void __launch_bounds__(kLbBlock, T2_LB_MIN_BLOCKS) lbfgsb_kernel(cons
 
 // ------------------------------------------------------------------------------------------------
 // lbfgsb_dense_kernel: the same optimiser with the limited-memory matrix as a dense n x n matrix (t2fit_lbfgsb_dense.cuh),
-// one voxel per thread, FP64, same lane queue.  The state of a voxel is the <= 10 correction pairs (480 B of local memory,
-// L1-resident) plus ~50 doubles the compiler keeps in registers, and the optimiser core is a few hundred flops per
-// iteration: the kernel is bound by the FP64 pipe evaluating the objective (N + 1 values per gradient, 2 exponentials per
-// echo), not by memory.
+// one voxel per thread, FP64, same lane queue.  The state of a voxel is the <= 10 correction pairs (480 B of local memory)
+// plus ~50 doubles in registers; the optimiser core is a few hundred flops per iteration, so the run time is the objective
+// evaluations: N + 1 values per gradient, walked in ONE loop over the echoes whose N + 1 dependent chains overlap
+// (DenseRun::fun_and_grad).  What that loop reads and writes -- the signal row and the 8 running sums of numpy's pairwise
+// np.sum per point -- lives in SHARED memory as [slot][thread] columns (4 E + 64 (N + 1) bytes per thread), not in local
+// memory: the loop issues no LDL / STL.
 // ------------------------------------------------------------------------------------------------
 #ifndef T2_LBD_MIN_BLOCKS
 #define T2_LBD_MIN_BLOCKS 4
 #endif
+constexpr size_t dense_smem_bytes(int n_par, int n_echo) { return (size_t)kLbBlock * ((size_t)(n_par + 1) * 8 * sizeof(double) + (size_t)n_echo * sizeof(float)); }
+
+// Epilogue of the voxels that ended in this pass of the warp (`fin` lanes, usually 2-3 of 32): what lb_store does, with the
+// residual (compute_residuals, utils/t2map_utils.py:62-89: E double-precision exp / sqrt per voxel) evaluated BY THE WHOLE
+// WARP, one echo per lane, instead of by the 2-3 finished lanes while the others wait: the same operations on the same
+// operands, summed in echo order, so `res` is bit for bit lb_store's.  ys = the block's signal rows in shared memory.
+template <int OBJ>
+__device__ __noinline__ void dense_finish(const lb::LbConsts& c, const KernelIO& io, const lb::LbVoxel& v, bool fin, unsigned fm,
+                                          const float* ys, int64_t i, int64_t row) {
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
+    const int E = c.n_echo, warp0 = threadIdx.x & ~31;
+    const float kf = (float)v.x[0], t2f = (float)v.x[1], sf = (OBJ == 0) ? 0.f : (float)v.x[2];
+    const double te = c.te[lane < (unsigned)E ? lane : 0];
+    double res = 0.0;
+    for (unsigned mm = fm; mm; mm &= mm - 1) {
+        const int src = __ffs(mm) - 1;
+        const float kk = __shfl_sync(full, kf, src), tt = __shfl_sync(full, t2f, src), ss = __shfl_sync(full, sf, src);
+        double term = 0.0;
+        if (lane < (unsigned)E) {
+            double pred = (double)kk * exp(-te / (double)tt);
+            if (OBJ != 0) pred = sqrt(pred * pred + (double)ss * (double)ss);
+            term = (double)ys[lane * kLbBlock + warp0 + src] - (double)(float)pred;
+        }
+        double acc = 0.0;
+        for (int e = 0; e < E; ++e) acc += __shfl_sync(full, term, e);
+        if ((int)lane == src) res = acc;
+    }
+    if (!fin) return;
+    const float resf = (float)(res / (double)E);
+    const int64_t o = io.dense ? row : i;
+    if (io.t2) io.t2[o] = t2f;
+    if (io.k) io.k[o] = kf;
+    if (OBJ != 0 && io.sigma) io.sigma[o] = sf;
+    if (io.res) io.res[o] = resf;
+    if (io.fun) io.fun[i] = (float)v.fun;
+    if (io.nit) io.nit[i] = v.nit;
+    if (io.status) io.status[i] = (uint8_t)v.status;
+    if (io.trace_len) io.trace_len[i] = v.trace_len;
+    if (io.dup.n) store_dups(io, i, t2f, kf, sf, resf, v.status);
+    if (v.status != 0 && io.counts) atomicAdd(io.counts + v.status, 1ull);
+}
+
 template <int OBJ>
 __global__ void __launch_bounds__(kLbBlock, T2_LBD_MIN_BLOCKS) lbfgsb_dense_kernel(const __grid_constant__ lb::LbConsts c,
                                                                 const __grid_constant__ KernelIO io,
                                                                 unsigned long long* __restrict__ queue) {
-    lb_queue_loop<OBJ, lb::DenseRun<OBJ>>(c, io, queue);
+    extern __shared__ __align__(16) unsigned char dense_smem[];
+    constexpr int N = OBJ == 0 ? 2 : 3;
+    using Run = lb::DenseRun<OBJ, lb::DenseStridedMem<kLbBlock>>;
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
+    const int E = c.n_echo;
+    float* const ys = reinterpret_cast<float*>(dense_smem + (size_t)(N + 1) * 8 * kLbBlock * sizeof(double));   // [E][kLbBlock]
+    double pairs[lb::DenseSolver<N>::kPairDoubles];           // the correction pairs: the one dynamically indexed array, an object of its own
+    Run run;
+    run.m.acc_ = reinterpret_cast<double*>(dense_smem) + threadIdx.x;                                   // [(N + 1) * 8][kLbBlock]
+    run.m.y_ = ys + threadIdx.x;
+    run.m.pairs_ = pairs;
+    run.active = false;
+    int64_t cur = -1, row = 0;
+    bool exhausted = false;
+    for (;;) {
+        bool fin = false;                                     // this lane's voxel ended in this round of the loop
+        const bool need = !run.active && !exhausted;
+        const unsigned m = __ballot_sync(full, need);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(m));
+            base = __shfl_sync(full, base, leader);
+            if (need) {
+                const int64_t i = (int64_t)base + __popc(m & ((1u << lane) - 1u));
+                if (i < io.n_fit) {
+                    cur = i;
+                    row = has_idx(io) ? guarded_row(io, raw_row(io, i)) : i;
+                    if (io.layout == T2FIT_LAYOUT_AOS) { for (int e = 0; e < E; ++e) run.m.y(e) = __ldg(io.echoes + row * E + e); }
+                    else {
+                        const int64_t col = io.layout == T2FIT_LAYOUT_SOA ? i : row;
+                        for (int e = 0; e < E; ++e) run.m.y(e) = __ldg(io.echoes + (int64_t)e * io.ld + col);
+                    }
+                    const bool tr = io.trace_cap > 0;
+                    run.start(c, (tr && io.trace_f) ? io.trace_f + i * io.trace_cap : nullptr,
+                              (tr && io.trace_step) ? io.trace_step + i * io.trace_cap : nullptr, tr ? io.trace_cap : 0);
+                    fin = !run.active;                        // non-finite input / bad bounds: no optimiser run
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        const bool any_active = __any_sync(full, run.active);
+        if (run.active) {
+            run.pass(c);
+            fin = !run.active;
+        }
+        __syncwarp(full);
+        const unsigned fm = __ballot_sync(full, fin);
+        if (fm) {
+            lb::LbVoxel v;
+            if (fin) v = run.finish();
+            dense_finish<OBJ>(c, io, v, fin, fm, ys, cur, row);
+        }
+        if (!any_active && __all_sync(full, exhausted)) break;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1152,15 +1251,18 @@ int launch_lbfgsb(Context* c, const lb::LbConsts& lc, KernelIO io, int model, in
     static const int env_per_sm = [] { const char* e = getenv("T2FIT_LB_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
     static const int env_per_sm_dense = [] { const char* e = getenv("T2FIT_LBD_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
     int per_sm = lc.dense ? env_per_sm_dense : env_per_sm;
+    // the dense kernel keeps the signal row and the running sums of its objective loop in shared memory
+    const size_t smem = lc.dense ? dense_smem_bytes(model == T2FIT_MODEL_GAUSSIAN ? 2 : 3, n_echo) : 0;
+    static_assert(dense_smem_bytes(3, kMaxEcho) <= 48 * 1024, "dynamic shared memory of lbfgsb_dense_kernel needs the opt-in attribute");
     if (per_sm <= 0) {
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kLbBlock, 0));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kLbBlock, smem));
         if (per_sm <= 0) per_sm = 1;
     }
     const int64_t want = (io.n_fit + kLbBlock - 1) / kLbBlock;
     const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)per_sm * c->prop.multiProcessorCount);
     unsigned long long* q = c->d_queue + (c->queue_next++ % kQueues);
     CU_TRY(cudaMemsetAsync(q, 0, sizeof(unsigned long long), st));
-    fn<<<grid, kLbBlock, 0, st>>>(lc, io, q);
+    fn<<<grid, kLbBlock, smem, st>>>(lc, io, q);
     CU_TRY(cudaGetLastError());
     return T2FIT_OK;
 }

@@ -42,7 +42,16 @@ struct DenseSolver {
     double t[N], r[N], d[N], z[N];
     int iwhere[N];
     // limited memory: the pairs (circular, `head` = oldest) and the matrix they define
-    double ws[kM][N], wy[kM][N];
+    // The pairs are the ONLY dynamically indexed data of the solver, and they are deliberately NOT members: an array indexed
+    // at run time inside this struct keeps the WHOLE struct in local memory (the compiler's scalar replacement gives up on an
+    // aggregate as soon as one access into it has an unknown offset) -- measured: every x, g, B, ... access an LDL / STL,
+    // 20 KB of DRAM traffic per voxel.  `pw` points at kPairDoubles doubles owned by the caller: s[kM][N], y[kM][N] and
+    // 1 / (y's) [kM] (rebuild() needs that quotient at every iteration; it does not change while the pair is stored).
+    double* pw;
+    static constexpr int kPairDoubles = kM * (2 * N + 1);
+    T2_HD double& ws(int pt, int i) { return pw[pt * N + i]; }
+    T2_HD double& wy(int pt, int i) { return pw[kM * N + pt * N + i]; }
+    T2_HD double& wiys(int pt) { return pw[2 * kM * N + pt]; }
     double B[N][N];
     double theta;
     int col, head, itail, iupdat;
@@ -95,16 +104,16 @@ struct DenseSolver {
             const int pt = (head + q) % kM;
             double s[N], y[N], bs[N];
 #pragma unroll
-            for (int i = 0; i < N; ++i) { s[i] = ws[pt][i]; y[i] = wy[pt][i]; }
-            double sbs = 0.0, ys = 0.0;
+            for (int i = 0; i < N; ++i) { s[i] = ws(pt, i); y[i] = wy(pt, i); }
+            double sbs = 0.0;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 double a = 0.0;
 #pragma unroll
                 for (int j = 0; j < N; ++j) a += B[i][j] * s[j];
-                bs[i] = a; sbs += a * s[i]; ys += y[i] * s[i];
+                bs[i] = a; sbs += a * s[i];
             }
-            const double isbs = 1.0 / sbs, iys = 1.0 / ys;
+            const double isbs = 1.0 / sbs, iys = wiys(pt);
 #pragma unroll
             for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -213,6 +222,10 @@ struct DenseSolver {
         return s;
     }
 
+    // a / d for a pivot d > 0 (finite or +inf): a zero numerator -- every entry of the identity padding below -- is its own
+    // quotient, sign included; the IEEE division would take its slow path for it (~60 instructions) to say the same
+    T2_HD static double div0(double a, double d) { return a == 0.0 ? a : ddiv(a, d); }
+
     // ---- subspace minimisation over the free variables at the Cauchy point; false = B_FF not positive definite ----
     T2_HD bool subsm() {
         // The free set F is NOT compacted: rows / columns of the other variables are replaced by those of the identity and
@@ -242,7 +255,7 @@ struct DenseSolver {
                 double tt = A[k][j];
 #pragma unroll
                 for (int q = 0; q < k; ++q) tt -= A[q][k] * A[q][j];
-                tt = ddiv(tt, A[k][k]);
+                tt = div0(tt, A[k][k]);
                 A[k][j] = tt;
                 sq += tt * tt;
             }
@@ -255,14 +268,14 @@ struct DenseSolver {
             double sq = rr_[j];
 #pragma unroll
             for (int q = 0; q < j; ++q) sq -= A[q][j] * rr_[q];
-            rr_[j] = ddiv(sq, A[j][j]);
+            rr_[j] = div0(sq, A[j][j]);
         }
 #pragma unroll
         for (int j = N - 1; j >= 0; --j) {
             double sq = rr_[j];
 #pragma unroll
             for (int q = j + 1; q < N; ++q) sq -= A[j][q] * rr_[q];
-            rr_[j] = ddiv(sq, A[j][j]);
+            rr_[j] = div0(sq, A[j][j]);
         }
         // projection of the Newton point onto the box (v3.0), else backtrack along the Newton direction
         double xp[N];
@@ -321,7 +334,10 @@ struct DenseSolver {
         if (iupdat <= kM) { col = iupdat; itail = (head + iupdat - 1) % kM; }
         else { itail = (itail + 1) % kM; head = (head + 1) % kM; }
 #pragma unroll
-        for (int i = 0; i < N; ++i) { ws[itail][i] = d[i]; wy[itail][i] = r[i]; }
+        double ys = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { ws(itail, i) = d[i]; wy(itail, i) = r[i]; ys += r[i] * d[i]; }
+        wiys(itail) = 1.0 / ys;
         theta = ddiv(rr, dr);
         rebuild();
     }
@@ -528,15 +544,71 @@ struct DenseSolver {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Where a voxel keeps the two arrays its objective loop walks: the signal row y[E] and, for each of the N + 1 points of one
+// fun_and_grad call, the 8 running sums of numpy's pairwise np.sum.  Host build and generic callers: plain arrays inside the
+// run.  lbfgsb_dense_kernel: shared memory, [slot][thread] (the slot index is uniform across a warp: no bank conflicts), so
+// that the loop touches no local memory at all.
+// ---------------------------------------------------------------------------------------------
+struct DenseLocalMem {
+    float y_[kMaxEcho];
+    double acc_[4 * 8];
+    double pairs_[kM * 7];
+    T2_HD double* pairs() { return pairs_; }
+    T2_HD float& y(int e) { return y_[e]; }
+    T2_HD const float& y(int e) const { return y_[e]; }
+    T2_HD double& acc(int p, int j) { return acc_[p * 8 + j]; }
+};
+
+template <int STRIDE>
+struct DenseStridedMem {                                     // y_ / acc_ point at this thread's column
+    float* y_;
+    double* acc_;
+    double* pairs_;                                          // DenseSolver::kPairDoubles doubles of the thread's own (local memory)
+    T2_HD double* pairs() { return pairs_; }
+    T2_HD float& y(int e) { return y_[e * STRIDE]; }
+    T2_HD const float& y(int e) const { return y_[e * STRIDE]; }
+    T2_HD double& acc(int p, int j) { return acc_[(p * 8 + j) * STRIDE]; }
+};
+
+// what one evaluation point contributes to every echo's term (the per-call quantities of objective_term_u, hoisted: the same
+// operations on the same operands, so the same bits)
+template <int OBJ>
+struct PointPre {
+    double a, s2, ls2, ts2;
+    T2_HD void set(double k, double sigma) {
+        if constexpr (OBJ == 0) a = k;
+        else if constexpr (OBJ == 1) { a = mul(k, k); s2 = mul(sigma, sigma); }
+        else { a = k; s2 = mul(sigma, sigma); ls2 = log(s2); ts2 = mul(2.0, s2); }
+    }
+    // objective_term_u (t2fit_lbfgsb.cuh) with yd = (double)y, lg = (double)logf(y), y2 = (double)(y * y in float32)
+    T2_HD double term(double yd, double lg, double y2, double u) const {
+        if constexpr (OBJ == 0) {
+            const double r = sub(yd, mul(a, u));
+            return mul(r, r);
+        } else if constexpr (OBJ == 1) {
+            const double r = sub(yd, sqrt(add(mul(a, u), s2)));
+            return mul(r, r);
+        } else {
+            const double m = mul(a, u);
+            const double x = mul(m, yd) / s2;
+            const double aa = sub(lg, ls2);
+            const double b = add(y2, mul(m, m)) / ts2;
+            const double cc = add(fabs(x), log(i0e(x)));
+            return add(sub(aa, b), cc);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // One voxel through the dense form: fit_voxel's preamble (run_t2mapping.py:237-245), scipy's fun_and_grad per pass, what
 // fit_voxel returns -- the same contract as VoxelRun (t2fit_lbfgsb.cuh), force-inlined so that the state stays in registers.
 // Every larger routine of the solver has exactly one call site in pass().
 // ---------------------------------------------------------------------------------------------
-template <int OBJ>
+template <int OBJ, class Mem = DenseLocalMem>
 struct DenseRun {
     static constexpr int N = (OBJ == 0) ? 2 : 3;
     DenseSolver<N> s;
-    float y[kMaxEcho];
+    Mem m;
     double xprev[N];
     float* trace_f;
     float* trace_step;
@@ -544,33 +616,41 @@ struct DenseRun {
     int nit, nfev, status;
     bool have_prev, started, active;
 
-    T2_HD void start(const float* yraw, const LbConsts& c, float* tf, float* ts, int tcap) {
+    // the signal row is in m.y(0 .. E-1) already (the caller loaded it there)
+    T2_HD void start(const LbConsts& c, float* tf, float* ts, int tcap) {
         const int E = c.n_echo;
         bool finite = true;
-        float ymax = yraw[0];
+        const float y0 = m.y(0);
+        float ymax = y0;
         T2_ROLLED for (int e = 0; e < E; ++e) {
-            y[e] = yraw[e];
-            finite = finite && ((yraw[e] - yraw[e]) == 0.0f);
-            ymax = yraw[e] > ymax ? yraw[e] : ymax;
+            const float v = m.y(e);
+            finite = finite && ((v - v) == 0.0f);
+            ymax = v > ymax ? v : ymax;
         }
         if (c.norm) {                                         // float32 / float32 (:237-238)
-            T2_ROLLED for (int e = 0; e < E; ++e) { y[e] = yraw[e] / ymax; finite = finite && ((y[e] - y[e]) == 0.0f); }
+            T2_ROLLED for (int e = 0; e < E; ++e) { const float v = m.y(e) / ymax; m.y(e) = v; finite = finite && ((v - v) == 0.0f); }
         }
         double lo[3], hi[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) { lo[i] = c.lb[i]; hi[i] = c.ub[i]; }
-        if (c.no_prior) lo[0] = (double)yraw[0];              // :243-245 (upper bound and T2 box are in c)
+        if (c.no_prior) lo[0] = (double)y0;                   // :243-245 (upper bound and T2 box are in c)
         status = kOk;
-        if (c.no_prior && (yraw[0] > (float)hi[0])) status = kBadBounds;   // scipy: "An upper bound is less than ..."
+        if (c.no_prior && (y0 > (float)hi[0])) status = kBadBounds;   // scipy: "An upper bound is less than ..."
         else if (!finite) status = kNonFinite;
         if (OBJ == 2 && status == kOk) {                      // rician: log(signal) needs signal > 0
-            T2_ROLLED for (int e = 0; e < E; ++e) if (!(y[e] > 0.0f)) status = kNonFinite;
+            T2_ROLLED for (int e = 0; e < E; ++e) if (!(m.y(e) > 0.0f)) status = kNonFinite;
         }
+        s.pw = m.pairs();
         s.setup(c.x0, lo, hi, c.ftol, c.pgtol, c.maxls);
         nit = 0; nfev = 0; tl = 0;
         have_prev = false; started = false;
         trace_f = tf; trace_step = ts; trace_cap = tcap;
         active = status == kOk;
+    }
+
+    T2_HD void start(const float* yraw, const LbConsts& c, float* tf, float* ts, int tcap) {
+        T2_ROLLED for (int e = 0; e < c.n_echo; ++e) m.y(e) = yraw[e];
+        start(c, tf, ts, tcap);
     }
 
     // scipy's approx_derivative step for variable i (absolute step, sign flip at a bound); the box as the solver holds it
@@ -585,44 +665,94 @@ struct DenseRun {
         return h;
     }
 
-    T2_HD void pass(const LbConsts& c) {
+    // f(x) and the N forward differences of one fun_and_grad call in ONE walk over the echoes.  The N + 1 points differ in
+    // one coordinate each; the points x + h e_k and x + h e_sigma have the exponentials of x (same T2), so an echo costs 2
+    // exponentials and N + 1 terms, and those N + 1 dependent chains (exp / sqrt / i0e) are independent of each other: the
+    // loop body offers the scheduler four-way instruction-level parallelism where four separate loops offered none.
+    // np.sum of every point's terms is accumulated on the fly in numpy's pairwise order (np_sum above: below 8 elements a
+    // plain running sum; else 8 running sums combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the E % 8 last terms one
+    // by one), so every value is bit for bit what objective<OBJ>() returns at that point.
+    T2_HD void fun_and_grad(const LbConsts& c, double& fv, double* gv) {
         const int E = c.n_echo;
+        double xt[N];
+        PointPre<OBJ> pre[N + 1];
+        pre[0].set(s.x[0], N == 3 ? s.x[N - 1] : 0.0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) xt[i] = s.x[i] + fd_h(i, c.fd_step);
+        pre[1].set(xt[0], N == 3 ? s.x[N - 1] : 0.0);
+        pre[2] = pre[0];
+        if constexpr (N == 3) pre[3].set(s.x[0], xt[N - 1]);
+        const double t2a = s.x[1], t2b = xt[1];
+        const int nb = E >= 8 ? E - (E % 8) : 0;
+        double sum[N + 1];
+#pragma unroll
+        for (int p = 0; p <= N; ++p) sum[p] = 0.0;
+        T2_ROLLED for (int phase = 0; phase < 2; ++phase) {
+            const int e1 = phase ? E : nb;
+            T2_ROLLED for (int e = phase ? nb : 0; e < e1; ++e) {
+                const float yf = m.y(e);
+                const double yd = (double)yf, te = c.te[e];
+                double lg = 0.0, y2 = 0.0;
+                if constexpr (OBJ == 2) { lg = (double)logf(yf); y2 = (double)mulf(yf, yf); }
+                const double ua = objective_expo<OBJ>(t2a, te), ub = objective_expo<OBJ>(t2b, te);
+                double v[N + 1];
+#pragma unroll
+                for (int p = 0; p <= N; ++p) v[p] = pre[p].term(yd, lg, y2, p == 2 ? ub : ua);
+                if (phase == 0) {
+                    const int j = e & 7;
+                    if (e < 8) {
+#pragma unroll
+                        for (int p = 0; p <= N; ++p) m.acc(p, j) = v[p];
+                    } else {
+#pragma unroll
+                        for (int p = 0; p <= N; ++p) m.acc(p, j) = add(m.acc(p, j), v[p]);
+                    }
+                } else {
+                    const bool first = e == 0;                // E < 8: np.sum starts from the first term itself
+#pragma unroll
+                    for (int p = 0; p <= N; ++p) sum[p] = first ? v[p] : add(sum[p], v[p]);
+                }
+            }
+            if (phase == 0 && nb) {
+#pragma unroll
+                for (int p = 0; p <= N; ++p)
+                    sum[p] = add(add(add(m.acc(p, 0), m.acc(p, 1)), add(m.acc(p, 2), m.acc(p, 3))),
+                                 add(add(m.acc(p, 4), m.acc(p, 5)), add(m.acc(p, 6), m.acc(p, 7))));
+            }
+        }
+        fv = (OBJ == 2) ? -sum[0] : sum[0] / (double)E;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double fi = (OBJ == 2) ? -sum[i + 1] : sum[i + 1] / (double)E;
+            gv[i] = ddiv(fi - fv, xt[i] - s.x[i]);
+        }
+    }
+
+    T2_HD void pass(const LbConsts& c) {
         double fv, gv[N];
 #ifdef T2FIT_HOSTSIM
         if (c.fd_step < 0.0) {                                // test hook: analytic gradient (as VoxelRun)
+            const int E = c.n_echo;
+            float y[kMaxEcho];
+            for (int e = 0; e < E; ++e) y[e] = m.y(e);
             fv = objective<OBJ>(s.x, y, c);
             for (int i = 0; i < N; ++i) gv[i] = 0.0;
             for (int e = 0; e < E; ++e) {
                 if (OBJ == 0) {
-                    const double u = exp(-c.te[e] / s.x[1]), m = s.x[0] * u, rr = (double)y[e] - m;
+                    const double u = exp(-c.te[e] / s.x[1]), mm = s.x[0] * u, rr = (double)y[e] - mm;
                     gv[0] += -2.0 * rr * u / E;
-                    gv[1] += -2.0 * rr * m * c.te[e] / (s.x[1] * s.x[1]) / E;
+                    gv[1] += -2.0 * rr * mm * c.te[e] / (s.x[1] * s.x[1]) / E;
                 } else if (OBJ == 1) {
-                    const double u2 = exp(-2.0 * c.te[e] / s.x[1]), m = sqrt(s.x[0] * s.x[0] * u2 + s.x[2 % N] * s.x[2 % N]);
-                    const double rr = (double)y[e] - m;
-                    gv[0] += -2.0 * rr * (s.x[0] * u2 / m) / E;
-                    gv[1] += -2.0 * rr * (s.x[0] * s.x[0] * u2 * c.te[e] / (s.x[1] * s.x[1]) / m) / E;
-                    gv[2 % N] += -2.0 * rr * (s.x[2 % N] / m) / E;
+                    const double u2 = exp(-2.0 * c.te[e] / s.x[1]), mm = sqrt(s.x[0] * s.x[0] * u2 + s.x[2 % N] * s.x[2 % N]);
+                    const double rr = (double)y[e] - mm;
+                    gv[0] += -2.0 * rr * (s.x[0] * u2 / mm) / E;
+                    gv[1] += -2.0 * rr * (s.x[0] * s.x[0] * u2 * c.te[e] / (s.x[1] * s.x[1]) / mm) / E;
+                    gv[2 % N] += -2.0 * rr * (s.x[2 % N] / mm) / E;
                 }
             }
         } else
 #endif
-        {
-            // f(x) and the N forward differences: the points x + h e_k and x + h e_sigma have the exponentials of x (same
-            // T2), so 2 exponentials per echo instead of N + 1; every value is bit for bit what objective<OBJ>() returns there
-            double u[kMaxEcho], v[kMaxEcho], xt[N];
-            T2_ROLLED for (int e = 0; e < E; ++e) { u[e] = objective_expo<OBJ>(s.x[1], c.te[e]); v[e] = objective_term_u<OBJ>(s.x, y[e], u[e]); }
-            fv = objective_reduce<OBJ>(v, E);
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-#pragma unroll
-                for (int j = 0; j < N; ++j) xt[j] = s.x[j];
-                xt[i] = s.x[i] + fd_h(i, c.fd_step);
-                if (i == 1) { T2_ROLLED for (int e = 0; e < E; ++e) v[e] = objective_term_u<OBJ>(xt, y[e], objective_expo<OBJ>(xt[1], c.te[e])); }
-                else { T2_ROLLED for (int e = 0; e < E; ++e) v[e] = objective_term_u<OBJ>(xt, y[e], u[e]); }
-                gv[i] = ddiv(objective_reduce<OBJ>(v, E) - fv, xt[i] - s.x[i]);
-            }
-        }
+        fun_and_grad(c, fv, gv);
         nfev += N + 1;
         if (!started) {
             if (!(fv - fv == 0.0)) {                          // objective not finite at the start point: scipy ends ABNORMAL there
