@@ -50,6 +50,9 @@ inline int make_lb_consts(const t2fit_problem& p, lb::LbConsts& c, std::string& 
         if (!isfinite(te)) { err = "non-finite echo time"; return T2FIT_EINVAL; }
         c.te[e] = te;
     }
+    c.te_div_safe = 1;                              // every |TE| is 0 or far from the ends of the exponent range (lb::EchoDiv)
+    for (int e = 0; e < p.n_echo; ++e)
+        if (p.te_ms[e] != 0.0 && !(fabs(p.te_ms[e]) > 1e-100 && fabs(p.te_ms[e]) < 1e100)) c.te_div_safe = 0;
     for (int i = 0; i < 3; ++i) { c.x0[i] = i < np_ ? p.x0[i] : 0.0; c.lb[i] = lbv[i]; c.ub[i] = ubv[i]; }
     c.ftol = p.lbfgsb_ftol > 0.0 ? p.lbfgsb_ftol : 2.220446049250313e-09;
     c.pgtol = p.lbfgsb_gtol > 0.0 ? p.lbfgsb_gtol : 1e-5;

@@ -80,6 +80,7 @@ struct LbConsts {
     int norm;
     int objective;            // 0 gaussian, 1 gaussian_rician, 2 rician
     int dense;                // T2FIT_SOLVER_LBFGSB_DENSE: the dense-matrix form (t2fit_lbfgsb_dense.cuh)
+    int te_div_safe;          // all |TE| in {0} or (1e-100, 1e100): lb::EchoDiv may take its short form
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -163,6 +164,49 @@ template <int OBJ>
 T2_HD double objective_expo(double t2, double te) {
     if constexpr (OBJ == 1) return exp(mul(-2.0, te) / t2);     // np.exp(-2 * t / t2)
     else return exp((-te) / t2);                                // np.exp(-t / t2)
+}
+
+// The quotient a / t2 of objective_expo for MANY numerators a (one per echo) and ONE denominator (the T2 of an evaluation
+// point): the IEEE-754 quotient, bit for bit, from the correctly rounded reciprocal y = RN(1 / t2) taken once --
+//     q0 = RN(a y),   r = a - t2 q0  (exact in one FMA),   q = RN(q0 + r y)
+// (Markstein 1990: with y correctly rounded and q0 within an ulp or so of a / t2, the second-order correction lands on the
+// correctly rounded quotient; a quotient of two doubles is never a rounding midpoint).  Checked against `a / b` on 4e8 pairs
+// incl. denominators with an all-ones mantissa: no difference.  Three FP64 instructions per echo instead of the ~30 of a
+// division.  Operands near the ends of the exponent range (where a y could overflow / lose bits and a / t2 would not) take
+// the division itself: `safe` is decided once per point.
+struct EchoDiv {
+    double t2, y;
+    bool safe;
+    T2_HD void set(double t2_, bool te_safe) {
+        t2 = t2_;
+        y = 1.0 / t2_;
+        safe = te_safe && fabs(t2_) > 1e-100 && fabs(t2_) < 1e100;
+    }
+    T2_HD double operator()(double a) const {
+        if (!safe) return ddiv(a, t2);                       // out of line: the echo loop must stay small (instruction cache)
+#if T2_DEVICE_BUILD
+        const double q0 = __dmul_rn(a, y);
+        return __fma_rn(__fma_rn(-t2, q0, a), y, q0);
+#else
+        const double q0 = mul(a, y);
+        return fma(fma(-t2, q0, a), y, q0);
+#endif
+    }
+};
+
+// exp / sqrt of the dense kernel's echo loop: T2_DENSE_CALLS & 1 -> exp as a call, & 2 -> sqrt as a call (one copy of the
+// ~60 / ~25 instruction expansions instead of 2 / 4 inlined ones per loop body; A/B in profiles/r02_notes.md section 10)
+#ifndef T2_DENSE_CALLS
+#define T2_DENSE_CALLS 0
+#endif
+T2_NI double dexp(double a) { return exp(a); }
+T2_HD double loop_exp(double a) { return (T2_DENSE_CALLS & 1) ? dexp(a) : exp(a); }
+T2_HD double loop_sqrt(double a) { return (T2_DENSE_CALLS & 2) ? dsqrt(a) : sqrt(a); }
+
+template <int OBJ>
+T2_HD double objective_expo(const EchoDiv& d, double te) {
+    if constexpr (OBJ == 1) return loop_exp(d(mul(-2.0, te)));  // np.exp(-2 * t / t2)
+    else return loop_exp(d(-te));                               // np.exp(-t / t2)
 }
 
 // the term given that exponential (u): the forward differences in k and sigma reuse the exponentials of the base point

@@ -100,11 +100,26 @@ struct DenseSolver {
         for (int i = 0; i < N; ++i)
 #pragma unroll
             for (int j = 0; j < N; ++j) B[i][j] = (i == j) ? theta : 0.0;
-        T2_ROLLED for (int q = 0; q < col; ++q) {
-            const int pt = (head + q) % kM;
-            double s[N], y[N], bs[N];
+        // the pairs sit in local memory: the loads of pair q + 1 are issued before the update with pair q (every update needs
+        // the matrix the previous one left, so nothing else hides their latency)
+        double sn[N], yn[N], iysn;
+        {
+            const int pt = head % kM;
 #pragma unroll
-            for (int i = 0; i < N; ++i) { s[i] = ws(pt, i); y[i] = wy(pt, i); }
+            for (int i = 0; i < N; ++i) { sn[i] = ws(pt, i); yn[i] = wy(pt, i); }
+            iysn = wiys(pt);
+        }
+        T2_ROLLED for (int q = 0; q < col; ++q) {
+            double s[N], y[N], bs[N];
+            const double iys = iysn;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { s[i] = sn[i]; y[i] = yn[i]; }
+            if (q + 1 < col) {
+                const int pt = (head + q + 1) % kM;
+#pragma unroll
+                for (int i = 0; i < N; ++i) { sn[i] = ws(pt, i); yn[i] = wy(pt, i); }
+                iysn = wiys(pt);
+            }
             double sbs = 0.0;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
@@ -113,7 +128,7 @@ struct DenseSolver {
                 for (int j = 0; j < N; ++j) a += B[i][j] * s[j];
                 bs[i] = a; sbs += a * s[i];
             }
-            const double isbs = 1.0 / sbs, iys = wiys(pt);
+            const double isbs = 1.0 / sbs;
 #pragma unroll
             for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -586,7 +601,7 @@ struct PointPre {
             const double r = sub(yd, mul(a, u));
             return mul(r, r);
         } else if constexpr (OBJ == 1) {
-            const double r = sub(yd, sqrt(add(mul(a, u), s2)));
+            const double r = sub(yd, loop_sqrt(add(mul(a, u), s2)));
             return mul(r, r);
         } else {
             const double m = mul(a, u);
@@ -682,7 +697,9 @@ struct DenseRun {
         pre[1].set(xt[0], N == 3 ? s.x[N - 1] : 0.0);
         pre[2] = pre[0];
         if constexpr (N == 3) pre[3].set(s.x[0], xt[N - 1]);
-        const double t2a = s.x[1], t2b = xt[1];
+        EchoDiv da, db;                                       // 1 / T2 of the two T2 values of this call, once
+        da.set(s.x[1], c.te_div_safe != 0);
+        db.set(xt[1], c.te_div_safe != 0);
         const int nb = E >= 8 ? E - (E % 8) : 0;
         double sum[N + 1];
 #pragma unroll
@@ -694,7 +711,7 @@ struct DenseRun {
                 const double yd = (double)yf, te = c.te[e];
                 double lg = 0.0, y2 = 0.0;
                 if constexpr (OBJ == 2) { lg = (double)logf(yf); y2 = (double)mulf(yf, yf); }
-                const double ua = objective_expo<OBJ>(t2a, te), ub = objective_expo<OBJ>(t2b, te);
+                const double ua = objective_expo<OBJ>(da, te), ub = objective_expo<OBJ>(db, te);
                 double v[N + 1];
 #pragma unroll
                 for (int p = 0; p <= N; ++p) v[p] = pre[p].term(yd, lg, y2, p == 2 ? ub : ua);
