@@ -686,9 +686,10 @@ def bench_volume(args, cfg):
                             "memory, DRAM-resident at 896 threads / SM), not by HBM bandwidth or a math pipe: frac is the "
                             "algorithmic-bytes figure the contract asks for, not a utilisation (DESIGN.md section 4)")
     if solver == "lbfgsb_dense":
-        roofline["note"] = ("the dense L-BFGS-B kernel is bound by the FP64 pipe evaluating the objective (N + 1 values per gradient, "
-                            "2 exponentials + N + 1 square roots per echo), not by HBM: frac is the algorithmic-bytes figure the "
-                            "contract asks for, not a utilisation (DESIGN.md section 4)")
+        roofline["note"] = ("the dense L-BFGS-B kernel is not HBM-bound: ncu puts it at 33 % issue-active, FP64 pipe 20 %, 17 of 32 lanes "
+                            "active (every lane is somewhere else in its optimiser), stalls = instruction fetch + dependent FP64 chains "
+                            "+ the correction pairs in local memory; frac is the algorithmic-bytes figure the contract asks for, not "
+                            "a utilisation (DESIGN.md section 4, profiles/r02_lbfgsb_dense_*)")
     roof_fp32 = None
     if mono and solver == "fast":
         wm = t2.work_model("gaussian", n_echo)
@@ -970,7 +971,7 @@ def bench_slab(args, cfg):
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
                              "kernel": (LB_KERNEL[solver] % "gaussian_rician" if solver in LB_SOLVERS else "floor_queue_kernel<16,AoS> (multi-start)"),
                              "kernel_ms": fit_ms, "bytes_per_fit": per_fit,
-                             "note": "not HBM-bound: FP64 pipe of the objective evaluations (lbfgsb_dense) / latency of the per-thread optimiser state (lbfgsb) / issue slots (fast); see DESIGN.md section 4"},
+                             "note": "not HBM-bound: instruction issue at 17 of 32 active lanes, FP64 pipe 20 % (lbfgsb_dense) / latency of the per-thread optimiser state (lbfgsb) / issue slots (fast); see DESIGN.md section 4"},
                 "cpu_baseline": cpu[0] if cpu else None, "parity": None,
                 "e2e": None, "gpu_launches": int(args.steps), "clocks": clocks, "device": t2.device_info()["name"]}
         if cpu is not None:

@@ -42,7 +42,7 @@ extern "C" {
 #define T2FIT_MODEL_GAUSSIAN 0        /* 'gaussian'        k exp(-te/T2)                   :129-131 */
 #define T2FIT_MODEL_GAUSSIAN_RICIAN 1 /* 'gaussian_rician' sqrt(k^2 exp(-2te/T2)+sigma^2)  :133-138 */
 #define T2FIT_MODEL_RICIAN 2          /* 'rician'  Rician negative log-likelihood (i0e)     :157-177;
-                                         T2FIT_SOLVER_LBFGSB only (it is not a least-squares problem) */
+                                         T2FIT_SOLVER_LBFGSB[_DENSE] only (not a least-squares problem) */
 
 /* which optimiser runs per voxel */
 #define T2FIT_SOLVER_FAST 0   /* float32 register-resident Newton / Levenberg-Marquardt: converges to the bounded
@@ -55,7 +55,7 @@ extern "C" {
 #define T2FIT_SOLVER_LBFGSB_DENSE 2 /* the same optimiser, same objectives / differences / line search / stopping tests
                                  and lbfgsb_* options, with the limited-memory matrix held as the n x n matrix it
                                  represents (n <= 3) instead of scipy's compact 2m x 2m form: equal in exact
-                                 arithmetic, equal parity with the reference on the golden fixtures, ~20-40x the
+                                 arithmetic, equal parity with the reference on the golden fixtures, ~20-30x the
                                  throughput (csrc/t2fit_lbfgsb_dense.cuh). */
 
 /* echo layout */

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "fetal_t2mapping_b200", "csrc")
 LIB = os.path.join(CSRC, "libt2fit.so")
 HOT = ["fit_kernel<0, 5, 0, true>", "fit_kernel<0, 5, 0, false>", "fit_kernel<0, 6, 2, true>", "floor_queue_kernel<12, 0>",
-       "floor_queue_kernel<16, 0>", "lbfgsb_kernel<0>", "lbfgsb_kernel<1>", "lbfgsb_kernel<2>", "lbfgsb_coop_kernel<1, 8>",
+       "floor_queue_kernel<16, 0>", "lbfgsb_dense_kernel<0>", "lbfgsb_dense_kernel<1>", "lbfgsb_dense_kernel<2>", "lbfgsb_kernel<0>", "lbfgsb_kernel<1>", "lbfgsb_kernel<2>", "lbfgsb_coop_kernel<1, 8>",
        "lbfgsb_coop_kernel<1, 32>", "zero_fill_kernel<true>", "zero_fill_kernel<false>", "mask_count_kernel", "mask_write_kernel",
        "mask_union_kernel", "roi_stats_kernel", "residual_kernel"]
 
@@ -53,7 +53,7 @@ def sass_histogram(out):
         f.write("SASS mnemonic histogram (cuobjdump -sass of the built libt2fit.so; static instruction counts, callees of a kernel included)\n")
         for b, n in zip(blocks, names):
             s = short(dm[n])
-            if not any(s == h for h in HOT[:10]):
+            if not any(s == h for h in HOT[:13]):
                 continue
             ops = collections.Counter()
             for m in re.finditer(r"^\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", b, re.M):
