@@ -585,7 +585,17 @@ __global__ void __launch_bounds__(kLbBlock, T2_LB_MIN_BLOCKS) lbfgsb_kernel(cons
 #ifndef T2_LBD_MIN_BLOCKS
 #define T2_LBD_MIN_BLOCKS 4
 #endif
-constexpr size_t dense_smem_bytes(int n_par, int n_echo) { return (size_t)kLbBlock * ((size_t)(n_par + 1) * 8 * sizeof(double) + (size_t)n_echo * sizeof(float)); }
+// T2_LBD_THREADS: threads per block.  T2_LBD_SYNC = 1: the warps of a block meet at a barrier before every pass, so that they
+// run the echo loop -- and then the optimiser core -- at the same time and fetch the same instructions (the kernel stalls on
+// instruction fetch: 83 KB of code, 32 KB L1.5 instruction cache); A/B in profiles/r02_notes.md section 10.
+#ifndef T2_LBD_THREADS
+#define T2_LBD_THREADS 128
+#endif
+#ifndef T2_LBD_SYNC
+#define T2_LBD_SYNC 1
+#endif
+constexpr int kLbdBlock = T2_LBD_THREADS;
+constexpr size_t dense_smem_bytes(int n_par, int n_echo) { return (size_t)kLbdBlock * ((size_t)(n_par + 1) * 8 * sizeof(double) + (size_t)n_echo * sizeof(float)); }
 
 // Epilogue of the voxels that ended in this pass of the warp (`fin` lanes, usually 2-3 of 32): what lb_store does, with the
 // residual (compute_residuals, utils/t2map_utils.py:62-89: E double-precision exp / sqrt per voxel) evaluated BY THE WHOLE
@@ -606,7 +616,7 @@ __device__ __noinline__ void dense_finish(const lb::LbConsts& c, const KernelIO&
         if (lane < (unsigned)E) {
             double pred = (double)kk * exp(-te / (double)tt);
             if (OBJ != 0) pred = sqrt(pred * pred + (double)ss * (double)ss);
-            term = (double)ys[lane * kLbBlock + warp0 + src] - (double)(float)pred;
+            term = (double)ys[lane * kLbdBlock + warp0 + src] - (double)(float)pred;
         }
         double acc = 0.0;
         for (int e = 0; e < E; ++e) acc += __shfl_sync(full, term, e);
@@ -628,23 +638,23 @@ __device__ __noinline__ void dense_finish(const lb::LbConsts& c, const KernelIO&
 }
 
 template <int OBJ>
-__global__ void __launch_bounds__(kLbBlock, T2_LBD_MIN_BLOCKS) lbfgsb_dense_kernel(const __grid_constant__ lb::LbConsts c,
+__global__ void __launch_bounds__(kLbdBlock, T2_LBD_MIN_BLOCKS) lbfgsb_dense_kernel(const __grid_constant__ lb::LbConsts c,
                                                                 const __grid_constant__ KernelIO io,
                                                                 unsigned long long* __restrict__ queue) {
     extern __shared__ __align__(16) unsigned char dense_smem[];
     constexpr int N = OBJ == 0 ? 2 : 3;
-    using Run = lb::DenseRun<OBJ, lb::DenseStridedMem<kLbBlock>>;
+    using Run = lb::DenseRun<OBJ, lb::DenseStridedMem<kLbdBlock>>;
     const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
     const int E = c.n_echo;
-    float* const ys = reinterpret_cast<float*>(dense_smem + (size_t)(N + 1) * 8 * kLbBlock * sizeof(double));   // [E][kLbBlock]
+    float* const ys = reinterpret_cast<float*>(dense_smem + (size_t)(N + 1) * 8 * kLbdBlock * sizeof(double));   // [E][kLbdBlock]
     double pairs[lb::DenseSolver<N>::kPairDoubles];           // the correction pairs: the one dynamically indexed array, an object of its own
     Run run;
-    run.m.acc_ = reinterpret_cast<double*>(dense_smem) + threadIdx.x;                                   // [(N + 1) * 8][kLbBlock]
+    run.m.acc_ = reinterpret_cast<double*>(dense_smem) + threadIdx.x;                                   // [(N + 1) * 8][kLbdBlock]
     run.m.y_ = ys + threadIdx.x;
     run.m.pairs_ = pairs;
     run.active = false;
     int64_t cur = -1, row = 0;
-    bool exhausted = false;
+    bool exhausted = false, warp_done = false;
     for (;;) {
         bool fin = false;                                     // this lane's voxel ended in this round of the loop
         const bool need = !run.active && !exhausted;
@@ -674,6 +684,9 @@ __global__ void __launch_bounds__(kLbBlock, T2_LBD_MIN_BLOCKS) lbfgsb_dense_kern
             }
         }
         const bool any_active = __any_sync(full, run.active);
+#if T2_LBD_SYNC
+        if (!__syncthreads_or(!warp_done)) break;             // every warp of the block has run dry
+#endif
         if (run.active) {
             run.pass(c);
             fin = !run.active;
@@ -685,7 +698,10 @@ __global__ void __launch_bounds__(kLbBlock, T2_LBD_MIN_BLOCKS) lbfgsb_dense_kern
             if (fin) v = run.finish();
             dense_finish<OBJ>(c, io, v, fin, fm, ys, cur, row);
         }
-        if (!any_active && __all_sync(full, exhausted)) break;
+        if (!any_active && __all_sync(full, exhausted)) warp_done = true;
+#if !T2_LBD_SYNC
+        if (warp_done) break;
+#endif
     }
 }
 
@@ -1253,16 +1269,25 @@ int launch_lbfgsb(Context* c, const lb::LbConsts& lc, KernelIO io, int model, in
     int per_sm = lc.dense ? env_per_sm_dense : env_per_sm;
     // the dense kernel keeps the signal row and the running sums of its objective loop in shared memory
     const size_t smem = lc.dense ? dense_smem_bytes(model == T2FIT_MODEL_GAUSSIAN ? 2 : 3, n_echo) : 0;
-    static_assert(dense_smem_bytes(3, kMaxEcho) <= 48 * 1024, "dynamic shared memory of lbfgsb_dense_kernel needs the opt-in attribute");
+    if (smem > 48 * 1024) {
+        static std::mutex mu;
+        static std::vector<LbFn> prepared;
+        std::lock_guard<std::mutex> lk(mu);
+        if (std::find(prepared.begin(), prepared.end(), fn) == prepared.end()) {
+            CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem_bytes(3, kMaxEcho)));
+            prepared.push_back(fn);
+        }
+    }
+    const int threads = lc.dense ? kLbdBlock : kLbBlock;
     if (per_sm <= 0) {
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kLbBlock, smem));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
         if (per_sm <= 0) per_sm = 1;
     }
-    const int64_t want = (io.n_fit + kLbBlock - 1) / kLbBlock;
+    const int64_t want = (io.n_fit + threads - 1) / threads;
     const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)per_sm * c->prop.multiProcessorCount);
     unsigned long long* q = c->d_queue + (c->queue_next++ % kQueues);
     CU_TRY(cudaMemsetAsync(q, 0, sizeof(unsigned long long), st));
-    fn<<<grid, kLbBlock, smem, st>>>(lc, io, q);
+    fn<<<grid, threads, smem, st>>>(lc, io, q);
     CU_TRY(cudaGetLastError());
     return T2FIT_OK;
 }

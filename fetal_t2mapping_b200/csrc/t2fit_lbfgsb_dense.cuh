@@ -169,8 +169,9 @@ struct DenseSolver {
             } else {
                 dd[i] = neggi;
                 f1 -= neggi * neggi;
-                if (nbd[i] <= 2 && nbd[i] != 0 && neggi < 0.0) { tt[i] = ddiv(tl, -neggi); pending[i] = true; ++nbreak; }
-                else if (nbd[i] >= 2 && neggi > 0.0) { tt[i] = ddiv(tu, neggi); pending[i] = true; ++nbreak; }
+                // (one division site for both directions: the lanes of a warp that need either call it together)
+                const bool to_lower = nbd[i] <= 2 && nbd[i] != 0 && neggi < 0.0, to_upper = !to_lower && nbd[i] >= 2 && neggi > 0.0;
+                if (to_lower || to_upper) { tt[i] = ddiv(to_lower ? tl : tu, to_lower ? -neggi : neggi); pending[i] = true; ++nbreak; }
                 else { any_unbounded = true; if (fabs(neggi) > 0.0) bnded = false; }
             }
         }
@@ -318,14 +319,11 @@ struct DenseSolver {
             for (int k = 0; k < N; ++k) if (fr[k]) {
                 const double dk = rr_[k];
                 if (nbd[k] != 0) {
-                    if (dk < 0.0 && nbd[k] <= 2) {
-                        const double temp2 = l[k] - z[k];
-                        if (temp2 >= 0.0) temp1 = 0.0;
-                        else if (dk * alpha < temp2) temp1 = ddiv(temp2, dk);
-                    } else if (dk > 0.0 && nbd[k] >= 2) {
-                        const double temp2 = u[k] - z[k];
-                        if (temp2 <= 0.0) temp1 = 0.0;
-                        else if (dk * alpha > temp2) temp1 = ddiv(temp2, dk);
+                    const bool dn = dk < 0.0 && nbd[k] <= 2, up = !dn && dk > 0.0 && nbd[k] >= 2;
+                    if (dn || up) {
+                        const double temp2 = (dn ? l[k] : u[k]) - z[k];
+                        if (dn ? temp2 >= 0.0 : temp2 <= 0.0) temp1 = 0.0;
+                        else if (dn ? dk * alpha < temp2 : dk * alpha > temp2) temp1 = ddiv(temp2, dk);
                     }
                     if (temp1 < alpha) { alpha = temp1; ibd = k; }
                 }
@@ -464,14 +462,11 @@ struct DenseSolver {
                     for (int i = 0; i < N; ++i) {
                         const double a1 = d[i];
                         if (nbd[i] != 0) {
-                            if (a1 < 0.0 && nbd[i] <= 2) {
-                                const double a2 = l[i] - x[i];
-                                if (a2 >= 0.0) stpmx = 0.0;
-                                else if (a1 * stpmx < a2) stpmx = ddiv(a2, a1);
-                            } else if (a1 > 0.0 && nbd[i] >= 2) {
-                                const double a2 = u[i] - x[i];
-                                if (a2 <= 0.0) stpmx = 0.0;
-                                else if (a1 * stpmx > a2) stpmx = ddiv(a2, a1);
+                            const bool dn = a1 < 0.0 && nbd[i] <= 2, up = !dn && a1 > 0.0 && nbd[i] >= 2;
+                            if (dn || up) {
+                                const double a2 = (dn ? l[i] : u[i]) - x[i];
+                                if (dn ? a2 >= 0.0 : a2 <= 0.0) stpmx = 0.0;
+                                else if (dn ? a1 * stpmx < a2 : a1 * stpmx > a2) stpmx = ddiv(a2, a1);
                             }
                         }
                     }
