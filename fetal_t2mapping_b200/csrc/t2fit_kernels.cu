@@ -637,8 +637,12 @@ __device__ __noinline__ void dense_finish(const lb::LbConsts& c, const KernelIO&
     if (v.status != 0 && io.counts) atomicAdd(io.counts + v.status, 1ull);
 }
 
+// blocks per SM: 4 x 128 threads (128 registers) for the 3-parameter objectives; the 2-parameter fit measured + 15 % at 3 (168
+// registers, no spills: its echo loop is short, the spilled state weighs more) -- profiles/r02_notes.md section 10
+constexpr int dense_min_blocks(int obj) { return (obj == 0 && T2_LBD_MIN_BLOCKS == 4 && T2_LBD_THREADS == 128) ? 3 : T2_LBD_MIN_BLOCKS; }
+
 template <int OBJ>
-__global__ void __launch_bounds__(kLbdBlock, T2_LBD_MIN_BLOCKS) lbfgsb_dense_kernel(const __grid_constant__ lb::LbConsts c,
+__global__ void __launch_bounds__(kLbdBlock, dense_min_blocks(OBJ)) lbfgsb_dense_kernel(const __grid_constant__ lb::LbConsts c,
                                                                 const __grid_constant__ KernelIO io,
                                                                 unsigned long long* __restrict__ queue) {
     extern __shared__ __align__(16) unsigned char dense_smem[];

@@ -115,6 +115,15 @@ extern "C" int hostsim_lbfgsb_dense(const t2fit_problem* p, double* x, double* f
 
 extern "C" double hostsim_i0e(double x) { return lb::i0e(x); }
 
+// lb::EchoDiv (the dense kernel's per-echo quotient from one reciprocal per T2) on n operand pairs: q[i] = EchoDiv(b[i])(a[i])
+extern "C" void hostsim_echodiv(const double* a, const double* b, double* q, int64_t n, int te_safe) {
+    for (int64_t i = 0; i < n; ++i) {
+        lb::EchoDiv d;
+        d.set(b[i], te_safe != 0);
+        q[i] = d(a[i]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // cooperative (lane-group-per-voxel) form of the same solver on the lane emulator: G fibers per voxel, lanes scheduled
 // forwards (reverse = 0) or backwards (reverse = 1) between barriers

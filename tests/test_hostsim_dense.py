@@ -104,3 +104,26 @@ def test_dense_edge_cases(fit, prior):
     ok = keep & g["ref_success"] & g["converged"] & (g["ref_params"][:, 1] > 10.0)
     rel = np.abs(o["x"][ok, 1] - oc["x"][ok, 1]) / oc["x"][ok, 1]
     assert np.mean(rel <= 1e-3) >= 0.75 and rel.max() <= 5e-2
+
+
+def test_echo_quotient_from_one_reciprocal_is_the_ieee_division():
+    """lb::EchoDiv: a / t2 for many numerators and one denominator as q0 = RN(a y), q = RN(q0 + (a - t2 q0) y) with
+    y = RN(1 / t2) must be the correctly rounded quotient, bit for bit (the objective's exp(-2 TE / T2) argument), on the
+    operand ranges the fit sees, on mantissas of all ones / a single one, and must fall back to the division itself near the
+    ends of the exponent range.  (The 4e8-pair run quoted in DESIGN.md section 4 used the same recurrence in C.)"""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    n = 400_000
+    te = -2.0 * rng.integers(1, 4000, n) * 0.5
+    t2 = np.exp(rng.uniform(np.log(1e-3), np.log(1e4), n))
+    a = np.concatenate([te, -rng.uniform(10.0, 2000.0, n), -(1.0 + rng.random(n)), np.array([0.0, -0.0, -2.0, -1e-300, -1e300, -3.0])])
+    b = np.concatenate([t2, rng.uniform(10.0, 2000.0, n), np.nextafter(2.0, 0.0) - rng.integers(0, 4, n) * 2.0 ** -52,
+                        np.array([37.0, 37.0, 1e-310, 7.0, 1e-200, 1e250])])
+    q = np.empty_like(a)
+    L = hostsim.lib(strict=True)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)
+    L.hostsim_echodiv(vp(a), vp(b), vp(q), C.c_int64(a.size), C.c_int(1))
+    with np.errstate(all="ignore"):
+        want = a / b
+    assert np.array_equal(q, want), f"{np.count_nonzero(q != want)} of {a.size} quotients differ from a / b"
+    # (array_equal: a zero numerator gives +0.0 where the division gives -0.0 -- TE = 0; exp of either is 1)
