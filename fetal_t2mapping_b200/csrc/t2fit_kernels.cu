@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(kLbBlock, T2_LB_MIN_BLOCKS) lbfgsb_kernel(cons
 #define T2_LBD_SYNC 1
 #endif
 constexpr int kLbdBlock = T2_LBD_THREADS;
-constexpr size_t dense_smem_bytes(int n_par, int n_echo) { return (size_t)kLbdBlock * ((size_t)(n_par + 1) * 8 * sizeof(double) + (size_t)n_echo * sizeof(float)); }
+constexpr size_t dense_smem_bytes(int n_par, int n_echo) { return (size_t)kLbdBlock * (((size_t)(n_par + 1) * 8 + lb::kLsSlots) * sizeof(double) + (size_t)n_echo * sizeof(float)); }
 
 // Epilogue of the voxels that ended in this pass of the warp (`fin` lanes, usually 2-3 of 32): what lb_store does, with the
 // residual (compute_residuals, utils/t2map_utils.py:62-89: E double-precision exp / sqrt per voxel) evaluated BY THE WHOLE
@@ -650,12 +650,14 @@ __global__ void __launch_bounds__(kLbdBlock, dense_min_blocks(OBJ)) lbfgsb_dense
     using Run = lb::DenseRun<OBJ, lb::DenseStridedMem<kLbdBlock>>;
     const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
     const int E = c.n_echo;
-    float* const ys = reinterpret_cast<float*>(dense_smem + (size_t)(N + 1) * 8 * kLbdBlock * sizeof(double));   // [E][kLbdBlock]
+    double* const lsb = reinterpret_cast<double*>(dense_smem) + (size_t)(N + 1) * 8 * kLbdBlock;                  // [kLsSlots][kLbdBlock]
+    float* const ys = reinterpret_cast<float*>(lsb + (size_t)lb::kLsSlots * kLbdBlock);                          // [E][kLbdBlock]
     double pairs[lb::DenseSolver<N>::kPairDoubles];           // the correction pairs: the one dynamically indexed array, an object of its own
     Run run;
     run.m.acc_ = reinterpret_cast<double*>(dense_smem) + threadIdx.x;                                   // [(N + 1) * 8][kLbdBlock]
     run.m.y_ = ys + threadIdx.x;
     run.m.pairs_ = pairs;
+    run.m.ls_ = lsb + threadIdx.x;
     run.active = false;
     int64_t cur = -1, row = 0;
     bool exhausted = false, warp_done = false;

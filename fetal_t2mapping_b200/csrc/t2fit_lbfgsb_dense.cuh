@@ -29,7 +29,23 @@
 namespace t2fit {
 namespace lb {
 
-template <int N>
+// The bracket of the More'-Thuente search (10 doubles, touched only while a line search goes past its first trial point) has
+// a store of its own: members on the host; on the device a column of shared memory [slot][thread], so that 20 registers'
+// worth of cold state neither occupies registers during the echo loop nor comes back from local memory (L2 latency) when
+// dcsrch needs it.
+enum LsSlot : int { kGx, kGy, kFx, kFy, kStx, kSty, kStmin, kStmax, kWidth, kWidth1, kLsSlots };
+template <int STRIDE>
+struct LsStore {
+    double* p;
+    T2_HD double& operator[](int i) { return p[i * STRIDE]; }
+};
+template <>
+struct LsStore<0> {
+    double v[kLsSlots];
+    T2_HD double& operator[](int i) { return v[i]; }
+};
+
+template <int N, int LS_STRIDE = 0>
 struct DenseSolver {
     // problem
     double l[N], u[N];
@@ -62,7 +78,7 @@ struct DenseSolver {
     int iter, ifun, iback, nfgv;
     bool brackt;
     int stage;
-    double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
+    LsStore<LS_STRIDE> ls;      // gx, gy, fx, fy, stx, sty, stmin, stmax, width, width1 (finit = fold, ginit = gdold, gtest = 1e-3 gdold)
     int result;
 
     T2_HD void projgr() {
@@ -358,8 +374,10 @@ struct DenseSolver {
     // dcsrch after the first call: 0 = evaluate at the new stp, 1 = line search finished (CONVERGENCE or WARNING)
     T2_HD int dcsrch_next(double fv, double gv) {
         const double ls_gtol = 0.9, ls_xtol = 0.1, stpmin = 0.0, stpmax = stpmx;
+        const double finit = fold, ginit = gdold, gtest = 1e-3 * ginit;             // as set when the search started
         const double ftest = finit + stp * gtest;
         if (stage == 1 && fv <= ftest && gv >= 0.0) stage = 2;
+        double stmin = ls[kStmin], stmax = ls[kStmax];
         bool fin = false;
         if (brackt && (stp <= stmin || stp >= stmax)) fin = true;                 // rounding errors prevent progress
         if (brackt && stmax - stmin <= ls_xtol * stmax) fin = true;               // xtol test satisfied
@@ -367,6 +385,7 @@ struct DenseSolver {
         if (stp == stpmin && (fv > ftest || gv >= gtest)) fin = true;             // stp = stpmin
         if (fv <= ftest && fabs(gv) <= ls_gtol * (-ginit)) fin = true;            // strong Wolfe conditions hold
         if (fin) return 1;
+        double stx = ls[kStx], sty = ls[kSty], fx = ls[kFx], fy = ls[kFy], gx = ls[kGx], gy = ls[kGy];
         // the modified function of stage 1 (psi = f - gtest stp) or f itself: ONE call of the safeguarded step
         const bool mod = stage == 1 && fv <= fx && fv > ftest;
         const double sh = mod ? gtest : 0.0;
@@ -377,15 +396,18 @@ struct DenseSolver {
         fx = mod ? fxm + stx * gtest : fxm; fy = mod ? fym + sty * gtest : fym;
         gx = gxm + sh; gy = gym + sh;
         if (brackt) {
-            if (fabs(sty - stx) >= 0.66 * width1) stp = stx + 0.5 * (sty - stx);
-            width1 = width;
-            width = fabs(sty - stx);
+            const double width = ls[kWidth];
+            if (fabs(sty - stx) >= 0.66 * ls[kWidth1]) stp = stx + 0.5 * (sty - stx);
+            ls[kWidth1] = width;
+            ls[kWidth] = fabs(sty - stx);
         }
         if (brackt) { stmin = rmin(stx, sty); stmax = rmax(stx, sty); }
         else { stmin = stp + 1.1 * (stp - stx); stmax = stp + 4.0 * (stp - stx); }
         stp = rmax(stp, stpmin);
         stp = rmin(stp, stpmax);
         if ((brackt && (stp <= stmin || stp >= stmax)) || (brackt && stmax - stmin <= ls_xtol * stmax)) stp = stx;
+        ls[kStx] = stx; ls[kSty] = sty; ls[kFx] = fx; ls[kFy] = fy; ls[kGx] = gx; ls[kGy] = gy;
+        ls[kStmin] = stmin; ls[kStmax] = stmax;
         return 0;
     }
 
@@ -486,10 +508,10 @@ struct DenseSolver {
                 reset_memory();
                 continue;
             }
-            brackt = false; stage = 1; finit = f; ginit = gd; gtest = 1e-3 * ginit;
-            width = stpmx - 0.0; width1 = width * 2.0;
-            stx = 0.0; fx = finit; gx = ginit; sty = 0.0; fy = finit; gy = ginit;
-            stmin = 0.0; stmax = stp + 4.0 * stp;
+            brackt = false; stage = 1;                        // dcsrch, first call (finit = fold = f, ginit = gdold = gd)
+            ls[kWidth] = stpmx - 0.0; ls[kWidth1] = (stpmx - 0.0) * 2.0;
+            ls[kStx] = 0.0; ls[kFx] = f; ls[kGx] = gd; ls[kSty] = 0.0; ls[kFy] = f; ls[kGy] = gd;
+            ls[kStmin] = 0.0; ls[kStmax] = stp + 4.0 * stp;
             ifun = 1; ++nfgv; iback = 0;
             trial_point();
             return;
@@ -563,7 +585,9 @@ struct DenseLocalMem {
     float y_[kMaxEcho];
     double acc_[4 * 8];
     double pairs_[kM * 7];
+    static constexpr int kLsStride = 0;                      // the line-search bracket is a member of the solver
     T2_HD double* pairs() { return pairs_; }
+    T2_HD double* ls_column() { return nullptr; }
     T2_HD float& y(int e) { return y_[e]; }
     T2_HD const float& y(int e) const { return y_[e]; }
     T2_HD double& acc(int p, int j) { return acc_[p * 8 + j]; }
@@ -574,7 +598,10 @@ struct DenseStridedMem {                                     // y_ / acc_ point 
     float* y_;
     double* acc_;
     double* pairs_;                                          // DenseSolver::kPairDoubles doubles of the thread's own (local memory)
+    double* ls_;                                             // [kLsSlots][STRIDE]: this thread's column of the line-search bracket
+    static constexpr int kLsStride = STRIDE;
     T2_HD double* pairs() { return pairs_; }
+    T2_HD double* ls_column() { return ls_; }
     T2_HD float& y(int e) { return y_[e * STRIDE]; }
     T2_HD const float& y(int e) const { return y_[e * STRIDE]; }
     T2_HD double& acc(int p, int j) { return acc_[(p * 8 + j) * STRIDE]; }
@@ -617,7 +644,7 @@ struct PointPre {
 template <int OBJ, class Mem = DenseLocalMem>
 struct DenseRun {
     static constexpr int N = (OBJ == 0) ? 2 : 3;
-    DenseSolver<N> s;
+    DenseSolver<N, Mem::kLsStride> s;
     Mem m;
     double xprev[N];
     float* trace_f;
@@ -651,6 +678,7 @@ struct DenseRun {
             T2_ROLLED for (int e = 0; e < E; ++e) if (!(m.y(e) > 0.0f)) status = kNonFinite;
         }
         s.pw = m.pairs();
+        if constexpr (Mem::kLsStride != 0) s.ls.p = m.ls_column();
         s.setup(c.x0, lo, hi, c.ftol, c.pgtol, c.maxls);
         nit = 0; nfev = 0; tl = 0;
         have_prev = false; started = false;
@@ -787,9 +815,11 @@ struct DenseRun {
                 if (trace_step) trace_step[tl] = (float)st;
             }
             ++tl;
+            if (trace_cap > 0) {                              // (the previous iterate is the trace's step size only)
 #pragma unroll
-            for (int i = 0; i < N; ++i) xprev[i] = s.x[i];
-            have_prev = true;
+                for (int i = 0; i < N; ++i) xprev[i] = s.x[i];
+                have_prev = true;
+            }
             if (nit >= c.maxiter) s.result = kMaxIter;
             else if (nfev > c.maxfun) s.result = kMaxFun;
             else s.continue_after_iterate();
