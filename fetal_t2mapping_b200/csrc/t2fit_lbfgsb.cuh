@@ -29,6 +29,7 @@
 #pragma once
 #include "t2fit_core.cuh"
 #include "t2fit_i0e_coeffs.h"
+#include <cstring>
 
 // the optimiser core is compiled once per parameter count (not once per echo count): out-of-line on the device
 #if T2_DEVICE_BUILD
@@ -200,7 +201,73 @@ struct EchoDiv {
 #define T2_DENSE_CALLS 0
 #endif
 T2_NI double dexp(double a) { return exp(a); }
-T2_HD double loop_exp(double a) { return (T2_DENSE_CALLS & 1) ? dexp(a) : exp(a); }
+
+// exp(a) for the arguments of the echo loop (a = -TE / T2 or -2 TE / T2, so a <= 0 and far from overflow), T2_DENSE_EXP = 1:
+//     k = rint(a log2 e),  r = a - k ln 2 (two FMAs, ln 2 in two parts),  exp(r) by its Taylor polynomial of degree 13
+//     (|r| <= 0.347: truncation 4e-18 relative),  2^k by the exponent field
+// -- the textbook scheme the CUDA library follows as well (its polynomial is a degree-11 minimax), error <= 1 ulp like the
+// library's (tests/test_hostsim_dense.py measures it against mpmath-grade references on the host build of this function).
+// The idea: the library's exp, inlined twice per echo, re-materialises its 11 coefficients through uniform-register moves on
+// every call (44 UMOV of the ~250 instructions of one echo); here they come from the constant bank.  MEASURED SLOWER (same
+// box, c3 9.95e7 -> 9.3e7, c5 1.30e8 -> 1.26e8 fits/s: the compiler fetches the coefficients with LDCU.128 / LDC.64 in front of
+// every polynomial, whose latency the four chains do not hide, and the polynomial is two FMAs longer), so it is OFF by
+// default and kept as the record of the experiment.  Anything outside (-700, 700) goes to the library as a call.
+#ifndef T2_DENSE_EXP
+#define T2_DENSE_EXP 0
+#endif
+#if T2_DEVICE_BUILD
+__device__ __constant__ double kExpTaylor[12] = {   // 1/13! ... 1/2!
+    1.60590438368216133409e-10, 2.08767569878681001866e-09, 2.50521083854417202239e-08, 2.75573192239858882758e-07,
+    2.75573192239858925110e-06, 2.48015873015873015658e-05, 1.98412698412698412526e-04, 1.38888888888888894189e-03,
+    8.33333333333333321769e-03, 4.16666666666666643537e-02, 1.66666666666666657415e-01, 5.00000000000000000000e-01};
+#else
+static const double kExpTaylor[12] = {
+    1.60590438368216133409e-10, 2.08767569878681001866e-09, 2.50521083854417202239e-08, 2.75573192239858882758e-07,
+    2.75573192239858925110e-06, 2.48015873015873015658e-05, 1.98412698412698412526e-04, 1.38888888888888894189e-03,
+    8.33333333333333321769e-03, 4.16666666666666643537e-02, 1.66666666666666657415e-01, 5.00000000000000000000e-01};
+#endif
+T2_HD double exp_echo(double a) {
+    if (!(fabs(a) < 700.0)) return dexp(a);
+    const double kMagic = 6755399441055744.0;                    // 1.5 * 2^52: adding it rounds to an integer (to nearest even)
+#if T2_DEVICE_BUILD
+    const double t = __fma_rn(a, 1.44269504088896338700e+00, kMagic);
+    const int k = __double2loint(t);
+    const double kd = __dsub_rn(t, kMagic);
+    double r = __fma_rn(kd, -6.93147180559945286227e-01, a);
+    r = __fma_rn(kd, -2.31904681384629955842e-17, r);
+    double p = kExpTaylor[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) p = __fma_rn(p, r, kExpTaylor[i]);
+    p = __fma_rn(p, r, 1.0);
+    p = __fma_rn(p, r, 1.0);
+    return __dmul_rn(p, __hiloint2double((k << 20) + 0x3ff00000, 0));
+#else
+    volatile double tv = fma(a, 1.44269504088896338700e+00, kMagic);
+    const double t = tv;
+    long long bits;
+    memcpy(&bits, &t, 8);
+    const int k = (int)(bits & 0xffffffffll);
+    volatile double kdv = t - kMagic;
+    const double kd = kdv;
+    double r = fma(kd, -6.93147180559945286227e-01, a);
+    r = fma(kd, -2.31904681384629955842e-17, r);
+    double p = kExpTaylor[0];
+    for (int i = 1; i < 12; ++i) p = fma(p, r, kExpTaylor[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const long long sb = ((long long)(k + 1023)) << 52;
+    double sc;
+    memcpy(&sc, &sb, 8);
+    return mul(p, sc);
+#endif
+}
+// the host build keeps libm's exp in the solver itself (the CPU parity tests are pinned to it); exp_echo is exported for its
+// own accuracy test
+#if T2_DEVICE_BUILD
+T2_HD double loop_exp(double a) { return (T2_DENSE_CALLS & 1) ? dexp(a) : (T2_DENSE_EXP ? exp_echo(a) : exp(a)); }
+#else
+T2_HD double loop_exp(double a) { return exp(a); }
+#endif
 T2_HD double loop_sqrt(double a) { return (T2_DENSE_CALLS & 2) ? dsqrt(a) : sqrt(a); }
 
 template <int OBJ>

@@ -115,6 +115,11 @@ extern "C" int hostsim_lbfgsb_dense(const t2fit_problem* p, double* x, double* f
 
 extern "C" double hostsim_i0e(double x) { return lb::i0e(x); }
 
+// lb::exp_echo (the dense kernel's exponential) on n arguments
+extern "C" void hostsim_exp_echo(const double* a, double* out, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) out[i] = lb::exp_echo(a[i]);
+}
+
 // lb::EchoDiv (the dense kernel's per-echo quotient from one reciprocal per T2) on n operand pairs: q[i] = EchoDiv(b[i])(a[i])
 extern "C" void hostsim_echodiv(const double* a, const double* b, double* q, int64_t n, int te_safe) {
     for (int64_t i = 0; i < n; ++i) {

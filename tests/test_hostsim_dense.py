@@ -127,3 +127,19 @@ def test_echo_quotient_from_one_reciprocal_is_the_ieee_division():
         want = a / b
     assert np.array_equal(q, want), f"{np.count_nonzero(q != want)} of {a.size} quotients differ from a / b"
     # (array_equal: a zero numerator gives +0.0 where the division gives -0.0 -- TE = 0; exp of either is 1)
+
+
+def test_constant_bank_exponential_is_within_one_ulp():
+    """lb::exp_echo (the T2_DENSE_EXP experiment: Taylor degree 13 after the two-part ln 2 reduction; off by default, measured
+    slower than the library's exp on the GPU) against an 80-bit reference on the arguments the echo loop produces."""
+    import ctypes as C
+    rng = np.random.default_rng(1)
+    a = np.concatenate([-rng.uniform(0, 700, 200000), -np.exp(rng.uniform(np.log(1e-12), np.log(700), 200000)),
+                        np.array([0.0, -0.0, -699.9, -700.0, -745.0, -1e9, 3.0, -np.inf])])
+    out = np.empty_like(a)
+    hostsim.lib(strict=True).hostsim_exp_echo(a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_int64(a.size))
+    fin = np.isfinite(a) & (a > -700)
+    ref = np.exp(a[fin].astype(np.longdouble))
+    err = np.abs((out[fin].astype(np.longdouble) - ref) / np.spacing(np.exp(a[fin])))
+    assert float(err.max()) <= 1.0
+    assert np.array_equal(out[~fin], np.exp(a[~fin]))                    # outside (-700, 700): the library's own
