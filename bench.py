@@ -528,6 +528,26 @@ def bench_volume(args, cfg):
         if int(okt[0]) == 0:
             fa = None
 
+        # multicast buffers (NVSwitch replicates one store into every rank's buffer): checked against the owners' slabs BEFORE
+        # anything is timed; any difference on any rank -> the unicast CUDA-IPC form on every rank
+        fused_note = None
+        if fa is not None and fa.multicast:
+            bounds_f = [(r * L, (r + 1) * L) for r in range(c.world)]
+            ok_m = 1
+            for _ in range(3):                                    # both buffer sets
+                rf = fa.result(fa.submit(rows_d, te, fp, prior=False, norm=False, solver=solver))
+                torch.cuda.synchronize()
+                tab = slab_hashes(torch, [rf[n][c.rank * L:(c.rank + 1) * L] for n in names], [(0, m_s)])[0]
+                tabs = torch.zeros((c.world, len(names)), dtype=torch.int64, device=c.dev)
+                c.dist.all_gather_into_tensor(tabs, tab)
+                ok_m &= int(torch.equal(tabs, slab_hashes(torch, [rf[n] for n in names], bounds_f)))
+            okt = torch.tensor([ok_m], device=c.dev, dtype=torch.int32)
+            c.dist.all_reduce(okt, op=c.dist.ReduceOp.MIN)
+            if int(okt[0]) == 0:
+                fused_note = "multicast stores did not reproduce the owners' slabs on this node: unicast peer stores used"
+                fa.close()
+                fa = D.FusedAllGather(n_job, fit, multicast="off")
+
         def fused_pass():
             fa.submit(rows_d, te, fp, prior=False, norm=False, solver=solver)
 
@@ -607,8 +627,9 @@ def bench_volume(args, cfg):
         bytes_in = sum((c.world - 1) * L * (1 if n == "status" else 4) for n in names)
         extra["sharded"] = {"form": "fused all-gather" if fa is not None else "NCCL all-gather, pipelined",
                             "op": ("fit of the rank's slab; the kernel epilogue stores the compact results (" + ", ".join(names) + "; status as uint8) into "
-                                   "its own buffer and, over NVLink, into every peer's buffer (CUDA-IPC peer stores); a one-element NCCL all-reduce "
-                                   "ordered after the kernels is the barrier (distributed.FusedAllGather)") if fa is not None else
+                                   "its own buffer and, over NVLink, into every peer's buffer (" + ("float fields: ONE store per value to the buffers' NVSwitch "
+                                   "multicast address, replicated by the switch; status: unicast peer stores" if fa.multicast else "CUDA-IPC peer stores")
+                                   + "); a one-element NCCL all-reduce ordered after the kernels is the barrier (distributed.FusedAllGather)") if fa is not None else
                                   "fit + in-place NCCL all_gather_into_tensor per field, two buffer sets (distributed.SlabPipeline)",
                             "ms_per_pass": pass_ms, "fit_only_ms": fit_ms, "gather_bytes_received_per_rank": int(bytes_in),
                             "gather_gbs_received_per_rank": bytes_in / max(pass_ms, 1e-9) / 1e6,
@@ -635,6 +656,10 @@ def bench_volume(args, cfg):
                                            "what": "the same fused all-gather moving only the PARAMETER maps (T2 and S0, 8 B per voxel: the 'final "
                                                    "gather of the parameter maps' of BASELINE.json read literally); res and status stay with the slab's owner"}
             fa2.close()
+        if fa is not None:
+            extra["sharded"]["multicast"] = bool(fa.multicast)
+            if fused_note:
+                extra["sharded"]["multicast_note"] = fused_note
         if fa is None:
             extra["sharded"]["fused_unavailable"] = fused_err if not ok_f else "CUDA IPC failed on another rank"
         extra["replicas"] = {"value": sum_over_ranks(c, m) / (rep_ms * 1e-3), "ms_per_pass": rep_ms,

@@ -26,6 +26,8 @@ gather / error logic is testable with ``gloo`` on CPU.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 __all__ = ["slab_bounds", "slab_length", "fit_voxels_sharded", "fit_slab_sharded", "gather_slabs", "gather_fields",
@@ -344,7 +346,7 @@ class FusedAllGather:
     ``depth`` buffer sets (default 2) let a consumer read job i while job i+1 is being written.  ``submit(rows, ...)`` ->
     slot; ``result(slot)`` -> full-length tensors (views of this rank's buffer, valid until the slot is reused)."""
 
-    def __init__(self, n_fit, fit, *, depth=2, group=None, device=None, gather=None):
+    def __init__(self, n_fit, fit, *, depth=2, group=None, device=None, gather=None, multicast=None):
         """``gather``: the fields every rank receives from every peer (default: all of them).  ``("t2", "k")`` is the
         literal "final gather of the parameter maps" of BASELINE.json (T2 and S0): res / sigma / status of a slab then stay
         with its owner (``result()`` returns the owner's slab of those, zeros elsewhere) and 8 instead of 13-17 bytes per
@@ -372,25 +374,89 @@ class FusedAllGather:
             o += tot * (1 if n == "status" else 4)
         self.nbytes = (o + 255) // 256 * 256
         self.sets = []
-        for _ in range(max(1, depth)):
-            ptr, handle = C.c_void_p(), C.create_string_buffer(64)
-            _abi.check(self.lib, self.lib.t2fit_shared_alloc(self.nbytes, C.byref(ptr), handle), "t2fit_shared_alloc")
-            handles = [None] * self.world
-            dist.all_gather_object(handles, handle.raw, group=group)
-            peers = {}
-            for r in range(self.world):
-                if r != self.rank:
-                    pp = C.c_void_p()
-                    _abi.check(self.lib, self.lib.t2fit_shared_open(handles[r], C.byref(pp)), "t2fit_shared_open")
-                    peers[r] = pp
-            raw = torch.as_tensor(_DeviceBytes(ptr.value, self.nbytes), device=self.dev)
-            raw.zero_()
-            self.sets.append({"ptr": ptr, "peers": peers, "raw": raw, "counts": torch.zeros(4, dtype=torch.int64, device=self.dev),
-                              "call": None})
+        want_mc = {"auto": self.world > 2, "on": True, "off": False, "1": True, "0": False}.get(
+            str(multicast if multicast is not None else os.environ.get("T2FIT_MULTICAST", "auto")).lower(), False)
+        self.multicast = False
+        if want_mc:                                         # all slots or none: the two kinds of buffer sets are never mixed
+            for _ in range(max(1, depth)):
+                st = self._alloc_multicast(group)
+                if st is None:
+                    self.sets = []
+                    break
+                self.sets.append(st)
+            self.multicast = bool(self.sets)
+        while len(self.sets) < max(1, depth):
+            self.sets.append(self._alloc_ipc(group))
+        for st in self.sets:
+            st["raw"].zero_()
+            st.update(counts=torch.zeros(4, dtype=torch.int64, device=self.dev), call=None)
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
         torch.cuda.synchronize()
         dist.barrier(group=group)
         self.next = 0
+
+    def _alloc_ipc(self, group):
+        """One buffer set from the library's own allocator, mapped into every peer through CUDA-IPC (t2fit_shared_*)."""
+        C, _abi, torch, dist = self.C, self._abi, self.torch, self.dist
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        _abi.check(self.lib, self.lib.t2fit_shared_alloc(self.nbytes, C.byref(ptr), handle), "t2fit_shared_alloc")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        peers = {}
+        for r in range(self.world):
+            if r != self.rank:
+                pp = C.c_void_p()
+                _abi.check(self.lib, self.lib.t2fit_shared_open(handles[r], C.byref(pp)), "t2fit_shared_open")
+                peers[r] = pp
+        raw = torch.as_tensor(_DeviceBytes(ptr.value, self.nbytes), device=self.dev)
+        return {"ptr": ptr, "peers": peers, "raw": raw, "mc": 0, "symm": None}
+
+    def _all_ok(self, ok, group):
+        """True on every rank only if ``ok`` is true on every rank."""
+        f = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.dev)
+        self.dist.all_reduce(f, op=self.dist.ReduceOp.MIN, group=group)
+        return bool(int(f.item()))
+
+    def _alloc_multicast(self, group):
+        """One buffer set in torch's symmetric memory (plumbing: CUDA VMM allocation, handle exchange, NVSwitch multicast
+        binding) when the node's fabric offers a MULTICAST address for it: a store to that address is replicated by the switch
+        into the same offset of every rank's buffer, so a slab leaves its GPU once instead of (world - 1) times.  Every step is
+        agreed across the ranks; None (on all of them) = use the CUDA-IPC peer mappings.  The address is probed before use:
+        every rank writes its rank number through it and all ranks must find all numbers in their own buffer."""
+        torch, dist = self.torch, self.dist
+        g = group if group is not None else dist.group.WORLD
+        try:
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(self.nbytes, dtype=torch.uint8, device=self.dev)
+        except Exception:                                   # noqa: BLE001
+            t = None
+        if not self._all_ok(t is not None, group):
+            return None
+        try:
+            hdl = symm.rendezvous(t, g)
+            mc = int(hdl.multicast_ptr or 0)
+            ptrs = [int(q) for q in hdl.buffer_ptrs]
+        except Exception:                                   # noqa: BLE001
+            hdl, mc, ptrs = None, 0, []
+        if not self._all_ok(mc != 0 and len(ptrs) == self.world and ptrs[self.rank] == t.data_ptr(), group):
+            return None
+        # probe: 256 bytes per rank at the start of the buffer
+        t[:256 * self.world].zero_()
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        torch.as_tensor(_DeviceBytes(mc + 256 * self.rank, 256), device=self.dev).fill_(self.rank + 1)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        seen = t[:256 * self.world].view(self.world, 256)
+        want = torch.arange(1, self.world + 1, dtype=torch.uint8, device=self.dev)[:, None].expand(self.world, 256)
+        ok = bool(torch.equal(seen, want))
+        if not self._all_ok(ok, group):
+            return None
+        class _P:                                           # same attribute as the ctypes pointers of the IPC form
+            def __init__(self, v):
+                self.value = v
+        return {"ptr": _P(ptrs[self.rank]), "peers": {r: _P(ptrs[r]) for r in range(self.world) if r != self.rank}, "raw": t,
+                "mc": mc, "symm": hdl}
 
     def _build(self, st, slab_rows, TEeffs, fit_params, prior, norm, solver):
         """The t2fit_run arguments of a slot (built once per slot and input tensor; a pass then is two C calls)."""
@@ -413,6 +479,10 @@ class FusedAllGather:
             pb = st["peers"][r].value
             for n, arr in (("t2", o.dup_t2), ("k", o.dup_k), ("res", o.dup_res), ("status", o.dup_status), ("sigma", o.dup_sigma)):
                 arr[j] = at(pb, n) if (n in self.off and n in sel) else None
+                if st["mc"] and n != "status":
+                    # float fields through the multicast address: ONE store per value (destination 0), replicated by the
+                    # switch into every rank's buffer; status (bytes; multimem stores are >= 32 bits wide) stays unicast
+                    arr[j] = at(st["mc"], n) if (j == 0 and n in self.off and n in sel) else None
         return {"p": p, "o": o, "keep": (keep, slab_rows), "key": (slab_rows.data_ptr(), slab_rows.shape[0], id(fit_params), prior, norm, solver)}
 
     def submit(self, slab_rows, TEeffs, fit_params, prior=True, norm=False, *, solver="auto"):
@@ -457,10 +527,13 @@ class FusedAllGather:
         self.torch.cuda.synchronize()
         self.dist.barrier(group=self.group)
         for st in self.sets:
-            for pp in st["peers"].values():
-                self.lib.t2fit_shared_close(pp)
+            if not st["mc"]:
+                for pp in st["peers"].values():
+                    self.lib.t2fit_shared_close(pp)
             st["raw"] = None
         self.dist.barrier(group=self.group)
         for st in self.sets:
-            self.lib.t2fit_shared_free(st["ptr"])
+            if not st["mc"]:
+                self.lib.t2fit_shared_free(st["ptr"])
+            st["symm"] = None
         self.sets = []

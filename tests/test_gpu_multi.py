@@ -79,6 +79,19 @@ def _worker(rank, world, port, tmp, fit):
     torch.cuda.synchronize()
     assert torch.equal(fused_ag.result(s2)["res"], out["res"])
     fused_ag.close()
+    # the same through the NVSwitch multicast address of the buffers (one store per value, replicated by the switch); on a
+    # node without multicast the constructor agrees on the unicast form on every rank and the check is the one above again
+    fused_mc = D.FusedAllGather(idx.numel(), fit, multicast="on")
+    slots_mc = [fused_mc.submit(r_, te, fp, prior=False) for r_ in (rows, rows2, rows)]
+    rm2, rm1 = fused_mc.result(slots_mc[2], check=True), fused_mc.result(slots_mc[1])
+    torch.cuda.synchronize()
+    for name in ("t2", "k", "res", "status") + (() if fit == "gaussian" else ("sigma",)):
+        assert torch.equal(rm2[name], out[name]), ("multicast", name)
+    assert torch.equal(rm1["t2"], single_mid.t2) and torch.equal(rm1["k"], single_mid.k)
+    print(f"rank {rank}: fused all-gather multicast = {fused_mc.multicast}", flush=True)
+    with open(os.path.join(tmp, f"mc_{rank}.txt"), "w") as fh:
+        fh.write(str(int(fused_mc.multicast)))
+    fused_mc.close()
     again = D.fit_voxels_sharded(flat, idx, te, fit, fp, prior=False)      # and the next clean job is unaffected
     assert torch.equal(again["t2"], out["t2"])
     np.save(os.path.join(tmp, f"t2_{rank}.npy"), out["t2"].cpu().numpy())
