@@ -343,6 +343,11 @@ class FusedAllGather:
     ~15 us at 2 GPUs where NCCL's all-gather of the same 21 MB costs 77 us (profiles/r02_notes.md).  Every rank still
     RECEIVES (world - 1) slabs per job: at 8 GPUs the NVLink ingest (~150 MB per rank for c2-sized slabs) bounds the pass.
 
+    ``multicast="on"``: the buffers live in torch symmetric memory and the float fields are stored ONCE per value to the
+    buffers' NVSwitch multicast address (the switch replicates the store into every rank's buffer; a plain ``st.global`` is
+    what ``multimem.st.weak`` assembles to on sm_100a).  Bit-identical, but measured slower than the unicast stores at 4 GPUs,
+    hence off by default.
+
     ``depth`` buffer sets (default 2) let a consumer read job i while job i+1 is being written.  ``submit(rows, ...)`` ->
     slot; ``result(slot)`` -> full-length tensors (views of this rank's buffer, valid until the slot is reused)."""
 
@@ -374,8 +379,10 @@ class FusedAllGather:
             o += tot * (1 if n == "status" else 4)
         self.nbytes = (o + 255) // 256 * 256
         self.sets = []
-        want_mc = {"auto": self.world > 2, "on": True, "off": False, "1": True, "0": False}.get(
-            str(multicast if multicast is not None else os.environ.get("T2FIT_MULTICAST", "auto")).lower(), False)
+        # opt-in (multicast="on" or T2FIT_MULTICAST=on): measured SLOWER than the unicast peer stores on 4 x B200 (c2-sized slabs,
+        # same box: 142.8 vs 122.6 us per pass, 442 vs 515 GB/s received per rank -- profiles/r02_notes.md section 11)
+        want_mc = {"on": True, "1": True}.get(
+            str(multicast if multicast is not None else os.environ.get("T2FIT_MULTICAST", "off")).lower(), False)
         self.multicast = False
         if want_mc:                                         # all slots or none: the two kinds of buffer sets are never mixed
             for _ in range(max(1, depth)):
