@@ -87,3 +87,19 @@ def test_converged_classification_is_reproducible():
                                 g["ref_success"][sel])
     assert np.array_equal(conv, g["converged"][sel])
     np.testing.assert_allclose(tp, g["tight_params"][sel], rtol=1e-9)
+
+
+def test_rician_promotion_probe_is_pinned_to_the_fixture():
+    """tests/golden/promotion_probe.py: its restatement of rician_obj under NumPy-2 promotion reproduces the fixture (= the
+    unmodified reference run here) exactly; the NumPy-1.26 emulation of the one float32 term is then a statement about the
+    pinned environment: same success set, a different trajectory on a large share of the voxels."""
+    import importlib.util
+    import os
+    from tests.conftest import ROOT
+    spec = importlib.util.spec_from_file_location("promotion_probe", os.path.join(ROOT, "tests", "golden", "promotion_probe.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    st = mod.main(limit=40, names=("c3_rician_prior",))["c3_rician_prior"]
+    assert st["pinned_max_rel"] == 0.0
+    assert st["success_sets_equal"]
+    assert st["t2_within_1e-3"] < 0.9          # float32 rounding steps / 1e-8 in the sigma gradient: not the same fit
